@@ -1,0 +1,82 @@
+/* nefii_b200 -- C ABI of the B200-native NeFII rendering hot path.
+ *
+ * The reference (FuxiComputerVision/Nefii) has no native code and no FFI: its seam is Python
+ * (SURVEY.md section 8b).  Every entry point below replaces a reference *function* on the hot path; the
+ * reference file:line it stands in for is cited next to it.  INTEGRATION.md shows the ctypes stub
+ * a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless marked `host`;
+ *     all tensors are contiguous row-major float32 unless noted; masks are uint8 (0/1).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); no call synchronises the
+ *     host unless stated.
+ *   - the caller owns every buffer; the library keeps nothing past the call except inside a
+ *     handle created by nefii_create (workspace + TMA descriptors), released by nefii_destroy.
+ *   - return value: 0 ok, <0 error (-1 bad argument, -2 CUDA error, -3 bad state); the text is
+ *     available from nefii_last_error() (thread-local).  Nothing throws, nothing exits.
+ */
+#ifndef NEFII_B200_H_
+#define NEFII_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* nefii_last_error(void);
+/* ABI version of this header (bumped on any signature change) */
+int nefii_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * SG shading -- replaces render_with_sg, code/model/sg_render.py:164-295 (forward).
+ *   lgt_sgs [M,7] raw parameter (axis, sharpness, rgb amplitude; abs()/normalise applied inside)
+ *   specular [K,3], roughness [K,1], albedo/normal/view [N,3] (unit normals / view dirs),
+ *   blending [N,K] or NULL.  Outputs [N,3]: sg_rgb, sg_specular_rgb, sg_diffuse_rgb.
+ * ------------------------------------------------------------------------------------------- */
+int nefii_sg_render_fwd(void* stream, int n_rays, int n_sg, int n_mat,
+                        const float* lgt_sgs, const float* specular, const float* roughness,
+                        const float* albedo, const float* normal, const float* view,
+                        const float* blending,
+                        float* out_rgb, float* out_specular, float* out_diffuse);
+
+/* Environment radiance along miss rays -- replaces IDRNetwork.get_background_rgb (light_type 'sg'),
+ * code/model/implicit_differentiable_renderer.py:646-663 + sg_fn path_tracing_render.py:404-413. */
+int nefii_background_sg_fwd(void* stream, int n_rays, int n_sg,
+                            const float* lgt_sgs, const float* dirs, float* out_rgb);
+
+/* ---------------------------------------------------------------------------------------------
+ * MLP layer GEMM on tcgen05 -- the building block that replaces nn.Linear (+ Softplus/ReLU/ELU) in
+ * ImplicitNetwork.forward/.gradient (implicit_differentiable_renderer.py:85-123),
+ * RenderingNetwork.forward (:196-241) and EnvmapMaterialNetwork.forward (sg_envmap_material.py:357-425).
+ * fp32 values travel as two bf16 planes (hi, lo); see csrc/mlp_gemm.cu.
+ * The struct is a host-side argument block (all pointers inside are device pointers).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct nefii_gemm_desc {
+  const void* a_hi; const void* a_lo; int32_t a_ld; int32_t rows_cap;   /* activations [rows_cap, a_ld] bf16 planes */
+  const void* b_hi; const void* b_lo; int32_t b_ld; int32_t n_pad;      /* weights [n_pad, b_ld] bf16 planes, n_pad % 256 == 0 */
+  int32_t k_pad;                  /* reduction length, multiple of 64 */
+  const int32_t* count;           /* device int: valid rows (NULL = rows_cap) */
+  int32_t mode;                   /* 0 forward (bias + act), 1 backward (x act'(saved forward output)) */
+  int32_t act;                    /* 0 none, 1 softplus(beta=100), 2 relu, 3 elu */
+  int32_t n_valid;                /* real output columns */
+  const float* bias;              /* [n_valid] or NULL */
+  float out_scale;
+  void* dst_hi; void* dst_lo; int32_t dst_ld; int32_t dst_col0; int32_t dst_ncols;   /* output planes (may be NULL) */
+  float* dst_f32; int32_t f32_ld; int32_t f32_begin; int32_t f32_end;                /* optional fp32 output columns */
+  const float* w_last; const float* b_last; int32_t n_last; int32_t w_last_ld; float* dst_last; /* fused tiny output layer */
+  void* seed_hi; void* seed_lo; int32_t seed_ld;                                     /* input-gradient seed planes */
+  const void* sav_hi; const void* sav_lo; int32_t sav_ld; int32_t sav_ncols; float sav_scale; /* backward: saved activations */
+} nefii_gemm_desc;
+
+int nefii_gemm_split_bf16(void* stream, const nefii_gemm_desc* desc /* host */);
+
+/* fp32 [rows, cols] (row stride ld_src) -> zero-padded bf16 hi/lo planes [rows_pad, cols_pad];
+ * transpose != 0 writes the transpose.  Used to pack weights (and test inputs). */
+int nefii_split_to_planes(void* stream, const float* src, int rows, int cols, int ld_src, int transpose, float scale,
+                          void* dst_hi, void* dst_lo, int rows_pad, int cols_pad);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEFII_B200_H_ */

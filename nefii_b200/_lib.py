@@ -1,0 +1,80 @@
+"""ctypes binding of libnefii_b200.so (the C ABI declared in include/nefii_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import fails loudly, and every
+call on a non-CUDA tensor raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnefii_b200.so")
+
+c_void_p, c_int, c_float, c_longlong = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+
+# symbol -> argtypes; kept in sync with include/nefii_b200.h (tests/test_abi.py checks both ways)
+SIGNATURES = {
+    "nefii_abi_version": [],
+    "nefii_sg_render_fwd": [c_void_p, c_int, c_int, c_int] + [c_void_p] * 10,
+    "nefii_background_sg_fwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "nefii_gemm_split_bf16": [c_void_p, c_void_p],
+    "nefii_split_to_planes": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int],
+}
+
+
+class NefiiError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "nefii_b200: %s not found -- build it with `python -m nefii_b200.build` "
+            "(there is no CPU / PyTorch fallback path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.nefii_last_error.restype = ctypes.c_char_p
+    lib.nefii_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    return lib
+
+
+_lib = _load()
+
+
+def raw():
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise NefiiError("nefii_b200 error %d: %s" % (rc, _lib.nefii_last_error().decode("utf-8", "replace")))
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def dptr(t, dtype=torch.float32, allow_none=False):
+    """Device pointer of a contiguous CUDA tensor (raises instead of silently copying)."""
+    if t is None:
+        if allow_none:
+            return None
+        raise NefiiError("nefii_b200: required tensor is None")
+    if not t.is_cuda:
+        raise NefiiError("nefii_b200: expected a CUDA tensor (no CPU path exists)")
+    if t.dtype != dtype:
+        raise NefiiError("nefii_b200: expected dtype %s, got %s" % (dtype, t.dtype))
+    if not t.is_contiguous():
+        raise NefiiError("nefii_b200: expected a contiguous tensor")
+    return c_void_p(t.data_ptr())
+
+
+def f32c(t):
+    """float32 contiguous view/copy of a CUDA tensor (expanded views are materialised)."""
+    if not t.is_cuda:
+        raise NefiiError("nefii_b200: expected a CUDA tensor (no CPU path exists)")
+    return t.detach().to(torch.float32).contiguous()

@@ -1,0 +1,68 @@
+// extern "C" surface of libnefii_b200.so -- see include/nefii_b200.h for the contract.
+#include "common.cuh"
+#include "../../include/nefii_b200.h"
+#include "mlp_gemm.cuh"
+
+namespace nefii {
+
+char* error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sg_render_fwd(cudaStream_t, int, int, int, const float*, const float*, const float*, const float*, const float*,
+                  const float*, const float*, float*, float*, float*);
+int background_sg_fwd(cudaStream_t, int, int, const float*, const float*, float*);
+
+}  // namespace nefii
+
+extern "C" {
+
+const char* nefii_last_error(void) { return nefii::error_buffer(); }
+int nefii_abi_version(void) { return 1; }
+
+int nefii_sg_render_fwd(void* stream, int n_rays, int n_sg, int n_mat, const float* lgt_sgs, const float* specular,
+                        const float* roughness, const float* albedo, const float* normal, const float* view,
+                        const float* blending, float* out_rgb, float* out_specular, float* out_diffuse) {
+  return nefii::sg_render_fwd((cudaStream_t)stream, n_rays, n_sg, n_mat, lgt_sgs, specular, roughness, albedo, normal,
+                              view, blending, out_rgb, out_specular, out_diffuse);
+}
+
+int nefii_background_sg_fwd(void* stream, int n_rays, int n_sg, const float* lgt_sgs, const float* dirs,
+                            float* out_rgb) {
+  return nefii::background_sg_fwd((cudaStream_t)stream, n_rays, n_sg, lgt_sgs, dirs, out_rgb);
+}
+
+int nefii_gemm_split_bf16(void* stream, const nefii_gemm_desc* d) {
+  if (!d) return nefii::set_error(NEFII_ERR_ARG, "nefii_gemm_split_bf16: null descriptor");
+  nefii::GemmProblem p;
+  p.a_hi = (const __nv_bfloat16*)d->a_hi; p.a_lo = (const __nv_bfloat16*)d->a_lo; p.a_ld = d->a_ld; p.rows_cap = d->rows_cap;
+  p.b_hi = (const __nv_bfloat16*)d->b_hi; p.b_lo = (const __nv_bfloat16*)d->b_lo; p.b_ld = d->b_ld; p.n_pad = d->n_pad;
+  p.k_pad = d->k_pad; p.count = d->count;
+  nefii::GemmEpilogue& e = p.epi;
+  e.mode = d->mode; e.act = d->act; e.n_valid = d->n_valid; e.bias = d->bias; e.out_scale = d->out_scale;
+  e.dst.hi = (__nv_bfloat16*)d->dst_hi; e.dst.lo = (__nv_bfloat16*)d->dst_lo; e.dst.ld = d->dst_ld;
+  e.dst_col0 = d->dst_col0; e.dst_ncols = d->dst_ncols;
+  e.dst_f32 = d->dst_f32; e.f32_ld = d->f32_ld; e.f32_begin = d->f32_begin; e.f32_end = d->f32_end;
+  e.w_last = d->w_last; e.b_last = d->b_last; e.n_last = d->n_last; e.w_last_ld = d->w_last_ld; e.dst_last = d->dst_last;
+  e.seed.hi = (__nv_bfloat16*)d->seed_hi; e.seed.lo = (__nv_bfloat16*)d->seed_lo; e.seed.ld = d->seed_ld;
+  e.sav_hi = (const __nv_bfloat16*)d->sav_hi; e.sav_lo = (const __nv_bfloat16*)d->sav_lo; e.sav_ld = d->sav_ld;
+  e.sav_ncols = d->sav_ncols; e.sav_scale = d->sav_scale;
+  return nefii::gemm_split_bf16((cudaStream_t)stream, p);
+}
+
+int nefii_split_to_planes(void* stream, const float* src, int rows, int cols, int ld_src, int transpose, float scale,
+                          void* dst_hi, void* dst_lo, int rows_pad, int cols_pad) {
+  return nefii::split_to_planes((cudaStream_t)stream, src, rows, cols, ld_src, transpose, scale, (__nv_bfloat16*)dst_hi,
+                                (__nv_bfloat16*)dst_lo, rows_pad, cols_pad);
+}
+
+}  // extern "C"

@@ -1,0 +1,472 @@
+// Split-bf16 tcgen05 layer GEMM for the MLPs on the hot path (SDF net, radiance net, material net).
+//
+//   D[m, n] = sum_k  Ahi[m,k]*Bhi[n,k] + Ahi[m,k]*Blo[n,k] + Alo[m,k]*Bhi[n,k]        (fp32 accumulate in TMEM)
+//
+// The reference runs these layers as FP32 SGEMM (nn.Linear).  tcgen05 has no fp32 MMA, so every
+// fp32 value x travels as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)); three kind::f16 MMAs
+// per K step recover ~16 mantissa bits per operand (measured against the fp32 oracle in
+// tests/test_gemm.py and reported in DESIGN.md).
+//
+// One CTA owns a 128-row tile of points and loops over the output columns in chunks of 256:
+//   warp 0      : TMA producer (A/B hi+lo tiles, 128B swizzle, 2-stage mbarrier ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (2 x 256-column accumulators)
+//   warps 2..9  : epilogue (tcgen05.ld -> bias/activation/derivative -> bf16 planes / fp32 / fused
+//                 output layer), overlapped with the MMAs of the next column chunk.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "mlp_gemm.cuh"
+
+namespace nefii {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int kStages = 2;
+constexpr int kATileBytes = BM * BK * 2;   // 16 KB
+constexpr int kBTileBytes = BN * BK * 2;   // 32 KB
+constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;  // 96 KB
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;  // 320
+constexpr int kTmemCols = 512;
+constexpr int kMaxLast = 4;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ +
+                              2 * BM * kMaxLast * sizeof(float);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row atoms of 1024 B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset between 8-row atoms
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M=128, N=256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ float softplus100(float v) {
+  float t = 100.f * v;
+  if (t > 20.f) return v;
+  float e = __expf(t);
+  float l = (e < 1e-3f) ? e * (1.f - 0.5f * e) : __logf(1.f + e);
+  return l * 0.01f;
+}
+// derivative of the activation recovered from its saved output h
+__device__ __forceinline__ float dact_from_output(int act, float h) {
+  if (act == ACT_SOFTPLUS100) {
+    float u = 100.f * h;   // sigmoid(100 z) = 1 - exp(-100 h)
+    if (u < 0.01f) return u * (1.f - 0.5f * u + 0.16666667f * u * u);
+    return 1.f - __expf(-u);
+  }
+  if (act == ACT_RELU) return h > 0.f ? 1.f : 0.f;
+  if (act == ACT_ELU) return h > 0.f ? 1.f : h + 1.f;
+  return 1.f;
+}
+__device__ __forceinline__ float apply_act(int act, float v) {
+  if (act == ACT_SOFTPLUS100) return softplus100(v);
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_ELU) return v > 0.f ? v : expm1f(v);
+  return v;
+}
+
+__device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// store 32 consecutive values of one row as planes; vectorised when the whole run is in range
+__device__ __forceinline__ void store_planes32(const Planes& dst, long long row, int col_base, int n0, int n_limit,
+                                               const float* vals) {
+  __nv_bfloat16* ph = dst.hi + row * dst.ld + col_base + n0;
+  __nv_bfloat16* pl = dst.lo + row * dst.ld + col_base + n0;
+  if (n0 + 32 <= n_limit && ((col_base + n0) & 7) == 0) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      uint32_t wh[4], wl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split2(vals[v * 8 + 2 * j], h0, l0);
+        split2(vals[v * 8 + 2 * j + 1], h1, l1);
+        wh[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        wl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint4*>(ph + v * 8) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      *reinterpret_cast<uint4*>(pl + v * 8) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (n0 + j < n_limit) {
+        __nv_bfloat16 h, l;
+        split2(vals[j], h, l);
+        ph[j] = h;
+        pl[j] = l;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                       const int* __restrict__ count_ptr, int rows_cap, int k_blocks, int n_chunks,
+                       const GemmEpilogue epi) {
+  const int m_tile = blockIdx.x;
+  int m_limit = rows_cap;
+  if (count_ptr != nullptr) {
+    int c = *count_ptr;
+    if (c < m_limit) m_limit = c;
+  }
+  if ((long long)m_tile * BM >= m_limit) return;   // uniform exit before any barrier / TMEM use
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+  // bars[0..1] full, [2..3] empty, [4..5] tmem_full, [6..7] tmem_empty ; then tmem base slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* s_last = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes + 256);   // [2][BM][kMaxLast]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&bars[0 + s]), 1);
+      mbar_init(smem_u32(&bars[2 + s]), 1);
+      mbar_init(smem_u32(&bars[4 + s]), 1);
+      mbar_init(smem_u32(&bars[6 + s]), kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int nc = 0; nc < n_chunks; ++nc) {
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(smem_u32(&bars[2 + stage]), phase ^ 1);
+          const uint32_t full = smem_u32(&bars[0 + stage]);
+          mbar_expect_tx(full, kStageBytes);
+          unsigned char* st = tiles + (size_t)stage * kStageBytes;
+          tma_load_2d(smem_u32(st), &map_a_hi, full, kb * BK, m_tile * BM);
+          tma_load_2d(smem_u32(st + kATileBytes), &map_a_lo, full, kb * BK, m_tile * BM);
+          tma_load_2d(smem_u32(st + 2 * kATileBytes), &map_b_hi, full, kb * BK, nc * BN);
+          tma_load_2d(smem_u32(st + 2 * kATileBytes + kBTileBytes), &map_b_lo, full, kb * BK, nc * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int nc = 0; nc < n_chunks; ++nc) {
+        const int buf = nc & 1;
+        const uint32_t use = (uint32_t)(nc >> 1);
+        mbar_wait(smem_u32(&bars[6 + buf]), (use & 1) ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(smem_u32(&bars[0 + stage]), phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(tiles + (size_t)stage * kStageBytes);
+          const uint64_t a_hi = make_smem_desc(st);
+          const uint64_t a_lo = make_smem_desc(st + kATileBytes);
+          const uint64_t b_hi = make_smem_desc(st + 2 * kATileBytes);
+          const uint64_t b_lo = make_smem_desc(st + 2 * kATileBytes + kBTileBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step inside the swizzle row
+            tc_mma_bf16(tmem_d, a_hi + koff, b_hi + koff, kIdesc, (kb | k) != 0);
+            tc_mma_bf16(tmem_d, a_hi + koff, b_lo + koff, kIdesc, 1);
+            tc_mma_bf16(tmem_d, a_lo + koff, b_hi + koff, kIdesc, 1);
+          }
+          tc_commit(smem_u32(&bars[2 + stage]));   // frees the smem stage once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(smem_u32(&bars[4 + buf]));       // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps
+    const int e = warp - 2;             // 0..7
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int half = e >> 2;            // which 128-column half of the 256-column chunk
+    const int row_in_tile = quarter * 32 + lane;
+    const long long row = (long long)m_tile * BM + row_in_tile;
+    const bool row_ok = row < m_limit;
+    float part[kMaxLast] = {0.f, 0.f, 0.f, 0.f};
+    const int n_needed = epi.n_valid;   // columns beyond this are padding
+
+    for (int nc = 0; nc < n_chunks; ++nc) {
+      const int buf = nc & 1;
+      const uint32_t use = (uint32_t)(nc >> 1);
+      mbar_wait(smem_u32(&bars[4 + buf]), use & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int n0 = nc * BN + half * 128 + ch * 32;
+        if (n0 >= n_needed) break;      // warp-uniform
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + half * 128 + ch * 32), r);
+        float outv[32];
+        float seedv[32];
+        if (epi.mode == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + j;
+            float v = __uint_as_float(r[j]);
+            float h = 0.f;
+            if (n < n_needed) {
+              if (epi.bias) v += __ldg(epi.bias + n);
+              h = apply_act(epi.act, v);
+              if (epi.w_last) {
+#pragma unroll
+                for (int q = 0; q < kMaxLast; ++q)
+                  if (q < epi.n_last) part[q] = fmaf(h, __ldg(epi.w_last + (size_t)q * epi.w_last_ld + n), part[q]);
+                if (epi.seed.hi) seedv[j] = __ldg(epi.w_last + n) * dact_from_output(epi.act, h);
+              }
+            } else if (epi.seed.hi) {
+              seedv[j] = 0.f;
+            }
+            outv[j] = h;
+          }
+        } else {
+          const bool has_sav = epi.sav_hi != nullptr && row_ok;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + j;
+            float g = __uint_as_float(r[j]);
+            if (has_sav && n < epi.sav_ncols) {
+              const size_t off = (size_t)row * epi.sav_ld + n;
+              float h = (__bfloat162float(epi.sav_hi[off]) + __bfloat162float(epi.sav_lo[off])) * epi.sav_scale;
+              g *= dact_from_output(epi.act, h);
+            }
+            outv[j] = g;
+          }
+        }
+        if (row_ok) {
+          if (epi.dst_f32 && n0 < epi.f32_end && n0 + 32 > epi.f32_begin) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + j;
+              if (n >= epi.f32_begin && n < epi.f32_end) epi.dst_f32[(size_t)row * epi.f32_ld + (n - epi.f32_begin)] = outv[j];
+            }
+          }
+          if (epi.dst.hi && n0 < epi.dst_ncols) {
+            if (epi.out_scale != 1.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) outv[j] *= epi.out_scale;
+            }
+            store_planes32(epi.dst, row, epi.dst_col0, n0, epi.dst_ncols, outv);
+          }
+          if (epi.mode == 0 && epi.seed.hi) store_planes32(epi.seed, row, 0, n0, n_needed, seedv);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[6 + buf]));
+    }
+
+    if (epi.mode == 0 && epi.w_last != nullptr) {
+      // combine the two column halves of each row (deterministic order) and add the bias
+#pragma unroll
+      for (int q = 0; q < kMaxLast; ++q) s_last[(half * BM + row_in_tile) * kMaxLast + q] = part[q];
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+      if (half == 0 && row_ok) {
+        for (int q = 0; q < epi.n_last; ++q) {
+          float y = s_last[(0 * BM + row_in_tile) * kMaxLast + q] + s_last[(1 * BM + row_in_tile) * kMaxLast + q];
+          if (epi.b_last) y += __ldg(epi.b_last + q);
+          epi.dst_last[(size_t)row * epi.n_last + q] = y;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_map(CUtensorMap* map, const void* base, int rows, int ld, int k_extent, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(NEFII_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(NEFII_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d ld=%d", (int)r, rows, ld);
+  return NEFII_OK;
+}
+
+__global__ void split_to_planes_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, int transpose,
+                                       float scale, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                       int rows_pad, int cols_pad) {
+  const long long total = (long long)rows_pad * cols_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols_pad), c = (int)(i % cols_pad);
+    float x = 0.f;
+    if (!transpose) {
+      if (r < rows && c < cols) x = src[(size_t)r * ld_src + c];
+    } else {
+      if (r < cols && c < rows) x = src[(size_t)c * ld_src + r];
+    }
+    x *= scale;
+    __nv_bfloat16 h, l;
+    split2(x, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+}  // namespace
+
+int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
+  NEFII_CHECK_ARG(p.a_hi && p.a_lo && p.b_hi && p.b_lo, "gemm_split_bf16: null operand");
+  NEFII_CHECK_ARG(p.k_pad > 0 && p.k_pad % BK == 0 && p.k_pad <= p.a_ld && p.k_pad <= p.b_ld,
+                  "gemm_split_bf16: k_pad=%d must be a multiple of %d and <= ld (a_ld=%d b_ld=%d)", p.k_pad, BK, p.a_ld, p.b_ld);
+  NEFII_CHECK_ARG(p.n_pad > 0 && p.n_pad % BN == 0, "gemm_split_bf16: n_pad=%d must be a multiple of %d", p.n_pad, BN);
+  NEFII_CHECK_ARG(p.a_ld % 8 == 0 && p.b_ld % 8 == 0, "gemm_split_bf16: leading dimensions must be multiples of 8");
+  NEFII_CHECK_ARG(p.epi.n_valid > 0 && p.epi.n_valid <= p.n_pad, "gemm_split_bf16: n_valid out of range");
+  NEFII_CHECK_ARG(p.epi.n_last <= kMaxLast, "gemm_split_bf16: fused output layer supports at most %d outputs", kMaxLast);
+  if (p.rows_cap <= 0) return NEFII_OK;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, p.a_hi, p.rows_cap, p.a_ld, p.k_pad, BM))) return rc;
+  if ((rc = make_map(&ma_lo, p.a_lo, p.rows_cap, p.a_ld, p.k_pad, BM))) return rc;
+  if ((rc = make_map(&mb_hi, p.b_hi, p.n_pad, p.b_ld, p.k_pad, BN))) return rc;
+  if ((rc = make_map(&mb_lo, p.b_lo, p.n_pad, p.b_ld, p.k_pad, BN))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NEFII_CUDA(cudaFuncSetAttribute(gemm_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_set = true;
+  }
+  const int n_chunks = ceil_div(p.epi.n_valid, BN);
+  const int grid = ceil_div(p.rows_cap, BM);
+  gemm_split_bf16_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p.count, p.rows_cap,
+                                                                 p.k_pad / BK, n_chunks, p.epi);
+  NEFII_LAUNCH_CHECK();
+  return NEFII_OK;
+}
+
+int split_to_planes(cudaStream_t stream, const float* src, int rows, int cols, int ld_src, int transpose, float scale,
+                    __nv_bfloat16* hi, __nv_bfloat16* lo, int rows_pad, int cols_pad) {
+  NEFII_CHECK_ARG(src && hi && lo, "split_to_planes: null pointer");
+  const int out_rows = transpose ? cols : rows, out_cols = transpose ? rows : cols;
+  NEFII_CHECK_ARG(rows_pad >= out_rows && cols_pad >= out_cols, "split_to_planes: padded shape too small");
+  const long long total = (long long)rows_pad * cols_pad;
+  if (total == 0) return NEFII_OK;
+  int blocks = ceil_div(total, 256);
+  if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+  split_to_planes_kernel<<<blocks, 256, 0, stream>>>(src, rows, cols, ld_src, transpose, scale, hi, lo, rows_pad, cols_pad);
+  NEFII_LAUNCH_CHECK();
+  return NEFII_OK;
+}
+
+}  // namespace nefii

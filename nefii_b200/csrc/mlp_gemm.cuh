@@ -1,0 +1,61 @@
+// Split-bf16 ("bf16x3") tcgen05 layer GEMM -- declarations shared by the MLP sequencers.
+#pragma once
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace nefii {
+
+enum Act : int { ACT_NONE = 0, ACT_SOFTPLUS100 = 1, ACT_RELU = 2, ACT_ELU = 3 };
+
+// A value x is carried between layers as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)).
+struct Planes {
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int ld = 0;  // elements per row (multiple of 64)
+};
+
+struct GemmEpilogue {
+  int mode = 0;             // 0: forward layer (bias + activation), 1: backward layer (x act'(saved))
+  int act = ACT_NONE;
+  int n_valid = 0;          // output columns [0, n_valid) are real
+  const float* bias = nullptr;
+  float out_scale = 1.f;    // applied to what is written to dst planes (e.g. 1/sqrt(2) before a skip concat)
+  // destination planes: column n -> dst.{hi,lo}[m * dst.ld + dst_col0 + n] for n < dst_ncols
+  Planes dst;
+  int dst_col0 = 0;
+  int dst_ncols = 0;
+  // optional fp32 copy of columns [f32_begin, f32_end): dst_f32[m * f32_ld + n - f32_begin]
+  float* dst_f32 = nullptr;
+  int f32_ld = 0, f32_begin = 0, f32_end = 0;
+  // forward only: fused tiny output layer y[m, q] = sum_n act(z[m, n]) * w_last[q * w_last_ld + n] + b_last[q]
+  const float* w_last = nullptr;
+  const float* b_last = nullptr;
+  int n_last = 0, w_last_ld = 0;
+  float* dst_last = nullptr;   // [rows, n_last]
+  // forward only: seed of the input-gradient chain, split(w_last[n] * act'(z[m, n])) -> seed planes
+  Planes seed;
+  // backward only: forward activations that this layer's output gradient is multiplied with
+  // (act' is recovered from the saved post-activation value * sav_scale), columns [0, sav_ncols)
+  const __nv_bfloat16* sav_hi = nullptr;
+  const __nv_bfloat16* sav_lo = nullptr;
+  int sav_ld = 0, sav_ncols = 0;
+  float sav_scale = 1.f;
+};
+
+struct GemmProblem {
+  // A: activations [rows_cap, k_pad] as planes; B: weights [n_pad, k_pad] as planes (K-major both)
+  const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo; int a_ld; int rows_cap;
+  const __nv_bfloat16* b_hi; const __nv_bfloat16* b_lo; int b_ld; int n_pad;  // n_pad multiple of 256
+  int k_pad;                // multiple of 64, <= a_ld, <= b_ld
+  const int* count;         // device: number of valid rows (nullptr -> rows_cap)
+  GemmEpilogue epi;
+};
+
+int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p);
+
+// fp32 [rows, cols] (row stride ld_src) -> zero-padded bf16 planes [rows_pad, cols_pad];
+// transpose=1 writes src^T.
+int split_to_planes(cudaStream_t stream, const float* src, int rows, int cols, int ld_src, int transpose,
+                    float scale, __nv_bfloat16* hi, __nv_bfloat16* lo, int rows_pad, int cols_pad);
+
+}  // namespace nefii

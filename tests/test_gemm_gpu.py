@@ -1,0 +1,100 @@
+"""Parity of the tcgen05 split-bf16 layer GEMM (C ABI nefii_gemm_split_bf16) against fp32 torch."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _planes_to_f32(p):
+    return p[0].float() + p[1].float()
+
+
+@pytest.mark.parametrize("rows,k,n,act", [
+    (128, 64, 256, 0), (1000, 512, 512, 1), (4096, 512, 473, 1), (300, 640, 512, 2), (257, 576, 512, 3),
+])
+def test_forward_layer(cuda_device, rows, k, n, act):
+    from nefii_b200 import ops
+    torch.manual_seed(rows + k + n)
+    dev = cuda_device
+    x = torch.randn(rows, k, device=dev) * 0.5
+    w = torch.randn(n, k, device=dev) * (1.0 / k ** 0.5)
+    bias = torch.randn(n, device=dev) * 0.1
+    k_pad, n_pad = ops.round_up(k, 64), ops.round_up(n, 256)
+    a = ops.split_to_planes(x, cols_pad=k_pad)
+    b = ops.split_to_planes(w, rows_pad=n_pad, cols_pad=k_pad)
+    dst = (torch.zeros(rows, n_pad, device=dev, dtype=torch.bfloat16), torch.zeros(rows, n_pad, device=dev, dtype=torch.bfloat16))
+    f32 = torch.zeros(rows, n, device=dev)
+    ops.gemm_split_bf16(a, b, k_pad, n, act=act, bias=bias, dst=dst, dst_ncols=n, dst_f32=f32, f32_begin=0, f32_end=n)
+    torch.cuda.synchronize()
+    z = x.double() @ w.double().t() + bias.double()
+    if act == 1:
+        ref = torch.nn.functional.softplus(z, beta=100)
+    elif act == 2:
+        ref = torch.relu(z)
+    elif act == 3:
+        ref = torch.nn.functional.elu(z)
+    else:
+        ref = z
+    err = (f32.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err < 2e-5 * max(scale, 1.0), (err, scale)
+    # planes reproduce the fp32 result to ~2^-16 relative
+    perr = (_planes_to_f32(dst)[:, :n].double() - ref).abs().max().item()
+    assert perr < 4e-5 * max(scale, 1.0), perr
+    # padding columns of the destination stay untouched
+    assert _planes_to_f32(dst)[:, n:].abs().max().item() == 0 if n_pad > n else True
+
+
+def test_count_limits_rows_and_fused_last(cuda_device):
+    from nefii_b200 import ops
+    torch.manual_seed(3)
+    dev = cuda_device
+    rows, k, n = 700, 512, 512
+    x = torch.randn(rows, k, device=dev) * 0.3
+    w = torch.randn(n, k, device=dev) / k ** 0.5
+    bias = torch.zeros(n, device=dev)
+    w_last = torch.randn(3, n, device=dev) / n ** 0.5
+    b_last = torch.randn(3, device=dev)
+    a = ops.split_to_planes(x)
+    b = ops.split_to_planes(w)
+    count = torch.tensor([333], device=dev, dtype=torch.int32)
+    y = torch.full((rows, 3), -7.0, device=dev)
+    feat = torch.full((rows, n), -7.0, device=dev)
+    seed = (torch.zeros(rows, n, device=dev, dtype=torch.bfloat16), torch.zeros(rows, n, device=dev, dtype=torch.bfloat16))
+    ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, count=count, dst_f32=feat, f32_begin=0, f32_end=n,
+                        w_last=w_last, b_last=b_last, dst_last=y, seed=seed)
+    torch.cuda.synchronize()
+    z = x.double() @ w.double().t()
+    h = torch.nn.functional.softplus(z, beta=100)
+    yref = h @ w_last.double().t() + b_last.double()
+    assert (y[:333].double() - yref[:333]).abs().max().item() < 3e-5
+    assert (y[333:] == -7.0).all() and (feat[333:] == -7.0).all()
+    sref = w_last[0].double() * torch.sigmoid(100 * z)
+    assert ((seed[0].float() + seed[1].float())[:333].double() - sref[:333]).abs().max().item() < 3e-5
+
+
+def test_backward_layer(cuda_device):
+    from nefii_b200 import ops
+    torch.manual_seed(5)
+    dev = cuda_device
+    rows, k, n = 513, 512, 512          # g [rows, k] @ W[k(out), n(in)]  (B = W^T planes)
+    g = torch.randn(rows, k, device=dev)
+    w = torch.randn(k, n, device=dev) / k ** 0.5       # layer weight [out=k, in=n]
+    h_saved = torch.rand(rows, n, device=dev) * 0.05   # forward activations of the layer input
+    a = ops.split_to_planes(g)
+    bt = ops.split_to_planes(w, transpose=True)        # [n, k]
+    sav = ops.split_to_planes(h_saved * 0.70710678)
+    dst = (torch.zeros(rows, n, device=dev, dtype=torch.bfloat16), torch.zeros(rows, n, device=dev, dtype=torch.bfloat16))
+    pe = torch.zeros(rows, 39, device=dev)
+    ops.gemm_split_bf16(a, bt, k, n, mode=1, act=1, out_scale=0.70710678, dst=dst, dst_ncols=473,
+                        dst_f32=pe, f32_begin=473, f32_end=512, sav=sav, sav_ncols=473, sav_scale=1.41421356)
+    torch.cuda.synchronize()
+    full = g.double() @ w.double()
+    sig = 1 - torch.exp(-100 * (sav[0].float() + sav[1].float()).double() * 1.41421356)
+    ref = full.clone()
+    ref[:, :473] = full[:, :473] * sig[:, :473] * 0.70710678
+    got = (dst[0].float() + dst[1].float()).double()
+    assert (got[:, :473] - ref[:, :473]).abs().max().item() < 1e-4
+    assert (got[:, 473:] == 0).all()
+    # fp32 side output holds the raw product (no out_scale) for the PE columns
+    assert (pe.double() - full[:, 473:]).abs().max().item() < 1e-4

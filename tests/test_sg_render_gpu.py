@@ -1,0 +1,85 @@
+"""GPU: render_with_sg through the C ABI against the oracle on the same device and the golden vectors.
+
+Tolerance (BASELINE.json north_star): shading rel 1e-4 (abs floor 1e-6).  The FP32 reference is
+itself ill-conditioned at low roughness (its own f32-vs-f64 gap reaches 1e-2), so the
+assertion is on the fraction of lanes within rel 1e-4 of the *same-device f32 oracle*."""
+import pytest
+import torch
+
+from oracle import inputs, sg
+from tests.util import load_golden, rel_stats
+
+pytestmark = pytest.mark.gpu
+KEYS = ("sg_rgb", "sg_specular_rgb", "sg_diffuse_rgb")
+
+
+@pytest.mark.parametrize("lights", ["sunrise", "synthetic", "envmap1"])
+@pytest.mark.parametrize("rough", inputs.ROUGHNESS_SWEEP)
+def test_matches_oracle_same_device(cuda_device, lights, rough):
+    from nefii_b200.model.sg_render import render_with_sg
+    g = load_golden("sg_render_cfg1.npz")
+    dev = cuda_device
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    args = (t("lgt_" + lights), t("spec"), torch.tensor([[rough]], device=dev), t("albedo"), t("normal"), t("view"))
+    got = render_with_sg(*args)
+    ref = sg.render_with_sg(*args)
+    for k in KEYS:
+        frac, p99, mx = rel_stats(got[k], ref[k])
+        if k == "sg_specular_rgb" and rough < 0.2:
+            assert frac > 0.90, (k, frac, p99, mx)      # f32 reference is noise-dominated here
+        else:
+            assert frac > 0.995, (k, frac, p99, mx)
+
+
+def test_matches_golden_cpu_reference(cuda_device):
+    from nefii_b200.model.sg_render import render_with_sg
+    g = load_golden("sg_render_cfg1.npz")
+    dev = cuda_device
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    got = render_with_sg(t("lgt_sunrise"), t("spec"), torch.tensor([[0.5]], device=dev), t("albedo"), t("normal"), t("view"))
+    for k in KEYS:
+        ref64 = torch.from_numpy(g["sunrise_r0.5_%s_f64" % k])
+        ref32 = torch.from_numpy(g["sunrise_r0.5_%s_f32" % k])
+        floor = (ref32.double() - ref64).abs().max().item()      # the reference's own f32 noise
+        assert (got[k].cpu().double() - ref64).abs().max().item() <= 4 * floor + 1e-6
+
+
+def test_two_materials_blending_and_shapes(cuda_device):
+    from nefii_b200.model.sg_render import render_with_sg
+    g = load_golden("sg_render_cfg1.npz")
+    dev = cuda_device
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    got = render_with_sg(t("lgt_sunrise"), t("k2_spec"), t("k2_rough"), t("albedo").reshape(32, 32, 3),
+                         t("normal").reshape(32, 32, 3), t("view").reshape(32, 32, 3),
+                         blending_weights=t("k2_blend").reshape(32, 32, 2))
+    assert got["sg_rgb"].shape == (32, 32, 3)
+    for k in KEYS:
+        frac, p99, mx = rel_stats(got[k].reshape(-1, 3), torch.from_numpy(g["k2_" + k]))
+        assert frac > 0.98, (k, frac, p99, mx)
+
+
+def test_edge_sizes(cuda_device):
+    from nefii_b200.model.sg_render import render_with_sg
+    dev = cuda_device
+    lgt = inputs.synthetic_light_sgs(7, seed=9).to(dev)        # ragged SG count
+    spec, rough = torch.full((1, 3), 0.04, device=dev), torch.tensor([[0.4]], device=dev)
+    empty = render_with_sg(lgt, spec, rough, torch.zeros(0, 3, device=dev), torch.zeros(0, 3, device=dev), torch.zeros(0, 3, device=dev))
+    assert empty["sg_rgb"].shape == (0, 3)
+    for n in (1, 33, 100003):
+        normal, view, albedo = [x.to(dev) for x in inputs.shading_inputs(n, seed=n)]
+        got = render_with_sg(lgt, spec, rough, albedo, normal, view)
+        ref = sg.render_with_sg(lgt, spec, rough, albedo, normal, view)
+        frac, p99, mx = rel_stats(got["sg_rgb"], ref["sg_rgb"])
+        assert frac > 0.995, (n, frac, p99, mx)
+
+
+def test_background_sg(cuda_device):
+    import ctypes
+    from nefii_b200 import _lib
+    dev = cuda_device
+    lgt = inputs.synthetic_light_sgs(128, seed=1).to(dev)
+    d = torch.nn.functional.normalize(torch.randn(5000, 3, device=dev), dim=-1)
+    out = torch.empty(5000, 3, device=dev)
+    _lib.check(_lib.raw().nefii_background_sg_fwd(_lib.stream_ptr(dev), 5000, 128, _lib.dptr(lgt), _lib.dptr(d), _lib.dptr(out)))
+    ref = sg.background_sg(lgt, d)
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-6)

@@ -1,0 +1,82 @@
+"""GPU diagnostics printed during development trips (not part of the product or the tests)."""
+import sys
+import os
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import inputs, sg  # noqa: E402
+from tests.util import load_golden, rel_stats  # noqa: E402
+
+
+def ev_time(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def diag_sg():
+    from nefii_b200.model.sg_render import render_with_sg
+    dev = torch.device("cuda:0")
+    g = load_golden("sg_render_cfg1.npz")
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    for lights in ("sunrise", "synthetic", "envmap1"):
+        for rough in inputs.ROUGHNESS_SWEEP:
+            args = (t("lgt_" + lights), t("spec"), torch.tensor([[rough]], device=dev), t("albedo"), t("normal"), t("view"))
+            got = render_with_sg(*args)
+            ref = sg.render_with_sg(*args)
+            for k in ("sg_specular_rgb", "sg_diffuse_rgb"):
+                frac, p99, mx = rel_stats(got[k], ref[k])
+                r64 = torch.from_numpy(g["%s_r%g_%s_f64" % (lights, rough, k)])
+                f_ref = rel_stats(ref[k], r64)
+                f_got = rel_stats(got[k], r64)
+                print("SG %-9s r=%-5g %-16s vs-oracle: frac<=1e-4 %.4f p99 %.2e max %.2e | vs f64: oracle p99 %.2e ours p99 %.2e  bitexact %.3f"
+                      % (lights, rough, k, frac, p99, mx, f_ref[1], f_got[1], (got[k] == ref[k]).float().mean().item()))
+    for n in (1024, 131072, 1 << 20):
+        normal, view, albedo = [x.to(dev) for x in inputs.shading_inputs(n, seed=0)]
+        lgt = t("lgt_sunrise")
+        spec, rough = t("spec"), torch.tensor([[0.3]], device=dev)
+        ms = ev_time(lambda: render_with_sg(lgt, spec, rough, albedo, normal, view))
+        ms_ref = ev_time(lambda: sg.render_with_sg(lgt, spec, rough, albedo, normal, view), iters=3, warm=1) if n <= 131072 else float("nan")
+        print("SG time n=%d ours %.4f ms (%.1f Mray/s)  torch-oracle-on-gpu %.3f ms" % (n, ms, n / ms / 1e3, ms_ref))
+
+
+def diag_gemm():
+    from nefii_b200 import ops
+    dev = torch.device("cuda:0")
+    for rows in (4096, 131072, 1 << 20):
+        k = n = 512
+        x = torch.randn(rows, k, device=dev) * 0.3
+        w = torch.randn(n, k, device=dev) / k ** 0.5
+        bias = torch.zeros(n, device=dev)
+        a = ops.split_to_planes(x)
+        b = ops.split_to_planes(w)
+        dst = (torch.empty(rows, n, device=dev, dtype=torch.bfloat16), torch.empty(rows, n, device=dev, dtype=torch.bfloat16))
+        fn = lambda: ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n)
+        ms = ev_time(fn)
+        fl = 2.0 * rows * n * k
+        print("GEMM rows=%d: %.4f ms  %.1f TFLOP/s algorithmic (x3 MMA = %.1f bf16 TFLOP/s)" % (rows, ms, fl / ms / 1e9, 3 * fl / ms / 1e9))
+        if rows <= 131072:
+            z = torch.nn.functional.softplus(x @ w.t() + bias, beta=100)
+            got = dst[0].float() + dst[1].float()
+            z64 = torch.nn.functional.softplus(x.double() @ w.double().t() + bias.double(), beta=100)
+            print("   err vs f64: ours max %.2e mean %.2e | torch fp32 max %.2e mean %.2e" % (
+                (got.double() - z64).abs().max().item(), (got.double() - z64).abs().mean().item(),
+                (z.double() - z64).abs().max().item(), (z.double() - z64).abs().mean().item()))
+            ms_t = ev_time(lambda: torch.nn.functional.softplus(x @ w.t() + bias, beta=100))
+            print("   torch fp32 linear+softplus: %.4f ms" % ms_t)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["sg", "gemm"]
+    print(torch.cuda.get_device_name(0))
+    for w in which:
+        globals()["diag_" + w]()
