@@ -62,7 +62,7 @@ typedef struct nefii_gemm_desc {
   int32_t n_valid;                /* real output columns */
   const float* bias;              /* [n_valid] or NULL */
   float out_scale;
-  void* dst_hi; void* dst_lo; int32_t dst_ld; int32_t dst_col0; int32_t dst_ncols;   /* output planes (may be NULL) */
+  void* dst_hi; void* dst_lo; int32_t dst_ld; int32_t dst_col0; int32_t dst_ncols; int32_t dst_zero_to; /* output planes (may be NULL); cols [dst_ncols,dst_zero_to) zero-filled */
   float* dst_f32; int32_t f32_ld; int32_t f32_begin; int32_t f32_end;                /* optional fp32 output columns */
   const float* w_last; const float* b_last; int32_t n_last; int32_t w_last_ld; float* dst_last; /* fused tiny output layer */
   void* seed_hi; void* seed_lo; int32_t seed_ld;                                     /* input-gradient seed planes */
@@ -75,6 +75,33 @@ int nefii_gemm_split_bf16(void* stream, const nefii_gemm_desc* desc /* host */);
  * transpose != 0 writes the transpose.  Used to pack weights (and test inputs). */
 int nefii_split_to_planes(void* stream, const float* src, int rows, int cols, int ld_src, int transpose, float scale,
                           void* dst_hi, void* dst_lo, int rows_pad, int cols_pad);
+
+/* ---------------------------------------------------------------------------------------------
+ * SDF / feature MLP -- replaces ImplicitNetwork.forward and .gradient(x, no_grad=True),
+ * code/model/implicit_differentiable_renderer.py:85-123 (+ embedder.py:5-50).
+ * The handle owns the packed (bf16 hi/lo, transposed) copy of the weights; the caller owns the
+ * workspace and every input / output buffer.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct nefii_sdf_config {
+  int32_t d_in;        /* 3 */
+  int32_t n_freqs;     /* multires (6) */
+  int32_t width;       /* hidden width == feature_vector_size (512) */
+  int32_t n_hidden;    /* len(dims) (8) */
+  int32_t skip_layer;  /* skip_in[0] (4); <= 0: none */
+  int32_t d_out;       /* 1 */
+} nefii_sdf_config;
+
+int nefii_sdf_create(void** handle, const nefii_sdf_config* cfg /* host */);
+int nefii_sdf_destroy(void* handle);
+/* weights / biases: host arrays of n_hidden+1 device pointers; weights[l] is the EFFECTIVE fp32 matrix
+ * [out_l, in_l] (weight_norm folded: g * v / |v|), row-major contiguous.  Call again whenever the
+ * parameters change. */
+int nefii_sdf_set_weights(void* handle, void* stream, const float* const* weights, const float* const* biases);
+int64_t nefii_sdf_workspace_bytes(void* handle, int rows_cap, int with_grad);
+/* x [rows_cap,3]; count: device int32 with the number of valid rows or NULL; sdf [rows_cap];
+ * feat [rows_cap,width] or NULL; grad [rows_cap,3] or NULL (d sdf / d x). */
+int nefii_sdf_eval(void* handle, void* stream, int rows_cap, const int32_t* count, const float* x,
+                   void* workspace, int64_t workspace_bytes, float* sdf, float* feat, float* grad);
 
 #ifdef __cplusplus
 }

@@ -2,8 +2,8 @@
 
 Host code is Python/PyTorch and mirrors the reference's module API (`nefii_b200.model.*` has the
 same class / function names, arguments and return dicts as the reference's `code/model/*`);
-all device work goes through the C ABI in include/nefii_b200.h (libnefii_b200.so).
+all device work goes through the C ABI in include/nefii_b200.h (libnefii_b200.so, loaded by
+`nefii_b200._lib`, which raises ImportError when the library has not been built -- there is no
+CPU or PyTorch fallback).  Build with `python nefii_b200/build.py`.
 """
-from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
-
-__all__ = ["_lib"]
+__version__ = "0.1.0"

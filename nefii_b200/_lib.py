@@ -19,6 +19,11 @@ SIGNATURES = {
     "nefii_sg_render_fwd": [c_void_p, c_int, c_int, c_int] + [c_void_p] * 10,
     "nefii_background_sg_fwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "nefii_gemm_split_bf16": [c_void_p, c_void_p],
+    "nefii_sdf_create": [c_void_p, c_void_p],
+    "nefii_sdf_destroy": [c_void_p],
+    "nefii_sdf_set_weights": [c_void_p, c_void_p, c_void_p, c_void_p],
+    "nefii_sdf_workspace_bytes": [c_void_p, c_int, c_int],
+    "nefii_sdf_eval": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p],
     "nefii_split_to_planes": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int],
 }
 
@@ -39,6 +44,7 @@ def _load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_int
+    lib.nefii_sdf_workspace_bytes.restype = c_longlong
     return lib
 
 

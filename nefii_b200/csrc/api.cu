@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/nefii_b200.h"
 #include "mlp_gemm.cuh"
+#include "sdf_mlp.cuh"
 
 namespace nefii {
 
@@ -50,7 +51,7 @@ int nefii_gemm_split_bf16(void* stream, const nefii_gemm_desc* d) {
   nefii::GemmEpilogue& e = p.epi;
   e.mode = d->mode; e.act = d->act; e.n_valid = d->n_valid; e.bias = d->bias; e.out_scale = d->out_scale;
   e.dst.hi = (__nv_bfloat16*)d->dst_hi; e.dst.lo = (__nv_bfloat16*)d->dst_lo; e.dst.ld = d->dst_ld;
-  e.dst_col0 = d->dst_col0; e.dst_ncols = d->dst_ncols;
+  e.dst_col0 = d->dst_col0; e.dst_ncols = d->dst_ncols; e.dst_zero_to = d->dst_zero_to;
   e.dst_f32 = d->dst_f32; e.f32_ld = d->f32_ld; e.f32_begin = d->f32_begin; e.f32_end = d->f32_end;
   e.w_last = d->w_last; e.b_last = d->b_last; e.n_last = d->n_last; e.w_last_ld = d->w_last_ld; e.dst_last = d->dst_last;
   e.seed.hi = (__nv_bfloat16*)d->seed_hi; e.seed.lo = (__nv_bfloat16*)d->seed_lo; e.seed.ld = d->seed_ld;
@@ -63,6 +64,36 @@ int nefii_split_to_planes(void* stream, const float* src, int rows, int cols, in
                           void* dst_hi, void* dst_lo, int rows_pad, int cols_pad) {
   return nefii::split_to_planes((cudaStream_t)stream, src, rows, cols, ld_src, transpose, scale, (__nv_bfloat16*)dst_hi,
                                 (__nv_bfloat16*)dst_lo, rows_pad, cols_pad);
+}
+
+int nefii_sdf_create(void** handle, const nefii_sdf_config* cfg) {
+  if (!handle || !cfg) return nefii::set_error(NEFII_ERR_ARG, "nefii_sdf_create: null argument");
+  nefii::SdfConfig c;
+  c.d_in = cfg->d_in; c.n_freqs = cfg->n_freqs; c.width = cfg->width; c.n_hidden = cfg->n_hidden;
+  c.skip_layer = cfg->skip_layer; c.d_out = cfg->d_out;
+  nefii::SdfNet* net = new nefii::SdfNet();
+  int rc = net->init(c);
+  if (rc) { delete net; return rc; }
+  *handle = net;
+  return NEFII_OK;
+}
+int nefii_sdf_destroy(void* handle) {
+  delete static_cast<nefii::SdfNet*>(handle);
+  return NEFII_OK;
+}
+int nefii_sdf_set_weights(void* handle, void* stream, const float* const* weights, const float* const* biases) {
+  if (!handle || !weights || !biases) return nefii::set_error(NEFII_ERR_ARG, "nefii_sdf_set_weights: null argument");
+  return static_cast<nefii::SdfNet*>(handle)->set_weights((cudaStream_t)stream, weights, biases);
+}
+int64_t nefii_sdf_workspace_bytes(void* handle, int rows_cap, int with_grad) {
+  if (!handle) return -1;
+  return (int64_t)static_cast<nefii::SdfNet*>(handle)->workspace_bytes(rows_cap, with_grad != 0);
+}
+int nefii_sdf_eval(void* handle, void* stream, int rows_cap, const int32_t* count, const float* x, void* workspace,
+                   int64_t workspace_bytes, float* sdf, float* feat, float* grad) {
+  if (!handle) return nefii::set_error(NEFII_ERR_ARG, "nefii_sdf_eval: null handle");
+  return static_cast<nefii::SdfNet*>(handle)->eval((cudaStream_t)stream, rows_cap, count, x, workspace,
+                                                   (size_t)workspace_bytes, sdf, feat, grad);
 }
 
 }  // extern "C"

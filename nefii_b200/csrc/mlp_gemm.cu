@@ -280,6 +280,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     const bool row_ok = row < m_limit;
     float part[kMaxLast] = {0.f, 0.f, 0.f, 0.f};
     const int n_needed = epi.n_valid;   // columns beyond this are padding
+    const int n_loop = epi.dst_zero_to > n_needed ? epi.dst_zero_to : n_needed;
 
     for (int nc = 0; nc < n_chunks; ++nc) {
       const int buf = nc & 1;
@@ -289,7 +290,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         const int n0 = nc * BN + half * 128 + ch * 32;
-        if (n0 >= n_needed) break;      // warp-uniform
+        if (n0 >= n_loop) break;        // warp-uniform
         uint32_t r[32];
         tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + half * 128 + ch * 32), r);
         float outv[32];
@@ -336,12 +337,11 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
               if (n >= epi.f32_begin && n < epi.f32_end) epi.dst_f32[(size_t)row * epi.f32_ld + (n - epi.f32_begin)] = outv[j];
             }
           }
-          if (epi.dst.hi && n0 < epi.dst_ncols) {
-            if (epi.out_scale != 1.f) {
+          const int dst_end = epi.dst_zero_to > epi.dst_ncols ? epi.dst_zero_to : epi.dst_ncols;
+          if (epi.dst.hi && n0 < dst_end) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) outv[j] *= epi.out_scale;
-            }
-            store_planes32(epi.dst, row, epi.dst_col0, n0, epi.dst_ncols, outv);
+            for (int j = 0; j < 32; ++j) outv[j] = (n0 + j < epi.dst_ncols) ? outv[j] * epi.out_scale : 0.f;
+            store_planes32(epi.dst, row, epi.dst_col0, n0, dst_end, outv);
           }
           if (epi.mode == 0 && epi.seed.hi) store_planes32(epi.seed, row, 0, n0, n_needed, seedv);
         }
@@ -447,7 +447,8 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
     NEFII_CUDA(cudaFuncSetAttribute(gemm_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_set = true;
   }
-  const int n_chunks = ceil_div(p.epi.n_valid, BN);
+  const int n_chunks = ceil_div(p.epi.dst_zero_to > p.epi.n_valid ? p.epi.dst_zero_to : p.epi.n_valid, BN);
+  NEFII_CHECK_ARG(n_chunks * BN <= p.n_pad, "gemm_split_bf16: dst_zero_to beyond n_pad");
   const int grid = ceil_div(p.rows_cap, BM);
   gemm_split_bf16_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p.count, p.rows_cap,
                                                                  p.k_pad / BK, n_chunks, p.epi);

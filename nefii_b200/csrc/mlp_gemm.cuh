@@ -24,6 +24,7 @@ struct GemmEpilogue {
   Planes dst;
   int dst_col0 = 0;
   int dst_ncols = 0;
+  int dst_zero_to = 0;      // plane columns [dst_ncols, dst_zero_to) are written as zeros
   // optional fp32 copy of columns [f32_begin, f32_end): dst_f32[m * f32_ld + n - f32_begin]
   float* dst_f32 = nullptr;
   int f32_ld = 0, f32_begin = 0, f32_end = 0;

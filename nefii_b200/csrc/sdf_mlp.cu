@@ -1,0 +1,313 @@
+// SDF / feature MLP (reference ImplicitNetwork, code/model/implicit_differentiable_renderer.py:18-123)
+// sequenced over the tcgen05 layer GEMM: positional encoding -> n_hidden x (Linear + Softplus(100)),
+// skip concat at `skip_layer`, fused 1-wide output layer, and the closed-form input gradient
+// (d sdf / d x, what ImplicitNetwork.gradient obtains through autograd) as a reverse chain of GEMMs.
+#include <vector>
+#include <cuda_bf16.h>
+#include "mlp_gemm.cuh"
+#include "sdf_mlp.cuh"
+
+namespace nefii {
+
+namespace {
+
+constexpr float kInvSqrt2 = 0.70710678118654752f;
+constexpr float kSqrt2 = 1.41421356237309505f;
+
+__device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// value j of the positional encoding of point p (embedder.py:22-36)
+__device__ __forceinline__ float pe_value(const float* p, int j) {
+  if (j < 3) return p[j];
+  const int k = (j - 3) / 6, r = (j - 3) % 6;
+  const float a = p[r % 3] * exp2f((float)k);
+  return r < 3 ? sinf(a) : cosf(a);
+}
+
+// writes PE(x) * scale into plane columns [col0, col0 + d_pe) and zeros up to col0 + zero_to
+__global__ void encode_kernel(const float* __restrict__ x, const int* __restrict__ count, int rows_cap, int d_pe,
+                              float scale, Planes dst, int col0, int zero_to) {
+  int limit = rows_cap;
+  if (count) limit = min(limit, *count);
+  const int width = max(d_pe, zero_to);
+  const long long total = (long long)limit * width;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / width), j = (int)(i % width);
+    float v = 0.f;
+    if (j < d_pe) {
+      float p[3] = {x[(size_t)row * 3 + 0], x[(size_t)row * 3 + 1], x[(size_t)row * 3 + 2]};
+      v = pe_value(p, j) * scale;
+    }
+    __nv_bfloat16 h, l;
+    split2(v, h, l);
+    dst.hi[(size_t)row * dst.ld + col0 + j] = h;
+    dst.lo[(size_t)row * dst.ld + col0 + j] = l;
+  }
+}
+
+// d sdf/dx from the gradient w.r.t. the encoding: g = g0 + g_skip / sqrt(2)
+__global__ void pe_backward_kernel(const float* __restrict__ x, const int* __restrict__ count, int rows_cap, int n_freqs,
+                                   const float* __restrict__ g0, const float* __restrict__ g_skip, int ld,
+                                   float* __restrict__ grad) {
+  int limit = rows_cap;
+  if (count) limit = min(limit, *count);
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < limit; row += gridDim.x * blockDim.x) {
+    const float* a = g0 + (size_t)row * ld;
+    const float* b = g_skip ? g_skip + (size_t)row * ld : nullptr;
+    float out[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xc = x[(size_t)row * 3 + c];
+      float acc = a[c] + (b ? b[c] * kInvSqrt2 : 0.f);
+      for (int k = 0; k < n_freqs; ++k) {
+        const float f = exp2f((float)k);
+        const float gs = a[3 + 6 * k + c] + (b ? b[3 + 6 * k + c] * kInvSqrt2 : 0.f);
+        const float gc = a[6 + 6 * k + c] + (b ? b[6 + 6 * k + c] * kInvSqrt2 : 0.f);
+        acc += f * (cosf(xc * f) * gs - sinf(xc * f) * gc);
+      }
+      out[c] = acc;
+    }
+    grad[(size_t)row * 3 + 0] = out[0];
+    grad[(size_t)row * 3 + 1] = out[1];
+    grad[(size_t)row * 3 + 2] = out[2];
+  }
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct SdfNet::Impl {
+  SdfConfig cfg;
+  int d_pe = 0;
+  int n_lin = 0;                      // hidden layers + output layer
+  std::vector<int> in_dim, out_dim;   // logical sizes per linear layer
+  std::vector<int> k_pad, n_pad;      // forward padding (K multiple of 64, N multiple of 256)
+  // device storage
+  std::vector<Planes> w_fwd;          // [n_pad, k_pad]
+  std::vector<Planes> w_bwd;          // W^T: [round_up(in,256), round_up(out,64)]
+  std::vector<float*> bias;
+  float* w_last = nullptr;            // [d_out, width] fp32
+  float* b_last = nullptr;
+  void* blob = nullptr;
+  bool has_weights = false;
+};
+
+SdfNet::SdfNet() : impl_(new Impl) {}
+SdfNet::~SdfNet() {
+  if (impl_->blob) cudaFree(impl_->blob);
+  delete impl_;
+}
+
+const SdfConfig& SdfNet::config() const { return impl_->cfg; }
+
+int SdfNet::init(const SdfConfig& cfg) {
+  NEFII_CHECK_ARG(cfg.d_in == 3, "sdf: d_in must be 3");
+  NEFII_CHECK_ARG(cfg.n_freqs >= 0 && cfg.n_freqs <= 10, "sdf: n_freqs out of range");
+  NEFII_CHECK_ARG(cfg.width >= 64 && cfg.width % 64 == 0 && cfg.width <= 1024, "sdf: width must be a multiple of 64 in [64,1024]");
+  NEFII_CHECK_ARG(cfg.n_hidden >= 2 && cfg.n_hidden <= 16, "sdf: n_hidden out of range");
+  NEFII_CHECK_ARG(cfg.skip_layer < cfg.n_hidden, "sdf: skip_layer out of range");
+  NEFII_CHECK_ARG(cfg.d_out == 1, "sdf: d_out must be 1 (use_last_as_f layout)");
+  Impl& s = *impl_;
+  s.cfg = cfg;
+  s.d_pe = 3 + 6 * cfg.n_freqs;
+  NEFII_CHECK_ARG(s.d_pe <= 64, "sdf: positional encoding wider than 64 is not supported");
+  s.n_lin = cfg.n_hidden + 1;
+  s.in_dim.assign(s.n_lin, cfg.width);
+  s.out_dim.assign(s.n_lin, cfg.width);
+  s.in_dim[0] = s.d_pe;
+  s.out_dim[s.n_lin - 1] = cfg.d_out;
+  if (cfg.skip_layer > 0) s.out_dim[cfg.skip_layer - 1] = cfg.width - s.d_pe;
+  s.k_pad.resize(s.n_lin);
+  s.n_pad.resize(s.n_lin);
+  size_t bytes = 0;
+  auto take = [&](size_t n) { size_t o = bytes; bytes += (n + 255) / 256 * 256; return o; };
+  std::vector<size_t> off_fh(s.n_lin), off_fl(s.n_lin), off_bh(s.n_lin), off_bl(s.n_lin), off_bias(s.n_lin);
+  for (int l = 0; l < s.n_lin - 1; ++l) {
+    s.k_pad[l] = round_up(s.in_dim[l], 64);
+    s.n_pad[l] = round_up(s.out_dim[l], 256);
+    const size_t nf = (size_t)s.n_pad[l] * s.k_pad[l] * 2;
+    off_fh[l] = take(nf); off_fl[l] = take(nf);
+    const size_t nb = (size_t)round_up(s.in_dim[l], 256) * round_up(s.out_dim[l], 64) * 2;
+    off_bh[l] = take(nb); off_bl[l] = take(nb);
+    off_bias[l] = take((size_t)s.out_dim[l] * 4);
+  }
+  const size_t off_wl = take((size_t)cfg.d_out * cfg.width * 4);
+  const size_t off_bl_last = take((size_t)cfg.d_out * 4);
+  if (s.blob) cudaFree(s.blob);
+  NEFII_CUDA(cudaMalloc(&s.blob, bytes));
+  NEFII_CUDA(cudaMemset(s.blob, 0, bytes));
+  char* base = (char*)s.blob;
+  s.w_fwd.resize(s.n_lin - 1);
+  s.w_bwd.resize(s.n_lin - 1);
+  s.bias.resize(s.n_lin - 1);
+  for (int l = 0; l < s.n_lin - 1; ++l) {
+    s.w_fwd[l].hi = (__nv_bfloat16*)(base + off_fh[l]);
+    s.w_fwd[l].lo = (__nv_bfloat16*)(base + off_fl[l]);
+    s.w_fwd[l].ld = s.k_pad[l];
+    s.w_bwd[l].hi = (__nv_bfloat16*)(base + off_bh[l]);
+    s.w_bwd[l].lo = (__nv_bfloat16*)(base + off_bl[l]);
+    s.w_bwd[l].ld = round_up(s.out_dim[l], 64);
+    s.bias[l] = (float*)(base + off_bias[l]);
+  }
+  s.w_last = (float*)(base + off_wl);
+  s.b_last = (float*)(base + off_bl_last);
+  s.has_weights = false;
+  return NEFII_OK;
+}
+
+int SdfNet::set_weights(cudaStream_t stream, const float* const* weights, const float* const* biases) {
+  Impl& s = *impl_;
+  NEFII_CHECK_ARG(s.blob != nullptr, "sdf: set_weights before init");
+  for (int l = 0; l < s.n_lin; ++l) NEFII_CHECK_ARG(weights[l] && biases[l], "sdf: null weight pointer for layer %d", l);
+  int rc;
+  for (int l = 0; l < s.n_lin - 1; ++l) {
+    if ((rc = split_to_planes(stream, weights[l], s.out_dim[l], s.in_dim[l], s.in_dim[l], 0, 1.f, s.w_fwd[l].hi,
+                              s.w_fwd[l].lo, s.n_pad[l], s.k_pad[l])))
+      return rc;
+    if ((rc = split_to_planes(stream, weights[l], s.out_dim[l], s.in_dim[l], s.in_dim[l], 1, 1.f, s.w_bwd[l].hi,
+                              s.w_bwd[l].lo, round_up(s.in_dim[l], 256), round_up(s.out_dim[l], 64))))
+      return rc;
+    NEFII_CUDA(cudaMemcpyAsync(s.bias[l], biases[l], (size_t)s.out_dim[l] * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  NEFII_CUDA(cudaMemcpyAsync(s.w_last, weights[s.n_lin - 1], (size_t)s.cfg.d_out * s.cfg.width * 4, cudaMemcpyDeviceToDevice, stream));
+  NEFII_CUDA(cudaMemcpyAsync(s.b_last, biases[s.n_lin - 1], (size_t)s.cfg.d_out * 4, cudaMemcpyDeviceToDevice, stream));
+  s.has_weights = true;
+  return NEFII_OK;
+}
+
+// Workspace layout (all plane buffers hold hi then lo, [rows_cap, ld] bf16 each):
+//   in0 (ld 64) | act buffers (ld width): 2 when ping-ponging, n_hidden-1 + 2 when the gradient is needed
+//   | fp32 g0 [rows, 64] | fp32 g_skip [rows, 64]
+size_t SdfNet::workspace_bytes(int rows_cap, bool with_grad) const {
+  const Impl& s = *impl_;
+  const size_t rows = (size_t)round_up(rows_cap > 0 ? rows_cap : 1, 128);
+  const size_t plane_w = rows * s.cfg.width * 2 * 2;
+  const size_t plane_0 = rows * 64 * 2 * 2;
+  const int n_act = with_grad ? (s.cfg.n_hidden - 1) + 2 : 2;
+  size_t b = plane_0 + (size_t)n_act * plane_w;
+  if (with_grad) b += 2 * rows * 64 * 4;
+  return b + 1024;
+}
+
+int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const float* x, void* workspace, size_t ws_bytes,
+                 float* sdf, float* feat, float* grad) const {
+  const Impl& s = *impl_;
+  NEFII_CHECK_ARG(s.has_weights, "sdf: eval before set_weights");
+  if (rows_cap <= 0) return NEFII_OK;
+  NEFII_CHECK_ARG(x && sdf && workspace, "sdf: null pointer");
+  const bool with_grad = grad != nullptr;
+  NEFII_CHECK_ARG(ws_bytes >= workspace_bytes(rows_cap, with_grad), "sdf: workspace too small (%zu < %zu)", ws_bytes,
+                  workspace_bytes(rows_cap, with_grad));
+  const int W = s.cfg.width, H = s.cfg.n_hidden, skip = s.cfg.skip_layer;
+  const size_t rows = (size_t)round_up(rows_cap, 128);
+  char* p = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  auto planes = [&](int ld) {
+    Planes pl;
+    pl.hi = (__nv_bfloat16*)p; p += rows * ld * 2;
+    pl.lo = (__nv_bfloat16*)p; p += rows * ld * 2;
+    pl.ld = ld;
+    return pl;
+  };
+  Planes in0 = planes(64);
+  const int n_act = with_grad ? (H - 1) + 2 : 2;
+  std::vector<Planes> act(n_act);
+  for (int i = 0; i < n_act; ++i) act[i] = planes(W);
+  float* g0 = nullptr;
+  float* g_skip = nullptr;
+  if (with_grad) {
+    g0 = (float*)p; p += rows * 64 * 4;
+    g_skip = (float*)p; p += rows * 64 * 4;
+  }
+  // input planes of hidden layer l (l >= 1)
+  auto in_of = [&](int l) -> Planes& { return with_grad ? act[l - 1] : act[(l - 1) & 1]; };
+
+  const int ew_blocks = kNumSMs * 8;
+  int rc;
+  encode_kernel<<<ew_blocks, 256, 0, stream>>>(x, count, rows_cap, s.d_pe, 1.f, in0, 0, 64);
+  NEFII_LAUNCH_CHECK();
+
+  // ---------------------------------------------------------------- forward
+  Planes seed;  // gradient seed G_{H-1}
+  if (with_grad) seed = act[H - 1];
+  for (int l = 0; l < H; ++l) {
+    if (l + 1 == skip) {
+      // the skip layer's input = [h / sqrt2 | PE / sqrt2]; its PE columns are free from now on
+      encode_kernel<<<ew_blocks, 256, 0, stream>>>(x, count, rows_cap, s.d_pe, kInvSqrt2, in_of(skip), W - s.d_pe, 0);
+      NEFII_LAUNCH_CHECK();
+    }
+    GemmProblem g{};
+    const Planes& a = (l == 0) ? in0 : in_of(l);
+    g.a_hi = a.hi; g.a_lo = a.lo; g.a_ld = a.ld; g.rows_cap = rows_cap;
+    g.b_hi = s.w_fwd[l].hi; g.b_lo = s.w_fwd[l].lo; g.b_ld = s.w_fwd[l].ld; g.n_pad = s.n_pad[l];
+    g.k_pad = s.k_pad[l];
+    g.count = count;
+    g.epi.mode = 0;
+    g.epi.act = ACT_SOFTPLUS100;
+    g.epi.n_valid = s.out_dim[l];
+    g.epi.bias = s.bias[l];
+    if (l < H - 1) {
+      g.epi.dst = in_of(l + 1);
+      g.epi.dst_ncols = s.out_dim[l];
+      g.epi.out_scale = (l + 1 == skip) ? kInvSqrt2 : 1.f;
+    } else {
+      g.epi.w_last = s.w_last; g.epi.b_last = s.b_last; g.epi.n_last = s.cfg.d_out; g.epi.w_last_ld = W;
+      g.epi.dst_last = sdf;
+      if (feat) { g.epi.dst_f32 = feat; g.epi.f32_ld = W; g.epi.f32_begin = 0; g.epi.f32_end = W; }
+      if (with_grad) g.epi.seed = seed;
+    }
+    if ((rc = gemm_split_bf16(stream, g))) return rc;
+  }
+  if (!with_grad) return NEFII_OK;
+
+  // ---------------------------------------------------------------- reverse chain for d sdf / d x
+  // G_l = d sdf / d z_l as planes; G_{H-1} = seed.  For l = H-1 .. 1:  G_{l-1} = (G_l W_l) * act'(z_{l-1})
+  Planes cur = seed;
+  Planes spare = act[H];
+  for (int l = H - 1; l >= 1; --l) {
+    GemmProblem g{};
+    g.a_hi = cur.hi; g.a_lo = cur.lo; g.a_ld = cur.ld; g.rows_cap = rows_cap;
+    g.b_hi = s.w_bwd[l].hi; g.b_lo = s.w_bwd[l].lo; g.b_ld = s.w_bwd[l].ld; g.n_pad = round_up(s.in_dim[l], 256);
+    g.k_pad = round_up(s.out_dim[l], 64);
+    g.count = count;
+    g.epi.mode = 1;
+    g.epi.act = ACT_SOFTPLUS100;
+    g.epi.n_valid = s.in_dim[l];
+    const Planes& saved = in_of(l);   // forward input of layer l == activation output of layer l-1 (scaled at the skip)
+    g.epi.sav_hi = saved.hi; g.epi.sav_lo = saved.lo; g.epi.sav_ld = saved.ld;
+    g.epi.dst = spare;
+    if (l == skip) {
+      g.epi.sav_ncols = W - s.d_pe; g.epi.sav_scale = kSqrt2;
+      g.epi.out_scale = kInvSqrt2;
+      g.epi.dst_ncols = W - s.d_pe;
+      g.epi.dst_zero_to = round_up(W - s.d_pe, 64);   // K padding of the next GEMM must be finite zeros
+      g.epi.dst_f32 = g_skip; g.epi.f32_ld = 64; g.epi.f32_begin = W - s.d_pe; g.epi.f32_end = W;
+    } else {
+      g.epi.sav_ncols = s.in_dim[l]; g.epi.sav_scale = 1.f;
+      g.epi.dst_ncols = s.in_dim[l];
+    }
+    if ((rc = gemm_split_bf16(stream, g))) return rc;
+    Planes t = cur; cur = spare; spare = t;
+  }
+  {
+    GemmProblem g{};   // layer 0: gradient w.r.t. the encoding, fp32 out
+    g.a_hi = cur.hi; g.a_lo = cur.lo; g.a_ld = cur.ld; g.rows_cap = rows_cap;
+    g.b_hi = s.w_bwd[0].hi; g.b_lo = s.w_bwd[0].lo; g.b_ld = s.w_bwd[0].ld; g.n_pad = round_up(s.in_dim[0], 256);
+    g.k_pad = round_up(s.out_dim[0], 64);
+    g.count = count;
+    g.epi.mode = 1;
+    g.epi.act = ACT_NONE;
+    g.epi.n_valid = s.d_pe;
+    g.epi.dst_f32 = g0; g.epi.f32_ld = 64; g.epi.f32_begin = 0; g.epi.f32_end = s.d_pe;
+    if ((rc = gemm_split_bf16(stream, g))) return rc;
+  }
+  pe_backward_kernel<<<ceil_div(rows_cap, 128), 128, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, g0,
+                                                                  skip > 0 ? g_skip : nullptr, 64, grad);
+  NEFII_LAUNCH_CHECK();
+  return NEFII_OK;
+}
+
+}  // namespace nefii

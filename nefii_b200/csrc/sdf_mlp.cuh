@@ -1,0 +1,34 @@
+// SDF / feature MLP handle (see sdf_mlp.cu).
+#pragma once
+#include "common.cuh"
+
+namespace nefii {
+
+struct SdfConfig {
+  int d_in = 3;
+  int n_freqs = 6;      // positional-encoding frequencies (multires)
+  int width = 512;      // hidden width == feature size
+  int n_hidden = 8;     // Linear+Softplus layers before the 1-wide output layer
+  int skip_layer = 4;   // layer whose input is cat([h, PE]) / sqrt(2); <= 0: none
+  int d_out = 1;
+};
+
+class SdfNet {
+ public:
+  SdfNet();
+  ~SdfNet();
+  int init(const SdfConfig& cfg);
+  // weights[l]: device fp32 [out_l, in_l] (weight-norm already folded), biases[l]: [out_l]; l = 0..n_hidden
+  int set_weights(cudaStream_t stream, const float* const* weights, const float* const* biases);
+  size_t workspace_bytes(int rows_cap, bool with_grad) const;
+  // x [rows,3] -> sdf [rows], feat [rows,width] (optional), grad [rows,3] (optional)
+  int eval(cudaStream_t stream, int rows_cap, const int* count, const float* x, void* workspace, size_t ws_bytes,
+           float* sdf, float* feat, float* grad) const;
+  const SdfConfig& config() const;
+
+ private:
+  struct Impl;
+  Impl* impl_;
+};
+
+}  // namespace nefii

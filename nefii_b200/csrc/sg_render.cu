@@ -128,9 +128,9 @@ int sg_render_fwd(cudaStream_t stream, int n_rays, int n_sg, int n_mat, const fl
                   const float* blend, float* out_rgb, float* out_spec, float* out_diff) {
   NEFII_CHECK_ARG(n_rays >= 0 && n_sg > 0 && n_mat > 0 && n_mat <= kMaxMaterials,
                   "sg_render_fwd: bad sizes n_rays=%d n_sg=%d n_mat=%d", n_rays, n_sg, n_mat);
+  if (n_rays == 0) return NEFII_OK;
   NEFII_CHECK_ARG(lgt && spec && rough && albedo && normal && view && out_rgb && out_spec && out_diff,
                   "sg_render_fwd: null pointer");
-  if (n_rays == 0) return NEFII_OK;
   const size_t smem = sizeof(LightSG<float>) * (size_t)n_sg;
   NEFII_CHECK_ARG(smem <= 200 * 1024, "sg_render_fwd: too many light SGs (%d)", n_sg);
   // Small batches: a full warp per ray keeps all SMs busy; large batches: 4 lanes per ray so the

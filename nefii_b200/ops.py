@@ -20,7 +20,7 @@ class GemmDesc(ctypes.Structure):
         ("mode", c_int), ("act", c_int), ("n_valid", c_int),
         ("bias", c_void_p),
         ("out_scale", c_float),
-        ("dst_hi", c_void_p), ("dst_lo", c_void_p), ("dst_ld", c_int), ("dst_col0", c_int), ("dst_ncols", c_int),
+        ("dst_hi", c_void_p), ("dst_lo", c_void_p), ("dst_ld", c_int), ("dst_col0", c_int), ("dst_ncols", c_int), ("dst_zero_to", c_int),
         ("dst_f32", c_void_p), ("f32_ld", c_int), ("f32_begin", c_int), ("f32_end", c_int),
         ("w_last", c_void_p), ("b_last", c_void_p), ("n_last", c_int), ("w_last_ld", c_int), ("dst_last", c_void_p),
         ("seed_hi", c_void_p), ("seed_lo", c_void_p), ("seed_ld", c_int),
@@ -78,3 +78,68 @@ def gemm_split_bf16(a, b, k_pad, n_valid, *, mode=0, act=ACT_NONE, bias=None, ou
         d.sav_hi, d.sav_lo, d.sav_ld = _p(sav[0]), _p(sav[1]), sav[0].stride(0)
         d.sav_ncols, d.sav_scale = sav_ncols, sav_scale
     _lib.check(_lib.raw().nefii_gemm_split_bf16(_lib.stream_ptr(a[0].device), ctypes.byref(d)))
+
+
+class SdfConfig(ctypes.Structure):
+    """Mirror of ``nefii_sdf_config``."""
+    _fields_ = [("d_in", c_int), ("n_freqs", c_int), ("width", c_int), ("n_hidden", c_int),
+                ("skip_layer", c_int), ("d_out", c_int)]
+
+
+class SdfMlp:
+    """Owner of a ``nefii_sdf_*`` handle: packed weights live in the library, workspaces are torch tensors."""
+
+    def __init__(self, n_freqs=6, width=512, n_hidden=8, skip_layer=4, device=None):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.cfg = SdfConfig(3, n_freqs, width, n_hidden, skip_layer, 1)
+        self.width, self.n_hidden = width, n_hidden
+        h = c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.raw().nefii_sdf_create(ctypes.byref(h), ctypes.byref(self.cfg)))
+        self._h = h
+        self._ws = None
+        self._keep = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.raw().nefii_sdf_destroy(h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_weights(self, weights, biases):
+        """weights[l]: effective fp32 [out_l, in_l] CUDA tensors (weight norm folded)."""
+        n = self.n_hidden + 1
+        assert len(weights) == n and len(biases) == n
+        ws = [_lib.f32c(w) for w in weights]
+        bs = [_lib.f32c(b) for b in biases]
+        wp = (c_void_p * n)(*[w.data_ptr() for w in ws])
+        bp = (c_void_p * n)(*[b.data_ptr() for b in bs])
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.raw().nefii_sdf_set_weights(self._h, _lib.stream_ptr(self.device), wp, bp))
+        self._keep = (ws, bs)   # keep sources alive until the async copies have been ordered on the stream
+
+    def workspace(self, rows_cap, with_grad):
+        need = int(_lib.raw().nefii_sdf_workspace_bytes(self._h, int(rows_cap), 1 if with_grad else 0))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def eval(self, x, want_feat=False, want_grad=False, count=None):
+        """x [N,3] -> (sdf [N], feat [N,width] | None, grad [N,3] | None)."""
+        x = _lib.f32c(x).reshape(-1, 3)
+        n = x.shape[0]
+        sdf = torch.empty(n, device=x.device, dtype=torch.float32)
+        feat = torch.empty(n, self.width, device=x.device, dtype=torch.float32) if want_feat else None
+        grad = torch.empty(n, 3, device=x.device, dtype=torch.float32) if want_grad else None
+        if n == 0:
+            return sdf, feat, grad
+        ws = self.workspace(n, want_grad)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.raw().nefii_sdf_eval(
+                self._h, _lib.stream_ptr(self.device), n, _p(count), x.data_ptr(), ws.data_ptr(), ws.numel(),
+                sdf.data_ptr(), _p(feat), _p(grad)))
+        return sdf, feat, grad

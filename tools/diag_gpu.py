@@ -75,6 +75,36 @@ def diag_gemm():
             print("   torch fp32 linear+softplus: %.4f ms" % ms_t)
 
 
+def diag_sdf():
+    from nefii_b200 import ops
+    from oracle import mlp
+    dev = torch.device("cuda:0")
+    params = mlp.sdf_init(seed=1, bumps=0.3)
+    net = ops.SdfMlp(device=dev)
+    net.set_weights([w.to(dev) for w in params.W], [b.to(dev) for b in params.b])
+    p32 = params.to(dev)
+    p64 = params.to(dev, torch.float64)
+    for n in (4096, 131072, 1 << 20):
+        x = (torch.rand(n, 3, device=dev) * 1.8 - 0.9)
+        ms_f = ev_time(lambda: net.eval(x), iters=10)
+        ms_g = ev_time(lambda: net.eval(x, want_feat=True, want_grad=True), iters=10)
+        print("SDF n=%d fwd %.3f ms (%.1f TFLOP/s alg) fwd+grad %.3f ms (%.1f TFLOP/s alg)" % (
+            n, ms_f, n * 3.671e6 / ms_f / 1e9, ms_g, n * 7.342e6 / ms_g / 1e9))
+        if n <= 131072:
+            ms_t = ev_time(lambda: mlp.sdf_forward(p32, x), iters=5)
+            sdf, feat, grad = net.eval(x, want_feat=True, want_grad=True)
+            r64 = mlp.sdf_forward(p64, x.double())
+            r32 = mlp.sdf_forward(p32, x)
+            g64 = mlp.sdf_gradient(p64, x.double())
+            g32 = mlp.sdf_gradient(p32, x)
+            print("   torch fp32 fwd %.3f ms | sdf err vs f64: ours max %.2e mean %.2e ; torch fp32 max %.2e mean %.2e" % (
+                ms_t, (sdf.double() - r64[:, 0]).abs().max().item(), (sdf.double() - r64[:, 0]).abs().mean().item(),
+                (r32[:, 0].double() - r64[:, 0]).abs().max().item(), (r32[:, 0].double() - r64[:, 0]).abs().mean().item()))
+            print("   grad rel err vs f64: ours max %.2e ; torch fp32 max %.2e" % (
+                ((grad.double() - g64).norm(dim=-1) / g64.norm(dim=-1)).max().item(),
+                ((g32.double() - g64).norm(dim=-1) / g64.norm(dim=-1)).max().item()))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["sg", "gemm"]
     print(torch.cuda.get_device_name(0))
