@@ -10,7 +10,7 @@
 // One CTA owns a 128-row tile of points and loops over the output columns in chunks of 256:
 //   warp 0      : TMA producer (A/B hi+lo tiles, 128B swizzle, 2-stage mbarrier ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (2 x 256-column accumulators)
-//   warps 2..9  : epilogue (tcgen05.ld -> bias/activation/derivative -> bf16 planes / fp32 / fused
+//   warps 4..11 : epilogue (tcgen05.ld -> bias/activation/derivative -> bf16 planes / fp32 / fused
 //                 output layer), overlapped with the MMAs of the next column chunk.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -29,7 +29,7 @@ constexpr int kATileBytes = BM * BK * 2;   // 16 KB
 constexpr int kBTileBytes = BN * BK * 2;   // 32 KB
 constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;  // 96 KB
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + kEpiWarps * 32;  // 320
+constexpr int kThreads = 128 + kEpiWarps * 32;  // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1,2: epilogue
 constexpr int kTmemCols = 512;
 constexpr int kMaxLast = 4;
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ +
@@ -98,6 +98,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row atoms of 1024 B).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -112,29 +123,35 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M=128, N=256
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-__device__ __forceinline__ float softplus100(float v) {
-  float t = 100.f * v;
-  if (t > 20.f) return v;
-  float e = __expf(t);
-  float l = (e < 1e-3f) ? e * (1.f - 0.5f * e) : __logf(1.f + e);
-  return l * 0.01f;
+// ---- branch-free activation helpers (fast intrinsics: the error they add, <= 1e-9 absolute on a
+// softplus output, is far below the bf16x3 product error; the SG kernels never use them) ----------
+template <int ACT> __device__ __forceinline__ float act_fwd(float v) {
+  if (ACT == ACT_SOFTPLUS100) {
+    const float t = 100.f * v;
+    const float e = __expf(fminf(t, 20.f));
+    const float l = (e < 1e-3f) ? e * (1.f - 0.5f * e) : __logf(1.f + e);
+    return (t > 20.f) ? v : 0.01f * l;
+  } else if (ACT == ACT_RELU) {
+    return fmaxf(v, 0.f);
+  } else if (ACT == ACT_ELU) {
+    const float m = fminf(v, 0.f);
+    const float em = (m > -1e-2f) ? m * (1.f + m * (0.5f + 0.16666667f * m)) : __expf(m) - 1.f;
+    return (v > 0.f) ? v : em;
+  }
+  return v;
 }
 // derivative of the activation recovered from its saved output h
-__device__ __forceinline__ float dact_from_output(int act, float h) {
-  if (act == ACT_SOFTPLUS100) {
-    float u = 100.f * h;   // sigmoid(100 z) = 1 - exp(-100 h)
-    if (u < 0.01f) return u * (1.f - 0.5f * u + 0.16666667f * u * u);
-    return 1.f - __expf(-u);
+template <int ACT> __device__ __forceinline__ float act_bwd_from_output(float h) {
+  if (ACT == ACT_SOFTPLUS100) {
+    const float u = 100.f * h;   // sigmoid(100 z) = 1 - exp(-100 h)
+    const float small = u * (1.f - 0.5f * u + 0.16666667f * u * u);
+    return (u < 0.01f) ? small : 1.f - __expf(-u);
+  } else if (ACT == ACT_RELU) {
+    return h > 0.f ? 1.f : 0.f;
+  } else if (ACT == ACT_ELU) {
+    return h > 0.f ? 1.f : h + 1.f;
   }
-  if (act == ACT_RELU) return h > 0.f ? 1.f : 0.f;
-  if (act == ACT_ELU) return h > 0.f ? 1.f : h + 1.f;
   return 1.f;
-}
-__device__ __forceinline__ float apply_act(int act, float v) {
-  if (act == ACT_SOFTPLUS100) return softplus100(v);
-  if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_ELU) return v > 0.f ? v : expm1f(v);
-  return v;
 }
 
 __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -142,44 +159,156 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// store 32 consecutive values of one row as planes; vectorised when the whole run is in range
-__device__ __forceinline__ void store_planes32(const Planes& dst, long long row, int col_base, int n0, int n_limit,
+// pack 8 floats into 8 bf16 hi (uint4) + 8 bf16 lo (uint4)
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t wh[4], wl[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    wh[j] = *reinterpret_cast<const uint32_t*>(&h2);
+    wl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  hi = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+  lo = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+}
+
+// Store 32 consecutive values of one row as planes starting at plane column `col` (= col_base + n0);
+// elements with n0 + j >= n_limit are not written.  16-byte stores when a group of 8 is complete and aligned.
+__device__ __forceinline__ void store_planes32(const Planes& dst, long long row, int col, int n0, int n_limit,
                                                const float* vals) {
-  __nv_bfloat16* ph = dst.hi + row * dst.ld + col_base + n0;
-  __nv_bfloat16* pl = dst.lo + row * dst.ld + col_base + n0;
-  if (n0 + 32 <= n_limit && ((col_base + n0) & 7) == 0) {
+  __nv_bfloat16* ph = dst.hi + row * dst.ld + col;
+  __nv_bfloat16* pl = dst.lo + row * dst.ld + col;
+  const bool aligned = (col & 7) == 0;
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      uint32_t wh[4], wl[4];
+  for (int g = 0; g < 4; ++g) {
+    if (aligned && n0 + 8 * g + 8 <= n_limit) {
+      uint4 h, l;
+      split8(vals + 8 * g, h, l);
+      *reinterpret_cast<uint4*>(ph + 8 * g) = h;
+      *reinterpret_cast<uint4*>(pl + 8 * g) = l;
+    } else if (n0 + 8 * g < n_limit) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split2(vals[v * 8 + 2 * j], h0, l0);
-        split2(vals[v * 8 + 2 * j + 1], h1, l1);
-        wh[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        wl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-      }
-      *reinterpret_cast<uint4*>(ph + v * 8) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-      *reinterpret_cast<uint4*>(pl + v * 8) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (n0 + j < n_limit) {
-        __nv_bfloat16 h, l;
-        split2(vals[j], h, l);
-        ph[j] = h;
-        pl[j] = l;
+      for (int j = 0; j < 8; ++j) {
+        if (n0 + 8 * g + j < n_limit) {
+          __nv_bfloat16 h, l;
+          split2(vals[8 * g + j], h, l);
+          ph[8 * g + j] = h;
+          pl[8 * g + j] = l;
+        }
       }
     }
   }
 }
 
+// fp32 side output of columns [begin, end): dst[row * ld + n - begin]
+__device__ __forceinline__ void store_f32_32(float* dst, int ld, long long row, int n0, int begin, int end,
+                                             const float* vals) {
+  float* p = dst + row * ld + (n0 - begin);
+  const bool aligned = (((size_t)p) & 15) == 0;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int n = n0 + 4 * g;
+    if (aligned && n >= begin && n + 4 <= end) {
+      *reinterpret_cast<float4*>(p + 4 * g) = make_float4(vals[4 * g], vals[4 * g + 1], vals[4 * g + 2], vals[4 * g + 3]);
+    } else if (n + 4 > begin && n < end) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j >= begin && n + j < end) p[4 * g + j] = vals[4 * g + j];
+    }
+  }
+}
+
+constexpr int kColsPerWarp = BN / 2;   // each epilogue warp owns one TMEM lane quarter x 128 columns
+
+// Final per-tile math on the fp32 sums of one 32-column group held in registers (v[0..31]).
+template <int MODE, int ACT, bool FUSE>
+__device__ __forceinline__ void finish_group(const GemmEpilogue& epi, float* v, int n0, long long row, bool row_ok,
+                                             float* part) {
+  if (MODE == 0) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = n0 + j;
+      const bool real = n < epi.n_valid;
+      const float b = (epi.bias != nullptr && real) ? __ldg(epi.bias + n) : 0.f;
+      const float h = act_fwd<ACT>(v[j] + b);
+      v[j] = real ? h : 0.f;
+    }
+    if (FUSE) {
+#pragma unroll
+      for (int q = 0; q < kMaxLast; ++q) {
+        if (q < epi.n_last) {
+          float acc = part[q];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + j;
+            const float w = (n < epi.n_valid) ? __ldg(epi.w_last + (size_t)q * epi.w_last_ld + n) : 0.f;
+            acc = fmaf(v[j], w, acc);
+          }
+          part[q] = acc;
+        }
+      }
+      if (epi.seed.hi != nullptr && row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float sv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = n0 + 8 * g + j;
+            const float w = (n < epi.n_valid) ? __ldg(epi.w_last + n) : 0.f;
+            sv[j] = w * act_bwd_from_output<ACT>(v[8 * g + j]);
+          }
+          // the seed buffer is a full-width plane buffer: 16-byte stores are always aligned and in range
+          uint4 h, l;
+          split8(sv, h, l);
+          *reinterpret_cast<uint4*>(epi.seed.hi + row * epi.seed.ld + n0 + 8 * g) = h;
+          *reinterpret_cast<uint4*>(epi.seed.lo + row * epi.seed.ld + n0 + 8 * g) = l;
+        }
+      }
+    }
+  } else {
+    if (epi.sav_hi != nullptr && row_ok && n0 < epi.sav_ncols) {
+      const uint4* sh = reinterpret_cast<const uint4*>(epi.sav_hi + row * epi.sav_ld + n0);
+      const uint4* sl = reinterpret_cast<const uint4*>(epi.sav_lo + row * epi.sav_ld + n0);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint4 h4 = __ldg(sh + g), l4 = __ldg(sl + g);
+        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+          const float2 lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[j]));
+          const int n = n0 + 8 * g + 2 * j;
+          const float d0 = act_bwd_from_output<ACT>((hf.x + lf.x) * epi.sav_scale);
+          const float d1 = act_bwd_from_output<ACT>((hf.y + lf.y) * epi.sav_scale);
+          v[8 * g + 2 * j] *= (n < epi.sav_ncols) ? d0 : 1.f;
+          v[8 * g + 2 * j + 1] *= (n + 1 < epi.sav_ncols) ? d1 : 1.f;
+        }
+      }
+    }
+  }
+  if (!row_ok) return;
+  if (epi.dst_f32 != nullptr && n0 < epi.f32_end && n0 + 32 > epi.f32_begin)
+    store_f32_32(epi.dst_f32, epi.f32_ld, row, n0, epi.f32_begin, epi.f32_end, v);
+  const int dst_end = epi.dst_zero_to > epi.dst_ncols ? epi.dst_zero_to : epi.dst_ncols;
+  if (epi.dst.hi != nullptr && n0 < dst_end) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (n0 + j < epi.dst_ncols) ? v[j] * epi.out_scale : 0.f;
+    store_planes32(epi.dst, row, epi.dst_col0 + n0, n0, dst_end, v);
+  }
+}
+
+// Accumulation scheme (accuracy): tcgen05 adds into its fp32 accumulator with truncation, which biases long
+// sums (measured: -4 ulp at K=512, -39 ulp at K=2048, tools/diag_gpu.py trunc).  Every 64-wide K block is
+// therefore multiplied into a *fresh* TMEM buffer (the two small cross terms first, hi*hi last) and the
+// partial products are summed across K blocks by the epilogue warps in registers with round-to-nearest.
+template <int MODE, int ACT, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const int* __restrict__ count_ptr, int rows_cap, int k_blocks, int n_chunks,
-                       const GemmEpilogue epi) {
+                       const __grid_constant__ GemmEpilogue epi) {
   const int m_tile = blockIdx.x;
   int m_limit = rows_cap;
   if (count_ptr != nullptr) {
@@ -192,7 +321,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* tiles = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
-  // bars[0..1] full, [2..3] empty, [4..5] tmem_full, [6..7] tmem_empty ; then tmem base slot
+  // bars[0..1] smem full, [2..3] smem empty, [4..5] tmem full, [6..7] tmem empty ; then the TMEM base slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* s_last = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes + 256);   // [2][BM][kMaxLast]
 
@@ -218,7 +347,12 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int total_kb = n_chunks * k_blocks;
 
+  // Register re-partitioning (168 regs/thread at launch): the role warpgroup keeps 40, each epilogue
+  // warpgroup grows to 232 so the 128 fp32 partial sums per thread stay in registers.
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
@@ -243,115 +377,82 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int nc = 0; nc < n_chunks; ++nc) {
-        const int buf = nc & 1;
-        const uint32_t use = (uint32_t)(nc >> 1);
-        mbar_wait(smem_u32(&bars[6 + buf]), (use & 1) ^ 1);   // epilogue has drained this accumulator
+      for (int it = 0; it < total_kb; ++it) {
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&bars[6 + buf]), (((uint32_t)it >> 1) & 1) ^ 1);   // partial sums of 2 blocks ago were read
+        mbar_wait(smem_u32(&bars[0 + stage]), phase);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(smem_u32(&bars[0 + stage]), phase);
-          tc_fence_after();
-          const uint32_t st = smem_u32(tiles + (size_t)stage * kStageBytes);
-          const uint64_t a_hi = make_smem_desc(st);
-          const uint64_t a_lo = make_smem_desc(st + kATileBytes);
-          const uint64_t b_hi = make_smem_desc(st + 2 * kATileBytes);
-          const uint64_t b_lo = make_smem_desc(st + 2 * kATileBytes + kBTileBytes);
+        const uint32_t st = smem_u32(tiles + (size_t)stage * kStageBytes);
+        const uint64_t a_hi = make_smem_desc(st);
+        const uint64_t a_lo = make_smem_desc(st + kATileBytes);
+        const uint64_t b_hi = make_smem_desc(st + 2 * kATileBytes);
+        const uint64_t b_lo = make_smem_desc(st + 2 * kATileBytes + kBTileBytes);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step inside the swizzle row
-            tc_mma_bf16(tmem_d, a_hi + koff, b_hi + koff, kIdesc, (kb | k) != 0);
-            tc_mma_bf16(tmem_d, a_hi + koff, b_lo + koff, kIdesc, 1);
-            tc_mma_bf16(tmem_d, a_lo + koff, b_hi + koff, kIdesc, 1);
-          }
-          tc_commit(smem_u32(&bars[2 + stage]));   // frees the smem stage once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step inside the swizzle row
+          tc_mma_bf16(tmem_d, a_hi + koff, b_lo + koff, kIdesc, k != 0);
+          tc_mma_bf16(tmem_d, a_lo + koff, b_hi + koff, kIdesc, 1);
         }
-        tc_commit(smem_u32(&bars[4 + buf]));       // accumulator ready for the epilogue
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+          tc_mma_bf16(tmem_d, a_hi + koff, b_hi + koff, kIdesc, 1);
+        }
+        tc_commit(smem_u32(&bars[2 + stage]));   // frees the smem stage once these MMAs retire
+        tc_commit(smem_u32(&bars[4 + buf]));     // this K block's partial product is ready
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
+  }
   } else {
     // ---------------------------------------------------------------- epilogue warps
-    const int e = warp - 2;             // 0..7
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+    const int e = warp - 4;             // 0..7
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int half = e >> 2;            // which 128-column half of the 256-column chunk
     const int row_in_tile = quarter * 32 + lane;
     const long long row = (long long)m_tile * BM + row_in_tile;
     const bool row_ok = row < m_limit;
     float part[kMaxLast] = {0.f, 0.f, 0.f, 0.f};
-    const int n_needed = epi.n_valid;   // columns beyond this are padding
-    const int n_loop = epi.dst_zero_to > n_needed ? epi.dst_zero_to : n_needed;
-
+    const int n_loop = epi.dst_zero_to > epi.n_valid ? epi.dst_zero_to : epi.n_valid;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kColsPerWarp);
+    float acc[kColsPerWarp];
+    int it = 0;
     for (int nc = 0; nc < n_chunks; ++nc) {
-      const int buf = nc & 1;
-      const uint32_t use = (uint32_t)(nc >> 1);
-      mbar_wait(smem_u32(&bars[4 + buf]), use & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        const int n0 = nc * BN + half * 128 + ch * 32;
-        if (n0 >= n_loop) break;        // warp-uniform
-        uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + half * 128 + ch * 32), r);
-        float outv[32];
-        float seedv[32];
-        if (epi.mode == 0) {
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&bars[4 + buf]), ((uint32_t)it >> 1) & 1);
+        tc_fence_after();
+        if (kb == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            float v = __uint_as_float(r[j]);
-            float h = 0.f;
-            if (n < n_needed) {
-              if (epi.bias) v += __ldg(epi.bias + n);
-              h = apply_act(epi.act, v);
-              if (epi.w_last) {
+          for (int c = 0; c < kColsPerWarp / 16; ++c) {
+            uint32_t r[16];
+            tc_ld16(t_lane + (uint32_t)(buf * BN + c * 16), r);
 #pragma unroll
-                for (int q = 0; q < kMaxLast; ++q)
-                  if (q < epi.n_last) part[q] = fmaf(h, __ldg(epi.w_last + (size_t)q * epi.w_last_ld + n), part[q]);
-                if (epi.seed.hi) seedv[j] = __ldg(epi.w_last + n) * dact_from_output(epi.act, h);
-              }
-            } else if (epi.seed.hi) {
-              seedv[j] = 0.f;
-            }
-            outv[j] = h;
+            for (int j = 0; j < 16; ++j) acc[c * 16 + j] = __uint_as_float(r[j]);
           }
         } else {
-          const bool has_sav = epi.sav_hi != nullptr && row_ok;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            float g = __uint_as_float(r[j]);
-            if (has_sav && n < epi.sav_ncols) {
-              const size_t off = (size_t)row * epi.sav_ld + n;
-              float h = (__bfloat162float(epi.sav_hi[off]) + __bfloat162float(epi.sav_lo[off])) * epi.sav_scale;
-              g *= dact_from_output(epi.act, h);
-            }
-            outv[j] = g;
+          for (int c = 0; c < kColsPerWarp / 16; ++c) {
+            uint32_t r[16];
+            tc_ld16(t_lane + (uint32_t)(buf * BN + c * 16), r);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c * 16 + j] += __uint_as_float(r[j]);
           }
         }
-        if (row_ok) {
-          if (epi.dst_f32 && n0 < epi.f32_end && n0 + 32 > epi.f32_begin) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = n0 + j;
-              if (n >= epi.f32_begin && n < epi.f32_end) epi.dst_f32[(size_t)row * epi.f32_ld + (n - epi.f32_begin)] = outv[j];
-            }
-          }
-          const int dst_end = epi.dst_zero_to > epi.dst_ncols ? epi.dst_zero_to : epi.dst_ncols;
-          if (epi.dst.hi && n0 < dst_end) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) outv[j] = (n0 + j < epi.dst_ncols) ? outv[j] * epi.out_scale : 0.f;
-            store_planes32(epi.dst, row, epi.dst_col0, n0, dst_end, outv);
-          }
-          if (epi.mode == 0 && epi.seed.hi) store_planes32(epi.seed, row, 0, n0, n_needed, seedv);
-        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[6 + buf]));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars[6 + buf]));
+#pragma unroll
+      for (int c = 0; c < kColsPerWarp / 32; ++c) {
+        const int n0 = nc * BN + half * kColsPerWarp + c * 32;
+        if (n0 < n_loop) finish_group<MODE, ACT, FUSE>(epi, acc + c * 32, n0, row, row_ok, part);
+      }
     }
 
-    if (epi.mode == 0 && epi.w_last != nullptr) {
+    if (MODE == 0 && FUSE) {
       // combine the two column halves of each row (deterministic order) and add the bias
 #pragma unroll
       for (int q = 0; q < kMaxLast; ++q) s_last[(half * BM + row_in_tile) * kMaxLast + q] = part[q];
@@ -442,16 +543,38 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   if ((rc = make_map(&ma_lo, p.a_lo, p.rows_cap, p.a_ld, p.k_pad, BM))) return rc;
   if ((rc = make_map(&mb_hi, p.b_hi, p.n_pad, p.b_ld, p.k_pad, BN))) return rc;
   if ((rc = make_map(&mb_lo, p.b_lo, p.n_pad, p.b_ld, p.k_pad, BN))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NEFII_CUDA(cudaFuncSetAttribute(gemm_split_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_set = true;
-  }
   const int n_chunks = ceil_div(p.epi.dst_zero_to > p.epi.n_valid ? p.epi.dst_zero_to : p.epi.n_valid, BN);
   NEFII_CHECK_ARG(n_chunks * BN <= p.n_pad, "gemm_split_bf16: dst_zero_to beyond n_pad");
+  NEFII_CHECK_ARG(p.epi.mode == 0 || p.epi.sav_hi == nullptr || p.epi.sav_ld >= n_chunks * BN || p.epi.sav_ncols % 32 == 0,
+                  "gemm_split_bf16: saved-activation rows must cover whole 32-column groups");
   const int grid = ceil_div(p.rows_cap, BM);
-  gemm_split_bf16_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p.count, p.rows_cap,
-                                                                 p.k_pad / BK, n_chunks, p.epi);
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const int*, int, int, int, GemmEpilogue);
+  KernelFn fn = nullptr;
+  const bool fuse = p.epi.mode == 0 && p.epi.w_last != nullptr;
+  NEFII_CHECK_ARG(!fuse || (p.epi.dst_last != nullptr && p.epi.n_last >= 1), "gemm_split_bf16: fused output layer needs dst_last");
+  NEFII_CHECK_ARG(p.epi.seed.hi == nullptr || fuse, "gemm_split_bf16: seed planes need the fused output layer");
+  const int key = (fuse ? 8 : 0) + p.epi.mode * 4 + p.epi.act;
+  switch (key) {
+    case 0: fn = gemm_split_bf16_kernel<0, ACT_NONE, false>; break;
+    case 1: fn = gemm_split_bf16_kernel<0, ACT_SOFTPLUS100, false>; break;
+    case 2: fn = gemm_split_bf16_kernel<0, ACT_RELU, false>; break;
+    case 3: fn = gemm_split_bf16_kernel<0, ACT_ELU, false>; break;
+    case 4: fn = gemm_split_bf16_kernel<1, ACT_NONE, false>; break;
+    case 5: fn = gemm_split_bf16_kernel<1, ACT_SOFTPLUS100, false>; break;
+    case 6: fn = gemm_split_bf16_kernel<1, ACT_RELU, false>; break;
+    case 7: fn = gemm_split_bf16_kernel<1, ACT_ELU, false>; break;
+    case 8: fn = gemm_split_bf16_kernel<0, ACT_NONE, true>; break;
+    case 9: fn = gemm_split_bf16_kernel<0, ACT_SOFTPLUS100, true>; break;
+    case 10: fn = gemm_split_bf16_kernel<0, ACT_RELU, true>; break;
+    case 11: fn = gemm_split_bf16_kernel<0, ACT_ELU, true>; break;
+    default: return set_error(NEFII_ERR_ARG, "gemm_split_bf16: bad mode/act (%d/%d)", p.epi.mode, p.epi.act);
+  }
+  static bool attr_set[12] = {};
+  if (!attr_set[key]) {
+    NEFII_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_set[key] = true;
+  }
+  fn<<<grid, kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p.count, p.rows_cap, p.k_pad / BK, n_chunks, p.epi);
   NEFII_LAUNCH_CHECK();
   return NEFII_OK;
 }

@@ -105,6 +105,42 @@ def diag_sdf():
                 ((g32.double() - g64).norm(dim=-1) / g64.norm(dim=-1)).max().item()))
 
 
+def diag_gemmprof():
+    from nefii_b200 import ops
+    dev = torch.device("cuda:0")
+    rows, k, n = 131072, 512, 512
+    x = torch.randn(rows, k, device=dev) * 0.3
+    w = torch.randn(n, k, device=dev) / k ** 0.5
+    bias = torch.zeros(n, device=dev)
+    a = ops.split_to_planes(x)
+    b = ops.split_to_planes(w)
+    dst = (torch.empty(rows, n, device=dev, dtype=torch.bfloat16), torch.empty(rows, n, device=dev, dtype=torch.bfloat16))
+    for _ in range(8):
+        ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n)
+    torch.cuda.synchronize()
+
+
+def diag_trunc():
+    """Is the fp32 accumulation inside tcgen05 biased (truncation)?  All-positive operands make a bias visible."""
+    from nefii_b200 import ops
+    dev = torch.device("cuda:0")
+    rows, n = 4096, 256
+    for k in (64, 512, 2048):
+        x = torch.rand(rows, k, device=dev) + 0.5
+        w = torch.rand(n, k, device=dev) + 0.5
+        # make operands exactly representable in bf16 so only the accumulation can err
+        x = x.bfloat16().float(); w = w.bfloat16().float()
+        a = ops.split_to_planes(x); b = ops.split_to_planes(w)
+        out = torch.zeros(rows, n, device=dev)
+        ops.gemm_split_bf16(a, b, k, n, dst_f32=out, f32_begin=0, f32_end=n)
+        ref = x.double() @ w.double().t()
+        err = (out.double() - ref) / ref
+        t32 = (x @ w.t()).double()
+        e32 = (t32 - ref) / ref
+        print("TRUNC k=%d: ours signed mean rel err %.3e (in ulps of 2^-24: %.2f) max |rel| %.2e | torch fp32 mean %.3e max %.2e" % (
+            k, err.mean().item(), err.mean().item() / 2 ** -24, err.abs().max().item(), e32.mean().item(), e32.abs().max().item()))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["sg", "gemm"]
     print(torch.cuda.get_device_name(0))
