@@ -103,6 +103,41 @@ int64_t nefii_sdf_workspace_bytes(void* handle, int rows_cap, int with_grad);
 int nefii_sdf_eval(void* handle, void* stream, int rows_cap, const int32_t* count, const float* x,
                    void* workspace, int64_t workspace_bytes, float* sdf, float* feat, float* grad);
 
+/* ---------------------------------------------------------------------------------------------
+ * Sphere tracing -- replaces RayTracing.forward, code/model/ray_tracing.py:29-101 (sphere_tracing
+ * :104-193, ray_sampler :195-257, rootfind :259-280, minimal_sdf_points :309-337) and
+ * rend_util.get_sphere_intersection, code/utils/rend_util.py:200-221.
+ * The reference's `sdf` callable argument becomes an SDF source: the MLP handle (sdf_kind 0) or an
+ * analytic primitive table used by the bit-exact control-flow tests (sdf_kind 1: device float
+ * [n_prims, 8] rows = kind (0 sphere, 1 box), centre xyz, radius | half extents, pad).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct nefii_trace_config {
+  float object_bounding_sphere;   /* 1.0 */
+  float sdf_threshold;            /* 5e-5 */
+  float line_search_step;         /* 0.5 */
+  int32_t line_step_iters;        /* 3 */
+  int32_t sphere_tracing_iters;   /* 10 */
+  int32_t n_steps;                /* 100 */
+  int32_t n_rootfind_steps;       /* 32 */
+} nefii_trace_config;
+
+#define NEFII_TRACE_TRAINING 1      /* RayTracing.training */
+#define NEFII_TRACE_SKIP_MIN_SDF 2  /* skip minimal_sdf_points (outputs only reach lanes the caller masks out) */
+
+int64_t nefii_trace_workspace_bytes(int sdf_kind, const void* sdf, int n_rays, int n_steps);
+/* cam_loc [B,3], ray_dirs [B,P,3], object_mask [B*P] uint8 (NULL = all true);
+ * linspace: device [n_steps] = linspace(0,1,n_steps); uniforms: device [n_steps] U(0,1) draws shared by
+ * all rays (training only; the reference draws them on the CPU generator, ray_tracing.py:316).
+ * Outputs: points [B*P,3], hit [B*P] uint8 (network_object_mask), dists [B*P].
+ * stats: host int64[8] or NULL: {sampler rays, root-find rays, min-SDF rays, SDF point evaluations, ...}.
+ * Synchronises `stream` once internally (twice when stats != NULL). */
+int nefii_ray_trace(void* stream, const nefii_trace_config* cfg, int sdf_kind, const void* sdf, int n_prims,
+                    int n_batch, int n_pix, const float* cam_loc, const float* ray_dirs, const uint8_t* object_mask,
+                    int flags, const float* linspace, const float* uniforms, void* workspace, int64_t workspace_bytes,
+                    float* points, uint8_t* hit, float* dists, int64_t* stats);
+/* the analytic test SDF alone: x [n,3] -> sdf [n] */
+int nefii_analytic_sdf_eval(void* stream, const float* prims, int n_prims, int n, const float* x, float* sdf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,10 @@ SIGNATURES = {
     "nefii_sg_render_fwd": [c_void_p, c_int, c_int, c_int] + [c_void_p] * 10,
     "nefii_background_sg_fwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "nefii_gemm_split_bf16": [c_void_p, c_void_p],
+    "nefii_trace_workspace_bytes": [c_int, c_void_p, c_int, c_int],
+    "nefii_ray_trace": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                        c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p],
+    "nefii_analytic_sdf_eval": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "nefii_sdf_create": [c_void_p, c_void_p],
     "nefii_sdf_destroy": [c_void_p],
     "nefii_sdf_set_weights": [c_void_p, c_void_p, c_void_p, c_void_p],
@@ -45,6 +49,7 @@ def _load():
         fn.argtypes = argtypes
         fn.restype = c_int
     lib.nefii_sdf_workspace_bytes.restype = c_longlong
+    lib.nefii_trace_workspace_bytes.restype = c_longlong
     return lib
 
 

@@ -3,6 +3,7 @@
 #include "../../include/nefii_b200.h"
 #include "mlp_gemm.cuh"
 #include "sdf_mlp.cuh"
+#include "tracer.cuh"
 
 namespace nefii {
 
@@ -94,6 +95,32 @@ int nefii_sdf_eval(void* handle, void* stream, int rows_cap, const int32_t* coun
   if (!handle) return nefii::set_error(NEFII_ERR_ARG, "nefii_sdf_eval: null handle");
   return static_cast<nefii::SdfNet*>(handle)->eval((cudaStream_t)stream, rows_cap, count, x, workspace,
                                                    (size_t)workspace_bytes, sdf, feat, grad);
+}
+
+static nefii::SdfSource make_source(int sdf_kind, const void* sdf, int n_prims) {
+  nefii::SdfSource src;
+  if (sdf_kind == 0) src.net = static_cast<const nefii::SdfNet*>(sdf);
+  else { src.prims = static_cast<const float*>(sdf); src.n_prims = n_prims; }
+  return src;
+}
+int64_t nefii_trace_workspace_bytes(int sdf_kind, const void* sdf, int n_rays, int n_steps) {
+  return (int64_t)nefii::trace_workspace_bytes(make_source(sdf_kind, sdf, 1), n_rays, n_steps);
+}
+int nefii_ray_trace(void* stream, const nefii_trace_config* cfg, int sdf_kind, const void* sdf, int n_prims, int n_batch,
+                    int n_pix, const float* cam_loc, const float* ray_dirs, const uint8_t* object_mask, int flags,
+                    const float* linspace, const float* uniforms, void* workspace, int64_t workspace_bytes, float* points,
+                    uint8_t* hit, float* dists, int64_t* stats) {
+  if (!cfg || !sdf) return nefii::set_error(NEFII_ERR_ARG, "nefii_ray_trace: null config / sdf source");
+  nefii::TraceConfig c;
+  c.radius = cfg->object_bounding_sphere; c.sdf_threshold = cfg->sdf_threshold; c.line_search_step = cfg->line_search_step;
+  c.line_step_iters = cfg->line_step_iters; c.sphere_tracing_iters = cfg->sphere_tracing_iters; c.n_steps = cfg->n_steps;
+  c.n_rootfind_steps = cfg->n_rootfind_steps;
+  return nefii::ray_trace((cudaStream_t)stream, c, make_source(sdf_kind, sdf, n_prims), n_batch, n_pix, cam_loc, ray_dirs,
+                          object_mask, flags, linspace, uniforms, workspace, (size_t)workspace_bytes, points, hit, dists,
+                          (long long*)stats);
+}
+int nefii_analytic_sdf_eval(void* stream, const float* prims, int n_prims, int n, const float* x, float* sdf) {
+  return nefii::analytic_sdf_eval((cudaStream_t)stream, prims, n_prims, n, nullptr, x, sdf);
 }
 
 }  // extern "C"

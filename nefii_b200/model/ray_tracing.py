@@ -1,0 +1,163 @@
+"""Drop-in for the reference's code/model/ray_tracing.py (RayTracing, :6-337).
+
+Same constructor arguments and the same ``forward(sdf, cam_loc, object_mask, ray_directions)``
+-> ``(points, network_object_mask, dists)`` contract; the whole trace (sphere tracing, sampler,
+bisection, min-SDF sampling) runs in CUDA through the C ABI call ``nefii_ray_trace``.
+
+The reference passes the SDF as a Python callable.  Here the callable is only used to *find* the
+SDF source: an object exposing ``nefii_sdf_source()`` (our ImplicitNetwork, AnalyticSDF), a bound
+method of such an object, or a closure over one -- e.g. the reference's own
+``lambda x: self.implicit_network(x)[:, 0]`` (implicit_differentiable_renderer.py:344).
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+c_void_p = ctypes.c_void_p
+
+
+class TraceConfig(ctypes.Structure):
+    """Mirror of ``nefii_trace_config``."""
+    _fields_ = [("object_bounding_sphere", ctypes.c_float), ("sdf_threshold", ctypes.c_float),
+                ("line_search_step", ctypes.c_float), ("line_step_iters", ctypes.c_int32),
+                ("sphere_tracing_iters", ctypes.c_int32), ("n_steps", ctypes.c_int32),
+                ("n_rootfind_steps", ctypes.c_int32)]
+
+
+TRACE_TRAINING = 1
+TRACE_SKIP_MIN_SDF = 2
+
+
+class AnalyticSDF:
+    """Union of spheres / boxes evaluated inside the tracer (bit-exact control-flow tests).
+    prims: [n, 8] rows = kind (0 sphere, 1 box), centre xyz, radius | half extents, pad."""
+
+    def __init__(self, prims, device):
+        self.prims = prims.to(device=device, dtype=torch.float32).contiguous()
+
+    def nefii_sdf_source(self):
+        return 1, self.prims.data_ptr(), self.prims.shape[0], self.prims
+
+    def __call__(self, x):
+        x = _lib.f32c(x).reshape(-1, 3)
+        out = torch.empty(x.shape[0], device=x.device)
+        if x.shape[0]:
+            _lib.check(_lib.raw().nefii_analytic_sdf_eval(_lib.stream_ptr(x.device), self.prims.data_ptr(),
+                                                          self.prims.shape[0], x.shape[0], x.data_ptr(), out.data_ptr()))
+        return out
+
+
+def resolve_sdf_source(sdf):
+    """-> (kind, pointer, n_prims, keepalive) for anything that leads to an SDF source."""
+    seen = set()
+
+    def probe(obj, depth):
+        if obj is None or id(obj) in seen or depth > 3:
+            return None
+        seen.add(id(obj))
+        if hasattr(obj, "nefii_sdf_source"):
+            return obj.nefii_sdf_source()
+        inner = getattr(obj, "implicit_network", None)
+        if inner is not None and hasattr(inner, "nefii_sdf_source"):
+            return inner.nefii_sdf_source()
+        owner = getattr(obj, "__self__", None)
+        if owner is not None:
+            got = probe(owner, depth + 1)
+            if got:
+                return got
+        for cell in getattr(obj, "__closure__", None) or ():
+            try:
+                got = probe(cell.cell_contents, depth + 1)
+            except ValueError:
+                got = None
+            if got:
+                return got
+        return None
+
+    src = probe(sdf, 0)
+    if src is None:
+        raise TypeError("nefii_b200 RayTracing: `sdf` must lead to an SDF source (ImplicitNetwork, AnalyticSDF, "
+                        "a bound method of one, or a closure over one); arbitrary Python callables cannot run "
+                        "inside the CUDA tracer")
+    return src
+
+
+class RayTracing(nn.Module):
+    def __init__(
+            self,
+            object_bounding_sphere=1.0,
+            sdf_threshold=5.0e-5,
+            line_search_step=0.5,
+            line_step_iters=1,
+            sphere_tracing_iters=10,
+            n_steps=100,
+            n_rootfind_steps=8,
+    ):
+        super().__init__()
+        self.object_bounding_sphere = object_bounding_sphere
+        self.sdf_threshold = sdf_threshold
+        self.sphere_tracing_iters = sphere_tracing_iters
+        self.line_step_iters = line_step_iters
+        self.line_search_step = line_search_step
+        self.n_steps = n_steps
+        self.n_rootfind_steps = n_rootfind_steps
+        # nefii_b200 extension (default keeps the reference's behaviour): minimal_sdf_points can be skipped
+        # by callers that discard its lanes (the secondary-ray trace of the integrator).
+        self.skip_min_sdf = False
+        self.last_stats = None
+        self.collect_stats = False
+        self._ws = None
+        self._linspace = {}
+
+    def _config(self):
+        return TraceConfig(self.object_bounding_sphere, self.sdf_threshold, self.line_search_step, self.line_step_iters,
+                           self.sphere_tracing_iters, self.n_steps, self.n_rootfind_steps)
+
+    def forward(self, sdf, cam_loc, object_mask, ray_directions, uniforms=None, skip_min_sdf=None):
+        kind, ptr, n_prims, keep = resolve_sdf_source(sdf)
+        dev = ray_directions.device
+        batch_size, num_pixels, _ = ray_directions.shape
+        n_rays = batch_size * num_pixels
+        dirs = _lib.f32c(ray_directions)
+        cam = _lib.f32c(cam_loc).reshape(batch_size, 3)
+        obj = object_mask.reshape(-1).to(torch.uint8).contiguous() if object_mask is not None else None
+        points = torch.empty(n_rays, 3, device=dev, dtype=torch.float32)
+        hit = torch.empty(n_rays, device=dev, dtype=torch.uint8)
+        dists = torch.empty(n_rays, device=dev, dtype=torch.float32)
+        if n_rays == 0:
+            return points, hit.bool(), dists
+        flags = 0
+        skip = self.skip_min_sdf if skip_min_sdf is None else skip_min_sdf
+        if self.training:
+            flags |= TRACE_TRAINING
+            if skip:
+                flags |= TRACE_SKIP_MIN_SDF
+            elif uniforms is None:
+                # same draw as the reference (CPU generator, ray_tracing.py:316)
+                uniforms = torch.empty(self.n_steps).uniform_(0.0, 1.0)
+        if uniforms is not None:
+            uniforms = uniforms.to(device=dev, dtype=torch.float32).contiguous()
+        key = (self.n_steps, dev)
+        if key not in self._linspace:
+            self._linspace[key] = torch.linspace(0, 1, steps=self.n_steps).to(dev)   # CPU linspace, as the reference
+        lin = self._linspace[key]
+        cfg = self._config()
+        lib = _lib.raw()
+        need = int(lib.nefii_trace_workspace_bytes(kind, c_void_p(ptr), n_rays, self.n_steps))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        stats = (ctypes.c_int64 * 8)() if self.collect_stats else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.nefii_ray_trace(
+                _lib.stream_ptr(dev), ctypes.byref(cfg), kind, c_void_p(ptr), n_prims, batch_size, num_pixels,
+                cam.data_ptr(), dirs.data_ptr(), obj.data_ptr() if obj is not None else None, flags,
+                lin.data_ptr(), uniforms.data_ptr() if uniforms is not None else None,
+                self._ws.data_ptr(), self._ws.numel(), points.data_ptr(), hit.data_ptr(), dists.data_ptr(), stats))
+        if stats is not None:
+            self.last_stats = dict(n_sampler=stats[0], n_rootfind=stats[1], n_min_sdf=stats[2], n_evals=stats[3],
+                                   n_sphere_hits=stats[4] // 2)
+        return points, hit.bool(), dists

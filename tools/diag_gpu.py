@@ -141,6 +141,49 @@ def diag_trunc():
             k, err.mean().item(), err.mean().item() / 2 ** -24, err.abs().max().item(), e32.mean().item(), e32.abs().max().item()))
 
 
+def diag_trace():
+    from nefii_b200 import ops
+    from nefii_b200.model.ray_tracing import RayTracing
+    from oracle import mlp, tracer as otr
+    dev = torch.device("cuda:0")
+    for bumps in (0.0, 0.1, 0.2):
+        params = mlp.sdf_init(seed=1, bumps=bumps)
+        net = ops.SdfMlp(device=dev)
+        net.set_weights([w.to(dev) for w in params.W], [b.to(dev) for b in params.b])
+
+        class Src:
+            def nefii_sdf_source(self):
+                return 0, net.handle.value, 0, net
+        p32 = params.to(dev)
+        oracle_sdf = lambda x: mlp.sdf_forward(p32, x)[:, 0]
+        cfg = otr.TraceConfig()
+        for n_side, training in ((64, False), (64, True), (362, False), (362, True)):
+            K = torch.eye(4); K[0, 0] = K[1, 1] = n_side * 1.6; K[0, 2] = K[1, 2] = n_side / 2
+            pose = torch.eye(4); pose[:3, 3] = torch.tensor([0., 0., -3.])
+            ii, jj = torch.meshgrid(torch.arange(n_side).float(), torch.arange(n_side).float(), indexing="xy")
+            uv = torch.stack([ii, jj], -1).reshape(1, -1, 2) + 0.5
+            dirs, loc = otr.camera_rays(uv, pose[None], K[None])
+            dirs, loc = dirs.to(dev), loc.to(dev)
+            obj = torch.ones(n_side * n_side, dtype=torch.bool, device=dev)
+            rt = RayTracing(**cfg.as_kwargs()); rt.train(training); rt.collect_stats = True
+            u = torch.rand(100)
+            pts, mask, dist = rt(Src(), loc, obj, dirs, uniforms=u)
+            rt.collect_stats = False
+            ms = ev_time(lambda: rt(Src(), loc, obj, dirs, uniforms=u), iters=3, warm=1)
+            line = "TRACE bumps=%.2f n=%d train=%d: %.2f ms, hits %.3f, sampler %d, rootfind %d, minsdf %d, evals/ray %.1f -> %.1f TFLOP/s alg" % (
+                bumps, n_side * n_side, training, ms, mask.float().mean().item(), rt.last_stats["n_sampler"], rt.last_stats["n_rootfind"],
+                rt.last_stats["n_min_sdf"], rt.last_stats["n_evals"] / (n_side * n_side), rt.last_stats["n_evals"] * 3.671e6 / ms / 1e9)
+            if n_side <= 64:
+                t0 = time.time()
+                o_pts, o_mask, o_dist, st = otr.ray_trace(oracle_sdf, loc, obj, dirs, cfg, training=training, uniforms=u)
+                torch.cuda.synchronize()
+                both = mask & o_mask
+                line += " | oracle(torch gpu) %.0f ms evals/ray %.1f, mask agree %.4f, depth err med %.1e max %.1e" % (
+                    (time.time() - t0) * 1e3, st["n_evals"] / (n_side * n_side), (mask == o_mask).float().mean().item(),
+                    (dist - o_dist)[both].abs().median().item(), (dist - o_dist)[both].abs().max().item())
+            print(line)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["sg", "gemm"]
     print(torch.cuda.get_device_name(0))
