@@ -110,7 +110,7 @@ def test_mlp_scene_statistics(cuda_device):
     from nefii_b200 import ops
     from oracle import mlp
     dev = cuda_device
-    params = mlp.sdf_init(seed=1, bumps=0.15)
+    params = mlp.sdf_init(seed=1, bumps=0.03)
     net = ops.SdfMlp(device=dev)
     net.set_weights([w.to(dev) for w in params.W], [b.to(dev) for b in params.b])
 
@@ -120,7 +120,7 @@ def test_mlp_scene_statistics(cuda_device):
 
     p32 = params.to(dev)
     oracle_sdf = lambda x: mlp.sdf_forward(p32, x)[:, 0]
-    dirs, loc = _camera(dev, 64, seed=2)
+    dirs, loc = _camera(dev, 64, seed=2, f=2.4 * 64)     # ~50 % of the rays hit the blob
     obj = torch.ones(64 * 64, dtype=torch.bool, device=dev)
     rt, cfg = _module(False)
     pts, mask, dist = rt(Src(), loc, obj, dirs)

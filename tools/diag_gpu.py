@@ -146,7 +146,7 @@ def diag_trace():
     from nefii_b200.model.ray_tracing import RayTracing
     from oracle import mlp, tracer as otr
     dev = torch.device("cuda:0")
-    for bumps in (0.0, 0.1, 0.2):
+    for bumps in (0.03,):
         params = mlp.sdf_init(seed=1, bumps=bumps)
         net = ops.SdfMlp(device=dev)
         net.set_weights([w.to(dev) for w in params.W], [b.to(dev) for b in params.b])
@@ -158,7 +158,7 @@ def diag_trace():
         oracle_sdf = lambda x: mlp.sdf_forward(p32, x)[:, 0]
         cfg = otr.TraceConfig()
         for n_side, training in ((64, False), (64, True), (362, False), (362, True)):
-            K = torch.eye(4); K[0, 0] = K[1, 1] = n_side * 1.6; K[0, 2] = K[1, 2] = n_side / 2
+            K = torch.eye(4); K[0, 0] = K[1, 1] = n_side * 2.4; K[0, 2] = K[1, 2] = n_side / 2
             pose = torch.eye(4); pose[:3, 3] = torch.tensor([0., 0., -3.])
             ii, jj = torch.meshgrid(torch.arange(n_side).float(), torch.arange(n_side).float(), indexing="xy")
             uv = torch.stack([ii, jj], -1).reshape(1, -1, 2) + 0.5
@@ -180,7 +180,7 @@ def diag_trace():
                 both = mask & o_mask
                 line += " | oracle(torch gpu) %.0f ms evals/ray %.1f, mask agree %.4f, depth err med %.1e max %.1e" % (
                     (time.time() - t0) * 1e3, st["n_evals"] / (n_side * n_side), (mask == o_mask).float().mean().item(),
-                    (dist - o_dist)[both].abs().median().item(), (dist - o_dist)[both].abs().max().item())
+                    (dist - o_dist)[both].abs().median().item() if both.any() else -1, (dist - o_dist)[both].abs().max().item() if both.any() else -1)
             print(line)
 
 
