@@ -67,9 +67,10 @@ typedef struct nefii_gemm_desc {
   const float* w_last; const float* b_last; int32_t n_last; int32_t w_last_ld; float* dst_last; /* fused tiny output layer */
   void* seed_hi; void* seed_lo; int32_t seed_ld;                                     /* input-gradient seed planes */
   const void* sav_hi; const void* sav_lo; int32_t sav_ld; int32_t sav_ncols; float sav_scale; /* backward: saved activations */
+  int32_t k_splits; int64_t f32_split_stride; int32_t k_splits_used;   /* split-K: partial s -> dst_f32 + s*stride (floats); k_splits_used is an output */
 } nefii_gemm_desc;
 
-int nefii_gemm_split_bf16(void* stream, const nefii_gemm_desc* desc /* host */);
+int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* desc /* host */);
 
 /* fp32 [rows, cols] (row stride ld_src) -> zero-padded bf16 hi/lo planes [rows_pad, cols_pad];
  * transpose != 0 writes the transpose.  Used to pack weights (and test inputs). */
@@ -137,6 +138,60 @@ int nefii_ray_trace(void* stream, const nefii_trace_config* cfg, int sdf_kind, c
                     float* points, uint8_t* hit, float* dists, int64_t* stats);
 /* the analytic test SDF alone: x [n,3] -> sdf [n] */
 int nefii_analytic_sdf_eval(void* stream, const float* prims, int n_prims, int n, const float* x, float* sdf);
+
+/* ---------------------------------------------------------------------------------------------
+ * Near-field indirect-illumination integrator -- replaces the sampling and shading halves of
+ * pt_render_indirect_mlp, code/model/path_tracing_render.py:1255-1487 (cos_sampling :128-156,
+ * brdf_sampling :61-125, mix_sg_sampling :168-271, power_heuristic_list :390-401, shading :1406-1476).
+ * The secondary trace between the two halves is nefii_ray_trace; the radiance query is the MLP path.
+ * n = surface points; all per-sample arrays are laid out [3 (cos, ggx, mixture), n, ...].
+ * ------------------------------------------------------------------------------------------- */
+/* u [n,7]: the uniforms in the reference's torch.rand order (cos r1 r2, ggx r1 r2, mix r0 r1 r2).
+ * Outputs: wi [3,n,3], pdf [3,n] (clamped at 1e-6), weight [3,n] (power heuristic),
+ * pdf_matrix [3,3,n] or NULL (pdf of strategy j at direction i). */
+int nefii_mis_sample(void* stream, int n, int n_sg, const float* lgt_sgs, const float* roughness, const float* normal,
+                     const float* view, const float* u, float* wi, float* pdf, float* weight, float* pdf_matrix);
+/* specular: [1,3] (spec_per_point = 0) or [n,3]; hit [3,n] uint8 (secondary_mask); indirect [3,n,3].
+ * Outputs [n,3]: sg_rgb, sg_specular_rgb, sg_diffuse_rgb; light [3,n,3] (environment radiance along wi,
+ * kept for the backward pass) or NULL. */
+int nefii_mis_shade_fwd(void* stream, int n, int n_sg, const float* lgt_sgs, const float* specular, int spec_per_point,
+                        const float* roughness, const float* albedo, const float* normal, const float* view,
+                        const float* wi, const float* pdf, const float* weight, const uint8_t* hit,
+                        const float* indirect, float* out_rgb, float* out_specular, float* out_diffuse, float* light);
+/* g_rgb / g_specular / g_diffuse: upstream gradients [n,3] (any may be NULL).  Outputs: g_roughness [n],
+ * g_albedo [n,3], g_specular_refl [n,3] or NULL, g_indirect [3,n,3]; g_lgt_acc [n_sg,7] is ACCUMULATED
+ * (atomicAdd) in the unit parametrisation {d axis, d sharpness, d amplitude} -- convert with nefii_sg_param_grad. */
+int nefii_mis_shade_bwd(void* stream, int n, int n_sg, const float* lgt_sgs, const float* specular, int spec_per_point,
+                        const float* roughness, const float* albedo, const float* normal, const float* view,
+                        const float* wi, const float* pdf, const float* weight, const uint8_t* hit,
+                        const float* indirect, const float* light, const float* g_rgb, const float* g_specular,
+                        const float* g_diffuse, float* g_roughness, float* g_albedo, float* g_specular_refl,
+                        float* g_indirect, float* g_lgt_acc);
+/* backward of nefii_background_sg_fwd: accumulates into g_lgt_acc [n_sg,7] (unit parametrisation, eps 1e-8) */
+int nefii_background_sg_bwd(void* stream, int n_rays, int n_sg, const float* lgt_sgs, const float* dirs,
+                            const float* g_out, float* g_lgt_acc);
+/* unit-parametrisation accumulator -> gradient of the raw lgtSGs parameter (abs(), lobe / (|lobe| + eps));
+ * accumulate != 0 adds to g_lgt instead of overwriting */
+int nefii_sg_param_grad(void* stream, int n_sg, const float* lgt_sgs, const float* acc, float eps, float* g_lgt, int accumulate);
+
+/* Helpers of the trainable dense stacks (RenderingNetwork :196-241, EnvmapMaterialNetwork :357-425):
+ * input assembly: up to 4 segments, each a positional encoding (n_freqs >= 0) of a 3-vector or a raw copy
+ * (n_freqs = -1) of `width` floats per row, concatenated and zero padded to k_pad -> bf16 planes [rows, ld] */
+int nefii_assemble_input(void* stream, int rows, int n_seg, const float* const* src /* host array of device ptrs */,
+                         const int32_t* width /* host */, const int32_t* n_freqs /* host */, void* dst_hi, void* dst_lo,
+                         int ld, int k_pad);
+/* dst[c][r] = src[r][c] as planes, zero padded to [cols_pad, rows_pad] (row stride ld_dst); col_sum (or NULL)
+ * accumulates the column sums of src (bias gradient) */
+int nefii_transpose_planes(void* stream, const void* src_hi, const void* src_lo, int ld_src, int rows, int cols,
+                           void* dst_hi, void* dst_lo, int ld_dst, int rows_pad, int cols_pad, float* col_sum);
+/* backward of the fused tiny output layer y = act(z) W_last^T + b_last: G = (gy W_last) * act'(h) as planes,
+ * gw_last [n_out,width] and gb_last [n_out] are ACCUMULATED */
+int nefii_last_layer_bwd(void* stream, int act, int rows, int width, int n_out, const float* gy, const float* w_last,
+                         const void* h_hi, const void* h_lo, int h_ld, void* g_hi, void* g_lo, int g_ld,
+                         float* gw_last, float* gb_last);
+/* out[r, c] = sum_s partial[s * stride + r * ld_src + c] */
+int nefii_reduce_splits(void* stream, const float* partial, int n_splits, int64_t stride, int rows, int ld_src, int cols,
+                        float* out);
 
 #ifdef __cplusplus
 }

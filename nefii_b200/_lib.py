@@ -19,6 +19,16 @@ SIGNATURES = {
     "nefii_sg_render_fwd": [c_void_p, c_int, c_int, c_int] + [c_void_p] * 10,
     "nefii_background_sg_fwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "nefii_gemm_split_bf16": [c_void_p, c_void_p],
+    "nefii_assemble_input": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int],
+    "nefii_transpose_planes": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "nefii_last_layer_bwd": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                             c_void_p, c_int, c_void_p, c_void_p],
+    "nefii_reduce_splits": [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_void_p],
+    "nefii_mis_sample": [c_void_p, c_int, c_int] + [c_void_p] * 9,
+    "nefii_mis_shade_fwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 13,
+    "nefii_mis_shade_bwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 18,
+    "nefii_background_sg_bwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "nefii_sg_param_grad": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int],
     "nefii_trace_workspace_bytes": [c_int, c_void_p, c_int, c_int],
     "nefii_ray_trace": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                         c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p],

@@ -23,6 +23,19 @@ int set_error(int code, const char* fmt, ...) {
 int sg_render_fwd(cudaStream_t, int, int, int, const float*, const float*, const float*, const float*, const float*,
                   const float*, const float*, float*, float*, float*);
 int background_sg_fwd(cudaStream_t, int, int, const float*, const float*, float*);
+int mis_sample(cudaStream_t, int, int, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*);
+int mis_shade_fwd(cudaStream_t, int, int, const float*, const float*, int, const float*, const float*, const float*, const float*,
+                  const float*, const float*, const float*, const unsigned char*, const float*, float*, float*, float*, float*);
+int mis_shade_bwd(cudaStream_t, int, int, const float*, const float*, int, const float*, const float*, const float*, const float*,
+                  const float*, const float*, const float*, const unsigned char*, const float*, const float*, const float*,
+                  const float*, const float*, float*, float*, float*, float*, float*);
+int background_sg_bwd(cudaStream_t, int, int, const float*, const float*, const float*, float*);
+int sg_param_grad(cudaStream_t, int, const float*, const float*, float, float*, int);
+int assemble_input(cudaStream_t, int, int, const float* const*, const int*, const int*, __nv_bfloat16*, __nv_bfloat16*, int, int);
+int transpose_planes(cudaStream_t, const __nv_bfloat16*, const __nv_bfloat16*, int, int, int, __nv_bfloat16*, __nv_bfloat16*, int, int, int, float*);
+int last_layer_bwd(cudaStream_t, int, int, int, int, const float*, const float*, const __nv_bfloat16*, const __nv_bfloat16*, int,
+                   __nv_bfloat16*, __nv_bfloat16*, int, float*, float*);
+int reduce_splits(cudaStream_t, const float*, int, long long, int, int, int, float*);
 
 }  // namespace nefii
 
@@ -43,7 +56,7 @@ int nefii_background_sg_fwd(void* stream, int n_rays, int n_sg, const float* lgt
   return nefii::background_sg_fwd((cudaStream_t)stream, n_rays, n_sg, lgt_sgs, dirs, out_rgb);
 }
 
-int nefii_gemm_split_bf16(void* stream, const nefii_gemm_desc* d) {
+int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* d) {
   if (!d) return nefii::set_error(NEFII_ERR_ARG, "nefii_gemm_split_bf16: null descriptor");
   nefii::GemmProblem p;
   p.a_hi = (const __nv_bfloat16*)d->a_hi; p.a_lo = (const __nv_bfloat16*)d->a_lo; p.a_ld = d->a_ld; p.rows_cap = d->rows_cap;
@@ -58,7 +71,12 @@ int nefii_gemm_split_bf16(void* stream, const nefii_gemm_desc* d) {
   e.seed.hi = (__nv_bfloat16*)d->seed_hi; e.seed.lo = (__nv_bfloat16*)d->seed_lo; e.seed.ld = d->seed_ld;
   e.sav_hi = (const __nv_bfloat16*)d->sav_hi; e.sav_lo = (const __nv_bfloat16*)d->sav_lo; e.sav_ld = d->sav_ld;
   e.sav_ncols = d->sav_ncols; e.sav_scale = d->sav_scale;
-  return nefii::gemm_split_bf16((cudaStream_t)stream, p);
+  p.k_splits = d->k_splits; p.f32_split_stride = d->f32_split_stride;
+  int used = 1;
+  p.k_splits_used = &used;
+  int rc = nefii::gemm_split_bf16((cudaStream_t)stream, p);
+  d->k_splits_used = used;
+  return rc;
 }
 
 int nefii_split_to_planes(void* stream, const float* src, int rows, int cols, int ld_src, int transpose, float scale,
@@ -121,6 +139,56 @@ int nefii_ray_trace(void* stream, const nefii_trace_config* cfg, int sdf_kind, c
 }
 int nefii_analytic_sdf_eval(void* stream, const float* prims, int n_prims, int n, const float* x, float* sdf) {
   return nefii::analytic_sdf_eval((cudaStream_t)stream, prims, n_prims, n, nullptr, x, sdf);
+}
+
+int nefii_mis_sample(void* stream, int n, int n_sg, const float* lgt_sgs, const float* roughness, const float* normal,
+                     const float* view, const float* u, float* wi, float* pdf, float* weight, float* pdf_matrix) {
+  return nefii::mis_sample((cudaStream_t)stream, n, n_sg, lgt_sgs, roughness, normal, view, u, wi, pdf, weight, pdf_matrix);
+}
+int nefii_mis_shade_fwd(void* stream, int n, int n_sg, const float* lgt_sgs, const float* specular, int spec_per_point,
+                        const float* roughness, const float* albedo, const float* normal, const float* view,
+                        const float* wi, const float* pdf, const float* weight, const uint8_t* hit, const float* indirect,
+                        float* out_rgb, float* out_specular, float* out_diffuse, float* light) {
+  return nefii::mis_shade_fwd((cudaStream_t)stream, n, n_sg, lgt_sgs, specular, spec_per_point, roughness, albedo, normal,
+                              view, wi, pdf, weight, hit, indirect, out_rgb, out_specular, out_diffuse, light);
+}
+int nefii_mis_shade_bwd(void* stream, int n, int n_sg, const float* lgt_sgs, const float* specular, int spec_per_point,
+                        const float* roughness, const float* albedo, const float* normal, const float* view,
+                        const float* wi, const float* pdf, const float* weight, const uint8_t* hit, const float* indirect,
+                        const float* light, const float* g_rgb, const float* g_specular, const float* g_diffuse,
+                        float* g_roughness, float* g_albedo, float* g_specular_refl, float* g_indirect, float* g_lgt_acc) {
+  return nefii::mis_shade_bwd((cudaStream_t)stream, n, n_sg, lgt_sgs, specular, spec_per_point, roughness, albedo, normal,
+                              view, wi, pdf, weight, hit, indirect, light, g_rgb, g_specular, g_diffuse, g_roughness,
+                              g_albedo, g_specular_refl, g_indirect, g_lgt_acc);
+}
+int nefii_background_sg_bwd(void* stream, int n_rays, int n_sg, const float* lgt_sgs, const float* dirs, const float* g_out,
+                            float* g_lgt_acc) {
+  return nefii::background_sg_bwd((cudaStream_t)stream, n_rays, n_sg, lgt_sgs, dirs, g_out, g_lgt_acc);
+}
+int nefii_sg_param_grad(void* stream, int n_sg, const float* lgt_sgs, const float* acc, float eps, float* g_lgt, int accumulate) {
+  return nefii::sg_param_grad((cudaStream_t)stream, n_sg, lgt_sgs, acc, eps, g_lgt, accumulate);
+}
+
+int nefii_assemble_input(void* stream, int rows, int n_seg, const float* const* src, const int32_t* width,
+                         const int32_t* n_freqs, void* dst_hi, void* dst_lo, int ld, int k_pad) {
+  if (!src || !width || !n_freqs) return nefii::set_error(NEFII_ERR_ARG, "nefii_assemble_input: null argument");
+  return nefii::assemble_input((cudaStream_t)stream, rows, n_seg, src, width, n_freqs, (__nv_bfloat16*)dst_hi,
+                               (__nv_bfloat16*)dst_lo, ld, k_pad);
+}
+int nefii_transpose_planes(void* stream, const void* src_hi, const void* src_lo, int ld_src, int rows, int cols, void* dst_hi,
+                           void* dst_lo, int ld_dst, int rows_pad, int cols_pad, float* col_sum) {
+  return nefii::transpose_planes((cudaStream_t)stream, (const __nv_bfloat16*)src_hi, (const __nv_bfloat16*)src_lo, ld_src, rows,
+                                 cols, (__nv_bfloat16*)dst_hi, (__nv_bfloat16*)dst_lo, ld_dst, rows_pad, cols_pad, col_sum);
+}
+int nefii_last_layer_bwd(void* stream, int act, int rows, int width, int n_out, const float* gy, const float* w_last,
+                         const void* h_hi, const void* h_lo, int h_ld, void* g_hi, void* g_lo, int g_ld, float* gw_last,
+                         float* gb_last) {
+  return nefii::last_layer_bwd((cudaStream_t)stream, act, rows, width, n_out, gy, w_last, (const __nv_bfloat16*)h_hi,
+                               (const __nv_bfloat16*)h_lo, h_ld, (__nv_bfloat16*)g_hi, (__nv_bfloat16*)g_lo, g_ld, gw_last, gb_last);
+}
+int nefii_reduce_splits(void* stream, const float* partial, int n_splits, int64_t stride, int rows, int ld_src, int cols,
+                        float* out) {
+  return nefii::reduce_splits((cudaStream_t)stream, partial, n_splits, (long long)stride, rows, ld_src, cols, out);
 }
 
 }  // extern "C"

@@ -307,15 +307,20 @@ template <int MODE, int ACT, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                       const int* __restrict__ count_ptr, int rows_cap, int k_blocks, int n_chunks,
-                       const __grid_constant__ GemmEpilogue epi) {
+                       const int* __restrict__ count_ptr, int rows_cap, int k_blocks_total, int n_chunks, int kb_per_split,
+                       long long f32_split_stride, const __grid_constant__ GemmEpilogue epi_in) {
   const int m_tile = blockIdx.x;
+  // split-K (weight gradients): CTA (x, y) reduces K blocks [y * kb_per_split, ...) into its own fp32 partial
+  const int kb_begin = blockIdx.y * kb_per_split;
+  const int k_blocks = min(k_blocks_total, kb_begin + kb_per_split) - kb_begin;
+  GemmEpilogue epi = epi_in;
+  if (epi.dst_f32 != nullptr) epi.dst_f32 += (long long)blockIdx.y * f32_split_stride;
   int m_limit = rows_cap;
   if (count_ptr != nullptr) {
     int c = *count_ptr;
     if (c < m_limit) m_limit = c;
   }
-  if ((long long)m_tile * BM >= m_limit) return;   // uniform exit before any barrier / TMEM use
+  if ((long long)m_tile * BM >= m_limit || k_blocks <= 0) return;   // uniform exit before any barrier / TMEM use
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -364,10 +369,11 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           const uint32_t full = smem_u32(&bars[0 + stage]);
           mbar_expect_tx(full, kStageBytes);
           unsigned char* st = tiles + (size_t)stage * kStageBytes;
-          tma_load_2d(smem_u32(st), &map_a_hi, full, kb * BK, m_tile * BM);
-          tma_load_2d(smem_u32(st + kATileBytes), &map_a_lo, full, kb * BK, m_tile * BM);
-          tma_load_2d(smem_u32(st + 2 * kATileBytes), &map_b_hi, full, kb * BK, nc * BN);
-          tma_load_2d(smem_u32(st + 2 * kATileBytes + kBTileBytes), &map_b_lo, full, kb * BK, nc * BN);
+          const int kx = (kb_begin + kb) * BK;
+          tma_load_2d(smem_u32(st), &map_a_hi, full, kx, m_tile * BM);
+          tma_load_2d(smem_u32(st + kATileBytes), &map_a_lo, full, kx, m_tile * BM);
+          tma_load_2d(smem_u32(st + 2 * kATileBytes), &map_b_hi, full, kx, nc * BN);
+          tma_load_2d(smem_u32(st + 2 * kATileBytes + kBTileBytes), &map_b_lo, full, kx, nc * BN);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -548,7 +554,7 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   NEFII_CHECK_ARG(p.epi.mode == 0 || p.epi.sav_hi == nullptr || p.epi.sav_ld >= n_chunks * BN || p.epi.sav_ncols % 32 == 0,
                   "gemm_split_bf16: saved-activation rows must cover whole 32-column groups");
   const int grid = ceil_div(p.rows_cap, BM);
-  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const int*, int, int, int, GemmEpilogue);
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const int*, int, int, int, int, long long, GemmEpilogue);
   KernelFn fn = nullptr;
   const bool fuse = p.epi.mode == 0 && p.epi.w_last != nullptr;
   NEFII_CHECK_ARG(!fuse || (p.epi.dst_last != nullptr && p.epi.n_last >= 1), "gemm_split_bf16: fused output layer needs dst_last");
@@ -574,7 +580,16 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
     NEFII_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_set[key] = true;
   }
-  fn<<<grid, kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p.count, p.rows_cap, p.k_pad / BK, n_chunks, p.epi);
+  const int k_blocks = p.k_pad / BK;
+  int splits = p.k_splits > 1 ? p.k_splits : 1;
+  if (splits > k_blocks) splits = k_blocks;
+  const int kb_per = ceil_div(k_blocks, splits);
+  splits = ceil_div(k_blocks, kb_per);
+  NEFII_CHECK_ARG(splits == 1 || (p.epi.dst_f32 != nullptr && p.epi.dst.hi == nullptr && !fuse && p.epi.mode == 0 && p.epi.act == ACT_NONE),
+                  "gemm_split_bf16: split-K needs a plain fp32 output");
+  if (p.k_splits_used) *p.k_splits_used = splits;
+  fn<<<dim3(grid, splits), kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p.count, p.rows_cap, k_blocks, n_chunks,
+                                                           kb_per, (long long)p.f32_split_stride, p.epi);
   NEFII_LAUNCH_CHECK();
   return NEFII_OK;
 }

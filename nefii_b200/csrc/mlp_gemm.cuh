@@ -49,6 +49,9 @@ struct GemmProblem {
   const __nv_bfloat16* b_hi; const __nv_bfloat16* b_lo; int b_ld; int n_pad;  // n_pad multiple of 256
   int k_pad;                // multiple of 64, <= a_ld, <= b_ld
   const int* count;         // device: number of valid rows (nullptr -> rows_cap)
+  int k_splits = 1;         // >1: split-K over gridDim.y, partial s is written to dst_f32 + s * f32_split_stride
+  long long f32_split_stride = 0;
+  int* k_splits_used = nullptr;   // host out: number of partials actually produced
   GemmEpilogue epi;
 };
 

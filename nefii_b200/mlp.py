@@ -1,0 +1,183 @@
+"""Trainable dense stacks (radiance net, material net) on the tcgen05 layer GEMM, with autograd.
+
+``dense_mlp(segments, weights, biases, act)`` computes what the reference computes with
+``cat -> [Linear + act] * L -> Linear`` (RenderingNetwork.forward, implicit_differentiable_renderer.py:196-241;
+EnvmapMaterialNetwork.diffuse_albedo_layers, sg_envmap_material.py:357-366) and returns the raw output of the
+last Linear.  Gradients flow to the weights and biases only -- in the reference's step-2 training the inputs
+(points, normals, view directions, frozen geometry features) carry no gradient.
+
+Forward : input assembly (PE + concat) -> hidden layers (GEMM + bias + act fused) -> the last hidden layer's
+          epilogue also applies the tiny output layer in fp32.
+Backward: output layer backward (elementwise + reductions), then per hidden layer a weight-gradient GEMM
+          (K = points, split-K over the grid, operands transposed into K-major planes), the bias gradient as
+          column sums, and the data-gradient GEMM with the activation derivative fused into its epilogue.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+
+c_void_p = ctypes.c_void_p
+_NUM_SMS = 148
+
+
+def _planes(rows, cols, device):
+    return (torch.empty(rows, cols, device=device, dtype=torch.bfloat16),
+            torch.empty(rows, cols, device=device, dtype=torch.bfloat16))
+
+
+def assemble_input(segments, k_pad):
+    """segments: list of (tensor [N, w], n_freqs) with n_freqs = -1 for a raw copy.  -> planes [N, k_pad]."""
+    n = segments[0][0].shape[0]
+    dev = segments[0][0].device
+    srcs = [_lib.f32c(t).reshape(n, -1) for t, _ in segments]
+    dst = _planes(max(n, 1), k_pad, dev)
+    if n == 0:
+        return dst, srcs
+    ns = len(segments)
+    ptrs = (c_void_p * ns)(*[s.data_ptr() for s in srcs])
+    widths = (ctypes.c_int32 * ns)(*[s.shape[1] for s in srcs])
+    freqs = (ctypes.c_int32 * ns)(*[f for _, f in segments])
+    _lib.check(_lib.raw().nefii_assemble_input(_lib.stream_ptr(dev), n, ns, ptrs, widths, freqs, dst[0].data_ptr(),
+                                               dst[1].data_ptr(), k_pad, k_pad))
+    return dst, srcs
+
+
+def transpose_planes(src, rows, cols, rows_pad, cols_pad, col_sum=None):
+    dst = _planes(cols_pad, rows_pad, src[0].device)
+    _lib.check(_lib.raw().nefii_transpose_planes(
+        _lib.stream_ptr(src[0].device), src[0].data_ptr(), src[1].data_ptr(), src[0].stride(0), rows, cols,
+        dst[0].data_ptr(), dst[1].data_ptr(), rows_pad, rows_pad, cols_pad, col_sum.data_ptr() if col_sum is not None else None))
+    return dst
+
+
+def segment_width(segments):
+    return sum((3 + 6 * f) if f >= 0 else t.shape[-1] for t, f in segments)
+
+
+class _DenseMlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, act, seg_freqs, n_hidden, *tensors):
+        n_seg = len(seg_freqs)
+        seg_src = tensors[:n_seg]
+        params = tensors[n_seg:]
+        Ws = [params[2 * l] for l in range(n_hidden + 1)]
+        bs = [params[2 * l + 1] for l in range(n_hidden + 1)]
+        dev = seg_src[0].device
+        n = seg_src[0].shape[0]
+        segments = list(zip(seg_src, seg_freqs))
+        d_in = segment_width(segments)
+        assert d_in == Ws[0].shape[1], (d_in, Ws[0].shape)
+        n_out = Ws[-1].shape[0]
+        assert n_out <= 4
+        need_grad = any(p.requires_grad for p in params)
+        y = torch.empty(n, n_out, device=dev, dtype=torch.float32)
+        ctx.n_seg = n_seg
+        if n == 0:
+            ctx.empty = True
+            ctx.shapes = [p.shape for p in params]
+            return y
+        k0 = ops.round_up(d_in, 64)
+        in0, _keep = assemble_input(segments, k0)
+        w_last = _lib.f32c(Ws[-1])
+        b_last = _lib.f32c(bs[-1])
+        acts = [in0]
+        packed = []
+        for l in range(n_hidden):
+            W = _lib.f32c(Ws[l])
+            out_dim, in_dim = W.shape
+            k_pad = ops.round_up(in_dim, 64)
+            wp = ops.split_to_planes(W, rows_pad=ops.round_up(out_dim, 256), cols_pad=k_pad)
+            packed.append(W)
+            bias = _lib.f32c(bs[l])
+            a = acts[-1] if need_grad else acts[-1]
+            if l < n_hidden - 1:
+                dst = _planes(n, ops.round_up(out_dim, 64), dev)
+                ops.gemm_split_bf16(a, wp, k_pad, out_dim, act=act, bias=bias, dst=dst, dst_ncols=out_dim,
+                                    dst_zero_to=ops.round_up(out_dim, 64))
+            else:
+                dst = _planes(n, ops.round_up(out_dim, 64), dev) if need_grad else None
+                ops.gemm_split_bf16(a, wp, k_pad, out_dim, act=act, bias=bias, dst=dst, dst_ncols=out_dim if dst else 0,
+                                    dst_zero_to=ops.round_up(out_dim, 64) if dst else 0,
+                                    w_last=w_last, b_last=b_last, dst_last=y)
+            if need_grad or l < n_hidden - 1:
+                if not need_grad:
+                    acts = [dst]          # ping-pong: drop what is no longer needed
+                else:
+                    acts.append(dst)
+        ctx.empty = False
+        if need_grad:
+            ctx.act, ctx.n_hidden, ctx.n = act, n_hidden, n
+            ctx.acts = acts                # in0, h_1 .. h_L (planes)
+            ctx.weights = packed           # effective fp32 hidden weights
+            ctx.w_last = w_last
+            ctx.needs = [p.requires_grad for p in params]
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n_lead = 3
+        if ctx.empty:
+            return (None,) * (n_lead + ctx.n_seg) + tuple(torch.zeros(s, device=gy.device) for s in ctx.shapes)
+        act, L, n = ctx.act, ctx.n_hidden, ctx.n
+        dev = gy.device
+        gy = _lib.f32c(gy)
+        lib = _lib.raw()
+        sp = _lib.stream_ptr(dev)
+        acts = ctx.acts
+        width = ctx.w_last.shape[1]
+        n_out = ctx.w_last.shape[0]
+        gw_last = torch.zeros_like(ctx.w_last)
+        gb_last = torch.zeros(n_out, device=dev)
+        hL = acts[L]
+        G = _planes(n, hL[0].shape[1], dev)
+        _lib.check(lib.nefii_last_layer_bwd(sp, act, n, width, n_out, gy.data_ptr(), ctx.w_last.data_ptr(),
+                                            hL[0].data_ptr(), hL[1].data_ptr(), hL[0].stride(0),
+                                            G[0].data_ptr(), G[1].data_ptr(), G[0].stride(0),
+                                            gw_last.data_ptr(), gb_last.data_ptr()))
+        n_pad = ops.round_up(n, 64)
+        grads_w, grads_b = [None] * L, [None] * L
+        for l in range(L - 1, -1, -1):
+            W = ctx.weights[l]
+            out_dim, in_dim = W.shape
+            gb = torch.zeros(out_dim, device=dev)
+            GT = transpose_planes(G, n, out_dim, n_pad, ops.round_up(out_dim, 128), col_sum=gb)
+            h_prev = acts[l]
+            HT = transpose_planes(h_prev, n, in_dim, n_pad, ops.round_up(in_dim, 256))
+            splits = max(1, min(n_pad // 128, (_NUM_SMS + (GT[0].shape[0] // 128) - 1) // (GT[0].shape[0] // 128)))
+            partial = torch.empty(splits, out_dim, in_dim, device=dev, dtype=torch.float32)
+            used = ops.gemm_split_bf16(GT, HT, n_pad, in_dim, dst_f32=partial, f32_begin=0, f32_end=in_dim,
+                                       f32_ld=in_dim, k_splits=splits, f32_split_stride=out_dim * in_dim,
+                                       rows_cap=out_dim)
+            gW = torch.empty(out_dim, in_dim, device=dev, dtype=torch.float32)
+            _lib.check(lib.nefii_reduce_splits(sp, partial.data_ptr(), used, out_dim * in_dim, out_dim, in_dim, in_dim,
+                                               gW.data_ptr()))
+            grads_w[l], grads_b[l] = gW, gb
+            if l > 0:
+                wt = ops.split_to_planes(W, rows_pad=ops.round_up(in_dim, 256), cols_pad=ops.round_up(out_dim, 64), transpose=True)
+                G_prev = _planes(n, ops.round_up(in_dim, 64), dev)
+                ops.gemm_split_bf16(G, wt, ops.round_up(out_dim, 64), in_dim, mode=1, act=act, dst=G_prev, dst_ncols=in_dim,
+                                    dst_zero_to=ops.round_up(in_dim, 64), sav=h_prev, sav_ncols=in_dim)
+                G = G_prev
+        out = [None] * (n_lead + ctx.n_seg)
+        for l in range(L):
+            out += [grads_w[l] if ctx.needs[2 * l] else None, grads_b[l] if ctx.needs[2 * l + 1] else None]
+        out += [gw_last if ctx.needs[2 * L] else None, gb_last if ctx.needs[2 * L + 1] else None]
+        ctx.acts = None
+        return tuple(out)
+
+
+def dense_mlp(segments, weights, biases, act):
+    """segments: [(tensor [N,w], n_freqs | -1)], weights/biases: hidden layers then the output layer.
+    Returns the output layer's raw result [N, n_out] (n_out <= 4)."""
+    seg_src = [t for t, _ in segments]
+    for t in seg_src:
+        if t.requires_grad:
+            raise _lib.NefiiError("dense_mlp: gradients w.r.t. the MLP inputs are outside the hot-path scope "
+                                  "(geometry must be frozen, as in the reference's step 2)")
+    seg_freqs = tuple(f for _, f in segments)
+    params = []
+    for w, b in zip(weights, biases):
+        params += [w, b]
+    return _DenseMlp.apply(act, seg_freqs, len(weights) - 1, *seg_src, *params)

@@ -25,6 +25,7 @@ class GemmDesc(ctypes.Structure):
         ("w_last", c_void_p), ("b_last", c_void_p), ("n_last", c_int), ("w_last_ld", c_int), ("dst_last", c_void_p),
         ("seed_hi", c_void_p), ("seed_lo", c_void_p), ("seed_ld", c_int),
         ("sav_hi", c_void_p), ("sav_lo", c_void_p), ("sav_ld", c_int), ("sav_ncols", c_int), ("sav_scale", c_float),
+        ("k_splits", c_int), ("f32_split_stride", ctypes.c_int64), ("k_splits_used", c_int),
     ]
 
 
@@ -53,11 +54,12 @@ def split_to_planes(src, rows_pad=None, cols_pad=None, transpose=False, scale=1.
 
 
 def gemm_split_bf16(a, b, k_pad, n_valid, *, mode=0, act=ACT_NONE, bias=None, out_scale=1.0, count=None,
-                    dst=None, dst_col0=0, dst_ncols=0, dst_f32=None, f32_begin=0, f32_end=0,
-                    w_last=None, b_last=None, dst_last=None, seed=None, sav=None, sav_ncols=0, sav_scale=1.0):
+                    dst=None, dst_col0=0, dst_ncols=0, dst_zero_to=0, dst_f32=None, f32_begin=0, f32_end=0, f32_ld=None,
+                    w_last=None, b_last=None, dst_last=None, seed=None, sav=None, sav_ncols=0, sav_scale=1.0,
+                    k_splits=1, f32_split_stride=0, rows_cap=None):
     """a=(hi,lo) activations planes [rows_cap, a_ld], b=(hi,lo) weight planes [n_pad, b_ld]."""
     d = GemmDesc()
-    d.a_hi, d.a_lo, d.a_ld, d.rows_cap = _p(a[0]), _p(a[1]), a[0].stride(0), a[0].shape[0]
+    d.a_hi, d.a_lo, d.a_ld, d.rows_cap = _p(a[0]), _p(a[1]), a[0].stride(0), (a[0].shape[0] if rows_cap is None else rows_cap)
     d.b_hi, d.b_lo, d.b_ld, d.n_pad = _p(b[0]), _p(b[1]), b[0].stride(0), b[0].shape[0]
     d.k_pad = k_pad
     d.count = _p(count)
@@ -66,9 +68,10 @@ def gemm_split_bf16(a, b, k_pad, n_valid, *, mode=0, act=ACT_NONE, bias=None, ou
     d.out_scale = out_scale
     if dst is not None:
         d.dst_hi, d.dst_lo, d.dst_ld = _p(dst[0]), _p(dst[1]), dst[0].stride(0)
-        d.dst_col0, d.dst_ncols = dst_col0, dst_ncols
+        d.dst_col0, d.dst_ncols, d.dst_zero_to = dst_col0, dst_ncols, dst_zero_to
     if dst_f32 is not None:
-        d.dst_f32, d.f32_ld, d.f32_begin, d.f32_end = _p(dst_f32), dst_f32.stride(0), f32_begin, f32_end
+        d.dst_f32, d.f32_begin, d.f32_end = _p(dst_f32), f32_begin, f32_end
+        d.f32_ld = dst_f32.stride(0) if f32_ld is None else f32_ld
     if w_last is not None:
         d.w_last, d.b_last, d.n_last, d.w_last_ld = _p(w_last), _p(b_last), w_last.shape[0], w_last.stride(0)
         d.dst_last = _p(dst_last)
@@ -77,7 +80,9 @@ def gemm_split_bf16(a, b, k_pad, n_valid, *, mode=0, act=ACT_NONE, bias=None, ou
     if sav is not None:
         d.sav_hi, d.sav_lo, d.sav_ld = _p(sav[0]), _p(sav[1]), sav[0].stride(0)
         d.sav_ncols, d.sav_scale = sav_ncols, sav_scale
+    d.k_splits, d.f32_split_stride = k_splits, f32_split_stride
     _lib.check(_lib.raw().nefii_gemm_split_bf16(_lib.stream_ptr(a[0].device), ctypes.byref(d)))
+    return d.k_splits_used
 
 
 class SdfConfig(ctypes.Structure):
