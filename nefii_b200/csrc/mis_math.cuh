@@ -41,14 +41,19 @@ template <typename T> NEFII_HD void load_mix_lobe(const T* raw7, MixLobe<T>& L) 
   sgm::unit3(raw7, L.axis);
   L.sharp = m_abs(raw7[3]);
   L.amp[0] = m_abs(raw7[4]); L.amp[1] = m_abs(raw7[5]); L.amp[2] = m_abs(raw7[6]);
-  L.energy = (L.amp[0] + L.amp[1]) + L.amp[2];
+  L.energy = sgm::sum3(L.amp[0], L.amp[1], L.amp[2]);
   L.c = L.sharp / (K<T>::two_pi * (T(1) - m_exp(T(-2) * L.sharp)));
 }
 
+NEFII_HD float m_fma(float a, float b, float c) { return fmaf(a, b, c); }
+NEFII_HD double m_fma(double a, double b, double c) { return fma(a, b, c); }
+
+// torch.cross is ONE kernel (a1*b2 - a2*b1 per component), which nvcc contracts to fma(a1, b2, -(a2*b1));
+// everything else in the reference is one torch op per arithmetic operation (no contraction).
 template <typename T> NEFII_HD void cross3(const T* a, const T* b, T* c) {
-  c[0] = a[1] * b[2] - a[2] * b[1];
-  c[1] = a[2] * b[0] - a[0] * b[2];
-  c[2] = a[0] * b[1] - a[1] * b[0];
+  c[0] = m_fma(a[1], b[2], -(a[2] * b[1]));
+  c[1] = m_fma(a[2], b[0], -(a[0] * b[2]));
+  c[2] = m_fma(a[0], b[1], -(a[1] * b[0]));
 }
 
 // rotate_to_normal: local (z = n) -> world

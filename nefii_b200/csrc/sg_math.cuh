@@ -43,8 +43,11 @@ template <typename T> NEFII_HD T clamp_min(T x, T lo) { return x < lo ? lo : x; 
 template <typename T> NEFII_HD T clamp_max(T x, T hi) { return x > hi ? hi : x; }
 template <typename T> NEFII_HD T nan_min(T a, T b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
 
-template <typename T> NEFII_HD T dot3(const T* a, const T* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
-template <typename T> NEFII_HD T norm3(const T* a) { return m_sqrt((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]); }
+// torch.sum / torch.norm over a contiguous innermost axis of 3 reduce as a tree: (x0 + x2) + x1
+// (measured on B200 with torch 2.11, tools/diag_gpu.py dotorder: 100 % bit-exact against this association)
+template <typename T> NEFII_HD T sum3(T x0, T x1, T x2) { return (x0 + x2) + x1; }
+template <typename T> NEFII_HD T dot3(const T* a, const T* b) { return sum3(a[0] * b[0], a[1] * b[1], a[2] * b[2]); }
+template <typename T> NEFII_HD T norm3(const T* a) { return m_sqrt(sum3(a[0] * a[0], a[1] * a[1], a[2] * a[2])); }
 
 // v / (|v| + 1e-6)
 template <typename T> NEFII_HD void unit3(const T* v, T* out, T eps = K<T>::eps) {

@@ -7,6 +7,14 @@ from oracle import mlp as omlp
 pytestmark = pytest.mark.gpu
 
 
+def _check_grad(got, want):
+    """rel 1e-3 in the Frobenius sense; single entries may move more where a ReLU/ELU pre-activation sits within
+    float rounding of its kink (the mask flips for any forward that is not bit-identical to cuBLAS)."""
+    rel = (got - want).norm().item() / (want.norm().item() + 1e-20)
+    assert rel < 1e-3, rel
+    assert (got - want).abs().max().item() <= 5e-3 * (want.abs().max().item() + 1e-12)
+
+
 def _grads(params):
     return [p.grad.clone() for p in params]
 
@@ -33,8 +41,7 @@ def test_radiance_net_forward_backward(cuda_device, n):
     assert torch.allclose(out, ref.detach(), rtol=2e-4, atol=2e-5)
     (out * gy).sum().backward()
     for got, want in zip(_grads(p.tensors()), ref_grads):
-        scale = want.abs().max().item() + 1e-12
-        assert (got - want).abs().max().item() <= 1e-3 * scale, ((got - want).abs().max().item(), scale)
+        _check_grad(got, want)
 
 
 def test_material_net_forward_backward(cuda_device):
@@ -59,8 +66,7 @@ def test_material_net_forward_backward(cuda_device):
     assert torch.allclose(rough, r_ref.detach(), rtol=1e-4, atol=1e-5)
     ((albedo * ga).sum() + (rough * gr).sum()).backward()
     for got, want in zip(_grads(p.tensors()), ref_grads):
-        scale = want.abs().max().item() + 1e-12
-        assert (got - want).abs().max().item() <= 1e-3 * scale
+        _check_grad(got, want)
 
 
 def test_no_grad_path_and_empty(cuda_device):

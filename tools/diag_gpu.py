@@ -184,6 +184,103 @@ def diag_trace():
             print(line)
 
 
+def diag_mis():
+    from nefii_b200 import integrator
+    from oracle import mis
+    dev = torch.device("cuda:0")
+    n = 20000
+    normal, view, albedo = [x.to(dev) for x in inputs.shading_inputs(n, seed=0)]
+    g = torch.Generator().manual_seed(1)
+    rough = (torch.rand(n, 1, generator=g) * 0.9 + 0.089).to(dev)
+    lgt = inputs.synthetic_light_sgs(128, seed=2).to(dev)
+    u = torch.rand(n, 7, generator=g).to(dev)
+    wi, pdf, weight, mat = integrator.mis_sample(lgt, rough, normal, view, u, want_matrix=True)
+    o_wi, o_pdf, o_mat = mis.sample_directions(lgt, rough, normal, view, u)
+    for s in range(3):
+        dw = (wi[s] - o_wi[s]).abs().amax(-1)
+        rp = ((pdf[s] - o_pdf[s, :, 0]).abs() / o_pdf[s, :, 0].abs().clamp_min(1e-6))
+        print("MIS sample %d: wi maxdiff %.2e frac<2e-4 %.5f bitexact %.3f | pdf rel p99 %.2e max %.2e bitexact %.3f" % (
+            s, dw.max().item(), (dw < 2e-4).float().mean().item(), (wi[s] == o_wi[s]).all(-1).float().mean().item(),
+            rp.kthvalue(int(0.99 * n))[0].item(), rp.max().item(), (pdf[s] == o_pdf[s, :, 0]).float().mean().item()))
+        for j in range(3):
+            rm = ((mat[s, j] - o_mat[s, j, :, 0]).abs() / o_mat[s, j, :, 0].abs().clamp_min(1e-6))
+            print("     mat[%d][%d] rel p99 %.2e max %.2e" % (s, j, rm.kthvalue(int(0.99 * n))[0].item(), rm.max().item()))
+
+
+def diag_dense():
+    from nefii_b200 import mlp, ops
+    from oracle import mlp as omlp
+    dev = torch.device("cuda:0")
+    for n in (500, 6000):
+        g = torch.Generator().manual_seed(n)
+        pts = (torch.rand(n, 3, generator=g) - 0.5).to(dev)
+        nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(dev)
+        view = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(dev)
+        feat = torch.rand(n, 512, generator=g).to(dev)
+        p = omlp.radiance_init(seed=2).to(dev)
+        p.requires_grad_(True)
+        gy = torch.rand(n, 3, generator=g).to(dev)
+        ref = omlp.radiance_forward(p, pts, nrm, view, feat)
+        (ref * gy).sum().backward()
+        ref_grads = [t.grad.clone() for t in p.tensors()]
+        for t in p.tensors():
+            t.grad = None
+        raw = mlp.dense_mlp([(pts, 10), (view, 4), (nrm, -1), (feat, -1)], p.W, p.b, ops.ACT_RELU)
+        out = raw ** 2
+        print("DENSE n=%d fwd max abs err %.2e (ref max %.2e)" % (n, (out - ref).abs().max().item(), ref.abs().max().item()))
+        (out * gy).sum().backward()
+        for i, (t, want) in enumerate(zip(p.tensors(), ref_grads)):
+            print("   grad %d shape %s: max err %.2e scale %.2e" % (i, tuple(want.shape), (t.grad - want).abs().max().item(), want.abs().max().item()))
+
+
+def diag_dotorder():
+    """Which association does torch use for 3-element sum / norm / cross on this device?"""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    a = torch.randn(200000, 3, device=dev); b = torch.randn(200000, 3, device=dev)
+    p = a * b
+    s = torch.sum(p, dim=-1)
+    cands = {"(0+1)+2": (p[:, 0] + p[:, 1]) + p[:, 2], "(0+2)+1": (p[:, 0] + p[:, 2]) + p[:, 1], "0+(1+2)": p[:, 0] + (p[:, 1] + p[:, 2])}
+    for k, v in cands.items():
+        print("SUM3 %s: bitexact %.4f" % (k, (v == s).float().mean().item()))
+    s4 = torch.sum(p.reshape(-1, 1, 1, 3).expand(-1, 4, 1, 3), dim=-1)[:, 0, 0]
+    for k, v in cands.items():
+        print("SUM3(expanded) %s: bitexact %.4f" % (k, (v == s4).float().mean().item()))
+    sk = torch.sum(p, dim=-1, keepdim=True)[:, 0]
+    print("keepdim same as not:", (sk == s).all().item())
+    nrm = torch.norm(a, dim=-1)
+    q = a * a
+    ncands = {"sqrt((0+1)+2)": torch.sqrt((q[:, 0] + q[:, 1]) + q[:, 2]), "sqrt((0+2)+1)": torch.sqrt((q[:, 0] + q[:, 2]) + q[:, 1]),
+              "sqrt(0+(1+2))": torch.sqrt(q[:, 0] + (q[:, 1] + q[:, 2])),
+              "fma chain": torch.sqrt(torch.addcmul(torch.addcmul(q[:, 0], a[:, 1], a[:, 1]), a[:, 2], a[:, 2]))}
+    for k, v in ncands.items():
+        print("NORM3 %s: bitexact %.4f" % (k, (v == nrm).float().mean().item()))
+    nk = torch.norm(a, dim=-1, keepdim=True)[:, 0]
+    print("norm keepdim same:", (nk == nrm).all().item())
+    nrm2 = a.norm(2, 1)
+    print("a.norm(2,1) same:", (nrm2 == nrm).all().item())
+    c = torch.cross(a, b, dim=-1)
+    c_plain = a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1]
+    c_fma = torch.addcmul(-(a[:, 2] * b[:, 1]), a[:, 1], b[:, 2])
+    c_fma2 = -torch.addcmul(-(a[:, 1] * b[:, 2]), a[:, 2], b[:, 1])
+    print("CROSS plain %.4f fma(a1*b2 fused) %.4f fma(a2*b1 fused) %.4f" % ((c[:, 0] == c_plain).float().mean().item(),
+          (c[:, 0] == c_fma).float().mean().item(), (c[:, 0] == c_fma2).float().mean().item()))
+    # sum over 128 (dim=-2) order is not reproducible by a sequential loop; report how far a sequential sum is
+    x = torch.rand(5000, 128, 3, device=dev)
+    seq = torch.zeros(5000, 3, device=dev)
+    for m in range(128):
+        seq = seq + x[:, m]
+    ts = x.sum(-2)
+    print("SUM128 sequential vs torch: bitexact %.4f max rel %.2e" % ((seq == ts).float().mean().item(), ((seq - ts).abs() / ts).max().item()))
+    # F.normalize and pow
+    r = torch.rand(100000, device=dev) + 0.05
+    print("pow4: powf %.4f (r*r)*(r*r) %.4f ((r*r)*r)*r %.4f" % ((torch.pow(r, 4) == torch.pow(r, torch.tensor(4.0, device=dev))).float().mean().item(),
+          (torch.pow(r, 4) == (r * r) * (r * r)).float().mean().item(), (torch.pow(r, 4) == ((r * r) * r) * r).float().mean().item()))
+    print("div by python scalar == mul by reciprocal: %.4f ; == true division %.4f" % (
+        ((r / 3.141592653589793) == r * torch.tensor(1.0 / 3.14159274, device=dev).float()).float().mean().item(),
+        ((r / 3.141592653589793) == r / torch.tensor(3.141592653589793, device=dev)).float().mean().item()))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["sg", "gemm"]
     print(torch.cuda.get_device_name(0))
