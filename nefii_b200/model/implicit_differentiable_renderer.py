@@ -1,0 +1,450 @@
+"""Drop-in for the reference's code/model/implicit_differentiable_renderer.py.
+
+``IDRNetwork(conf)`` / ``.forward(input, with_point=False)`` keep the reference's signature, output-dict keys
+(:460-477), attributes (``implicit_network``, ``rendering_network``, ``envmap_material_network``, ``ray_tracer``,
+``freeze_*``) and ``state_dict`` keys (``implicit_network.lin{l}.{weight_g,weight_v,bias}``, ...), so
+``train.model_class = nefii_b200.model.implicit_differentiable_renderer.IDRNetwork`` is the only change a
+conf needs (utils/general.py:10-16 get_class is the plug-in point).
+
+Scope: the per-ray-batch rendering path with FROZEN geometry (step 2 training, rendering,
+evaluation).  Everything device-side runs through the C ABI; there is no PyTorch fallback.  Paths that need
+gradients into the SDF network (step 1 / un-frozen geometry: eikonal points, SampleNetwork) raise.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib, integrator, mlp, ops
+from ..utils import rend_util
+from .embedder import get_embedder
+from .path_tracing_render import pt_render_indirect_mlp
+from .ray_tracing import RayTracing
+from .sample_network import SampleNetwork
+from .sg_envmap_material import EnvmapMaterialNetwork
+from .sg_render import render_with_sg
+
+
+def _effective_weight(lin):
+    """g * v / ||v|| for weight-normed layers (same op torch's weight_norm hook runs), else the plain weight."""
+    if hasattr(lin, "weight_g"):
+        return torch._weight_norm(lin.weight_v, lin.weight_g, 0)
+    return lin.weight
+
+
+class ImplicitNetwork(nn.Module):
+    def __init__(
+            self,
+            feature_vector_size,
+            d_in,
+            d_out,
+            dims,
+            geometric_init=True,
+            bias=1.0,
+            skip_in=(),
+            weight_norm=True,
+            multires=0,
+            use_last_as_f=False
+    ):
+        super().__init__()
+        if not use_last_as_f or feature_vector_size != dims[-1] or d_in != 3 or d_out != 1 or len(skip_in) > 1:
+            raise NotImplementedError("nefii_b200: ImplicitNetwork is built for the use_last_as_f layout of conf.conf "
+                                      "(feature vector = input of the last layer, d_in 3, d_out 1, one skip)")
+        if len(set(dims)) != 1:
+            raise NotImplementedError("nefii_b200: hidden layers must share one width")
+        self.feature_vector_size = feature_vector_size
+        dims = [d_in] + list(dims) + [d_out]
+        self.embed_fn = None
+        self.multires = multires
+        if multires > 0:
+            self.embed_fn, input_ch = get_embedder(multires)
+            dims[0] = input_ch
+        self.num_layers = len(dims)
+        self.skip_in = skip_in
+        self.use_last_as_f = use_last_as_f
+        for l in range(0, self.num_layers - 1):
+            out_dim = dims[l + 1] - dims[0] if l + 1 in self.skip_in else dims[l + 1]
+            lin = nn.Linear(dims[l], out_dim)
+            if geometric_init:
+                if l == self.num_layers - 2:
+                    torch.nn.init.normal_(lin.weight, mean=np.sqrt(np.pi) / np.sqrt(dims[l]), std=0.0001)
+                    torch.nn.init.constant_(lin.bias, -bias)
+                elif multires > 0 and l == 0:
+                    torch.nn.init.constant_(lin.bias, 0.0)
+                    torch.nn.init.constant_(lin.weight[:, 3:], 0.0)
+                    torch.nn.init.normal_(lin.weight[:, :3], 0.0, np.sqrt(2) / np.sqrt(out_dim))
+                elif multires > 0 and l in self.skip_in:
+                    torch.nn.init.constant_(lin.bias, 0.0)
+                    torch.nn.init.normal_(lin.weight, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+                    torch.nn.init.constant_(lin.weight[:, -(dims[0] - 3):], 0.0)
+                else:
+                    torch.nn.init.constant_(lin.bias, 0.0)
+                    torch.nn.init.normal_(lin.weight, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+            if weight_norm:
+                lin = nn.utils.weight_norm(lin)
+            setattr(self, "lin" + str(l), lin)
+        self.softplus = nn.Softplus(beta=100)
+        self._width = dims[1]
+        self._n_hidden = self.num_layers - 2
+        self._sdf_mlp = None
+        self._packed_versions = None
+
+    # ---- packed-weight management ---------------------------------------------------------------
+    def _layers(self):
+        return [getattr(self, "lin" + str(l)) for l in range(self.num_layers - 1)]
+
+    def _sync(self, device):
+        params = list(self.parameters())
+        versions = tuple((p.data_ptr(), p._version) for p in params) + (str(device),)
+        if self._sdf_mlp is None or self._sdf_mlp.device != torch.device(device):
+            skip = self.skip_in[0] if len(self.skip_in) else 0
+            self._sdf_mlp = ops.SdfMlp(n_freqs=self.multires, width=self._width, n_hidden=self._n_hidden,
+                                       skip_layer=skip, device=device)
+            self._packed_versions = None
+        if versions != self._packed_versions:
+            with torch.no_grad():
+                ws = [_effective_weight(l) for l in self._layers()]
+                bs = [l.bias for l in self._layers()]
+            self._sdf_mlp.set_weights(ws, bs)
+            self._packed_versions = versions
+        return self._sdf_mlp
+
+    def nefii_sdf_source(self):
+        dev = next(self.parameters()).device
+        net = self._sync(dev)
+        return 0, net.handle.value, 0, net
+
+    def _check_frozen(self):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise _lib.NefiiError("nefii_b200: the SDF network runs inference-only on the accelerated path; call "
+                                  "model.freeze_geometry() (step 2 / rendering) or wrap the call in torch.no_grad()")
+
+    def evaluate(self, x, want_feat=False, want_grad=False):
+        """Fused pass: (sdf [N], feature [N,W] | None, d sdf/dx [N,3] | None)."""
+        self._check_frozen()
+        net = self._sync(x.device)
+        return net.eval(x.detach(), want_feat=want_feat, want_grad=want_grad)
+
+    # ---- reference API -----------------------------------------------------------------------------
+    def forward(self, input, compute_grad=False):
+        sdf, feat, _ = self.evaluate(input, want_feat=True)
+        return torch.cat([sdf.unsqueeze(-1), feat], dim=-1)
+
+    def gradient(self, x, no_grad=False):
+        if not no_grad:
+            raise _lib.NefiiError("nefii_b200: ImplicitNetwork.gradient(create_graph=True) needs a trainable geometry, "
+                                  "which is outside the accelerated path")
+        _, _, g = self.evaluate(x, want_grad=True)
+        return g.unsqueeze(1)
+
+
+class RenderingNetwork(nn.Module):
+    def __init__(
+            self,
+            feature_vector_size,
+            mode,
+            d_in,
+            d_out,
+            dims,
+            weight_norm=True,
+            weight_init=False,
+            multires_view=0,
+            multires_xyz=0,
+            normalize_output=True,
+            clip_output=False,
+            clip_method="relu",
+    ):
+        super().__init__()
+        if mode != 'idr' or d_out > 4:
+            raise NotImplementedError("nefii_b200: RenderingNetwork supports mode 'idr'")
+        self.normalize_output = normalize_output
+        self.clip_output = clip_output
+        self.clip_method = clip_method
+        self.feature_vector_size = feature_vector_size
+        self.mode = mode
+        dims = [d_in + feature_vector_size] + list(dims) + [d_out]
+        self.multires_view, self.multires_xyz = multires_view, multires_xyz
+        self.embedview_fn = None
+        if multires_view > 0:
+            self.embedview_fn, input_ch = get_embedder(multires_view)
+            dims[0] += (input_ch - 3)
+        self.embedxyz_fn = None
+        if multires_xyz > 0:
+            self.embedxyz_fn, input_ch = get_embedder(multires_xyz)
+            dims[0] += (input_ch - 3)
+        self.num_layers = len(dims)
+        for l in range(0, self.num_layers - 1):
+            lin = nn.Linear(dims[l], dims[l + 1])
+            if weight_norm:
+                lin = nn.utils.weight_norm(lin)
+            setattr(self, "lin" + str(l), lin)
+        if weight_init:
+            for l in range(0, self.num_layers - 2):
+                lin = getattr(self, "lin" + str(l))
+                nn.init.kaiming_uniform_(lin.weight, mode='fan_in', nonlinearity='relu')
+                nn.init.constant_(lin.bias, 0.0)
+            lin = getattr(self, "lin" + str(self.num_layers - 2))
+            nn.init.constant_(lin.bias, 0.0)
+            if self.normalize_output:
+                nn.init.xavier_uniform_(lin.weight, gain=nn.init.calculate_gain('tanh'))
+            elif self.clip_method == "relu":
+                nn.init.kaiming_uniform_(lin.weight, mode='fan_in', nonlinearity='relu')
+        self.relu = nn.ReLU()
+        self.tanh = nn.Tanh()
+
+    def forward(self, points, normals, view_dirs, feature_vectors=None):
+        segments = [(points, self.multires_xyz if self.multires_xyz > 0 else -1),
+                    (view_dirs, self.multires_view if self.multires_view > 0 else -1),
+                    (normals, -1)]
+        if feature_vectors is not None:
+            segments.append((feature_vectors, -1))
+        layers = [getattr(self, "lin" + str(l)) for l in range(self.num_layers - 1)]
+        x = mlp.dense_mlp(segments, [_effective_weight(l) for l in layers], [l.bias for l in layers], ops.ACT_RELU)
+        if self.normalize_output:
+            return (self.tanh(x) + 1.) / 2.
+        elif not self.clip_output:
+            return x
+        elif self.clip_method == "relu":
+            return self.relu(x)
+        elif self.clip_method == "abs":
+            return torch.abs(x)
+        elif self.clip_method == "relu_init":
+            return self.relu(x) + 0.5
+        elif self.clip_method == "pow2":
+            return x ** 2
+        raise NotImplementedError(self.clip_method)
+
+
+class IDRNetwork(nn.Module):
+    def __init__(self, conf):
+        super().__init__()
+        self.feature_vector_size = conf.get_int('feature_vector_size')
+        self.correct_normal = conf.get_bool('correct_normal', default=False)
+        self.implicit_network = ImplicitNetwork(self.feature_vector_size, **conf.get_config('implicit_network'))
+        self.rendering_network = RenderingNetwork(self.feature_vector_size, **conf.get_config('rendering_network'))
+        self.envmap_material_network = EnvmapMaterialNetwork(correct_normal=self.correct_normal,
+                                                             feature_vector_size=self.feature_vector_size,
+                                                             **conf.get_config('envmap_material_network'))
+        self.ray_tracer = RayTracing(**conf.get_config('ray_tracer'))
+        self.sample_network = SampleNetwork()
+        self.object_bounding_sphere = conf.get_float('ray_tracer.object_bounding_sphere')
+        self.render_type = conf.get_string('render_type', default='sg')
+        self.rgb_render = self.get_rgb_render(self.render_type)
+        self.fast_multi_ray = conf.get_bool('fast_multi_ray', default=False)
+        self.render_background = conf.get_bool('render_background', default=False)
+        if self.fast_multi_ray:
+            raise NotImplementedError("nefii_b200: fast_multi_ray is not used by the shipped confs")
+        self.state_freeze_geo = False
+        self.state_freeze_idr = False
+        self.state_freeze_env_mat = False
+
+    # ---- freezing API (idr_train.py:621-638) -------------------------------------------------------
+    def freeze_geometry(self):
+        for param in self.implicit_network.parameters():
+            param.requires_grad = False
+        self.state_freeze_geo = True
+
+    def unfreeze_geometry(self):
+        for param in self.implicit_network.parameters():
+            param.requires_grad = True
+        self.state_freeze_geo = False
+
+    def freeze_idr(self):
+        self.freeze_geometry()
+        for param in self.rendering_network.parameters():
+            param.requires_grad = False
+        self.state_freeze_idr = True
+
+    def unfreeze_idr(self):
+        self.unfreeze_geometry()
+        for param in self.rendering_network.parameters():
+            param.requires_grad = True
+        self.state_freeze_idr = False
+
+    def freeze_decompose_render(self):
+        for param in self.envmap_material_network.parameters():
+            param.requires_grad = False
+        self.state_freeze_env_mat = True
+
+    def unfreeze_decompose_render(self):
+        for param in self.envmap_material_network.parameters():
+            param.requires_grad = True
+        self.state_freeze_env_mat = False
+
+    def train(self, mode: bool = True):
+        nn.Module.train(self, mode)
+        if self.state_freeze_idr:
+            self.rendering_network.eval()
+        if self.state_freeze_geo:
+            self.implicit_network.eval()
+        if self.state_freeze_env_mat:
+            self.envmap_material_network.eval()
+        return self
+
+    def forward(self, input, with_point=False):
+        if not with_point:
+            return self.forward_with_uv(input)
+        return self.forward_with_point(input)
+
+    # ---- implicit_differentiable_renderer.py:312-501 ---------------------------------------------------
+    def forward_with_uv(self, input, uniforms=None, trace_uniforms=None):
+        if self.training and not self.state_freeze_geo:
+            raise _lib.NefiiError("nefii_b200: training with an un-frozen geometry (step 1 / eikonal + SampleNetwork) is "
+                                  "outside the accelerated path; call freeze_geometry() as run_s2.sh does")
+        intrinsics = input["intrinsics"]
+        uv = input["uv"]
+        pose = input["pose"]
+        object_mask = input["object_mask"].reshape(-1)
+        multi_ray_per_pix = len(uv.shape) == 4
+        if multi_ray_per_pix:
+            B, S, R, D = uv.shape
+            uv = uv.reshape(B, S * R, D)
+            object_mask = object_mask.reshape(B, S, 1).expand(B, S, R).reshape(-1)
+        ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics)
+        batch_size, num_pixels, _ = ray_dirs.shape
+
+        with torch.no_grad():
+            points, network_object_mask, dists = self.ray_tracer(sdf=self.implicit_network, cam_loc=cam_loc,
+                                                                 object_mask=object_mask, ray_directions=ray_dirs,
+                                                                 uniforms=trace_uniforms)
+            points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
+            sdf_all, _, _ = self.implicit_network.evaluate(points)
+            sdf_output = sdf_all.unsqueeze(-1)
+        ray_dirs = ray_dirs.reshape(-1, 3)
+        surface_mask = network_object_mask
+        differentiable_surface_points = points[surface_mask]
+        grad_theta = None
+
+        ones = torch.ones_like(points)
+        idr_rgb_values, sg_rgb_values, normal_values = ones.clone(), ones.clone(), ones.clone()
+        sg_diffuse_rgb_values, sg_diffuse_albedo_values = ones.clone(), ones.clone()
+        sg_specular_rgb_values = torch.zeros_like(points)
+        sg_roughness_values = torch.zeros_like(points[..., 0:1])
+        sg_specular_reflection_values = torch.zeros_like(points)
+        ret = {}
+        if differentiable_surface_points.shape[0] > 0:
+            view_dirs = -ray_dirs[surface_mask]
+            ret = self.get_rbg_value(differentiable_surface_points, view_dirs, uniforms=uniforms)
+            idr_rgb_values = idr_rgb_values.index_put((surface_mask,), ret['idr_rgb'])
+            sg_rgb_values = sg_rgb_values.index_put((surface_mask,), ret['sg_rgb'])
+            normal_values = normal_values.index_put((surface_mask,), ret['normals'])
+            sg_diffuse_rgb_values = sg_diffuse_rgb_values.index_put((surface_mask,), ret['sg_diffuse_rgb'])
+            sg_diffuse_albedo_values = sg_diffuse_albedo_values.index_put((surface_mask,), ret['sg_diffuse_albedo'])
+            sg_specular_rgb_values = sg_specular_rgb_values.index_put((surface_mask,), ret['sg_specular_rgb'])
+            sg_roughness_values = sg_roughness_values.index_put((surface_mask,), ret['sg_roughness'])
+            spec = ret['sg_specular_reflectance']
+            sg_specular_reflection_values = sg_specular_reflection_values.index_put(
+                (surface_mask,), spec.expand(differentiable_surface_points.shape[0], 3))
+
+        background_mask = ~surface_mask
+        if self.render_background and bool(background_mask.any()):
+            background_rgb = self.get_background_rgb(ray_dirs[background_mask])
+            sg_rgb_values = sg_rgb_values.index_put((background_mask,), background_rgb)
+
+        output = {
+            'points': points,
+            'idr_rgb_values': idr_rgb_values,
+            'sg_rgb_values': sg_rgb_values,
+            'normal_values': normal_values,
+            'sdf_output': sdf_output,
+            'network_object_mask': network_object_mask,
+            'object_mask': object_mask,
+            'grad_theta': grad_theta,
+            'sg_diffuse_rgb_values': sg_diffuse_rgb_values,
+            'sg_diffuse_albedo_values': sg_diffuse_albedo_values,
+            'sg_specular_rgb_values': sg_specular_rgb_values,
+            'sg_roughness_values': sg_roughness_values,
+            'sg_specular_reflection_values': sg_specular_reflection_values,
+            'secondary_points': ret.get('secondary_points', None),
+            'secondary_mask': ret.get('secondary_mask', None),
+            'secondary_dir': ret.get('secondary_dir', None),
+        }
+        if multi_ray_per_pix:
+            for key in ['idr_rgb_values', 'sg_rgb_values', 'network_object_mask', 'object_mask', 'sg_diffuse_rgb_values',
+                        'sg_diffuse_albedo_values', 'sg_specular_rgb_values', 'sdf_output', 'points', 'sg_roughness_values',
+                        'sg_specular_reflection_values']:
+                output[key] = self.mean_pixel(output[key], B * S, R)
+            output['normal_values'] = self.mean_pixel(output['normal_values'], B * S, R, vector=True)
+        return output
+
+    # ---- implicit_differentiable_renderer.py:503-527 ---------------------------------------------------
+    def forward_with_point(self, input):
+        points = input["points"]
+        ray_dirs = input["ray_dirs"]
+        N, R, _ = points.shape
+        points = points.reshape(-1, 3)
+        ray_dirs = ray_dirs.reshape(-1, 3)
+        view_dirs = -ray_dirs
+        state_freeze_geo = self.state_freeze_geo
+        self.state_freeze_geo = True
+        ret = self.get_rbg_value(points, view_dirs)
+        self.state_freeze_geo = state_freeze_geo
+        return {
+            'idr_rgb_values': self.mean_pixel(ret['idr_rgb'], N, R),
+            'sg_rgb_values': self.mean_pixel(ret['sg_rgb'], N, R),
+        }
+
+    # ---- implicit_differentiable_renderer.py:529-599 ---------------------------------------------------
+    def get_rbg_value(self, points, view_dirs, multi_ray_data_shape=None, uniforms=None):
+        with torch.no_grad():
+            _, feature_vectors, g = self.implicit_network.evaluate(points, want_feat=True, want_grad=True)
+            normals = g / (torch.norm(g, dim=-1, keepdim=True) + 1e-6)
+            view_dirs = view_dirs / (torch.norm(view_dirs, dim=-1, keepdim=True) + 1e-6)
+        ret = {'normals': normals}
+        idr_rgb = self.rendering_network(points, normals, view_dirs, feature_vectors)
+        sg_envmap_material = self.envmap_material_network(points, feature_vectors, normals)
+        ret['idr_rgb'] = idr_rgb
+        if self.render_type in ("pt_render_indirect_mlp",):
+            sg_ret = self.rgb_render(lgtSGs=sg_envmap_material['sg_lgtSGs'],
+                                     specular_reflectance=sg_envmap_material['sg_specular_reflectance'],
+                                     roughness=sg_envmap_material['sg_roughness'],
+                                     diffuse_albedo=sg_envmap_material['sg_diffuse_albedo'],
+                                     normal=normals, viewdirs=view_dirs,
+                                     blending_weights=sg_envmap_material['sg_blending_weights'],
+                                     points=points, model=self, uniforms=uniforms)
+        else:
+            sg_ret = self.rgb_render(lgtSGs=sg_envmap_material['sg_lgtSGs'],
+                                     specular_reflectance=sg_envmap_material['sg_specular_reflectance'],
+                                     roughness=sg_envmap_material['sg_roughness'],
+                                     diffuse_albedo=sg_envmap_material['sg_diffuse_albedo'],
+                                     normal=normals, viewdirs=view_dirs,
+                                     blending_weights=sg_envmap_material['sg_blending_weights'])
+        ret.update(sg_ret)
+        ret.update({
+            'sg_roughness': sg_envmap_material['sg_roughness'],
+            'sg_specular_reflectance': sg_envmap_material['sg_specular_reflectance'],
+            'sg_blending_weights': sg_envmap_material['sg_blending_weights']
+        })
+        return ret
+
+    # ---- implicit_differentiable_renderer.py:646-663 ---------------------------------------------------
+    def get_background_rgb(self, light_dir):
+        return integrator.background_sg(self.envmap_material_network.get_lgtSGs(), light_dir)
+
+    # ---- implicit_differentiable_renderer.py:695-719 ---------------------------------------------------
+    def mean_pixel(self, x, bs, r, vector=False):
+        assert x.shape[0] == bs * r
+        no_dim = len(x.shape) == 1
+        if no_dim:
+            x = x[..., None]
+        bsr, d = x.shape
+        x = x.reshape(bs, r, d)
+        if vector:
+            x = x[:, 0, :]
+        elif x.dtype == torch.float:
+            x = x.mean(1)
+        elif x.dtype == torch.bool:
+            x = x.all(1)
+        else:
+            raise TypeError("mean_pixel: undefined type %s" % x.dtype)
+        if no_dim:
+            x = x[..., 0]
+        return x
+
+    # ---- implicit_differentiable_renderer.py:721-759 ---------------------------------------------------
+    def get_rgb_render(self, render_type: str):
+        if render_type == "sg":
+            return render_with_sg
+        if render_type == "pt_render_indirect_mlp":
+            return pt_render_indirect_mlp
+        raise NotImplementedError("nefii_b200: render_type '%s' is one of the reference's non-default integrator variants "
+                                  "(SURVEY.md section 2: out of scope); supported: 'pt_render_indirect_mlp', 'sg'" % render_type)

@@ -9,13 +9,8 @@ import torch
 from . import inputs, mlp, pipeline, ref_shim, tracer
 
 
-def build_reference_model(om, render_type="pt_render_indirect_mlp"):
-    """IDRNetwork(conf.conf) with the OracleModel's weights copied in, geometry frozen."""
-    ref_shim.install()
-    with contextlib.redirect_stdout(io.StringIO()):
-        from model.implicit_differentiable_renderer import IDRNetwork
-        net = IDRNetwork(ref_shim.model_conf(render_type=render_type, num_lgt_sgs=om.lgtSGs.shape[0],
-                                             width=om.sdf.W[1].shape[0]))
+def load_oracle_weights(net, om):
+    """Copy an OracleModel's weights into an IDRNetwork (the reference's or nefii_b200's: same state_dict keys)."""
     net.implicit_network.load_state_dict(om.sdf.state_dict(""))
     sd = {}
     for l, (w, b) in enumerate(zip(om.radiance.W, om.radiance.b)):
@@ -31,6 +26,16 @@ def build_reference_model(om, render_type="pt_render_indirect_mlp"):
     net.envmap_material_network.load_state_dict(msd)
     net.freeze_geometry()
     return net
+
+
+def build_reference_model(om, render_type="pt_render_indirect_mlp"):
+    """IDRNetwork(conf.conf) of the REAL reference with the OracleModel's weights copied in, geometry frozen."""
+    ref_shim.install()
+    with contextlib.redirect_stdout(io.StringIO()):
+        from model.implicit_differentiable_renderer import IDRNetwork
+        net = IDRNetwork(ref_shim.model_conf(render_type=render_type, num_lgt_sgs=om.lgtSGs.shape[0],
+                                             width=om.sdf.W[1].shape[0]))
+    return load_oracle_weights(net, om)
 
 
 @contextlib.contextmanager
