@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- shaded rays/s of the NeFII per-ray-batch rendering hot path on B200.
+
+Workload (BASELINE.json configs[2], the config the metric "shaded rays/sec (primary+indirect, fwd+bwd)" is quoted
+on): one step-2 training iteration of conf.conf -- num_pixels=2048 (512 2x2 patches of a synthetic 800x800 view)
+x num_rays=64 = 131072 primary rays per GPU, 128 light SGs, 8x512 SDF MLP (PE 6, frozen), near-field indirect
+illumination with 3 importance-sampled secondary rays per hit, forward + loss + backward + both Adam steps.
+Random-init weights of that architecture (the reference's own initialisers), synthetic data.
+
+  python bench.py --gpus N --steps K --warmup W            # N=1 default; N>1: launched by torchrun, one rank per GPU
+  python bench.py --impl reference ...                     # the reference's algorithm on the host CPU (oracle port)
+
+One JSON line on stdout (rank 0).  value = (primary + secondary rays of all ranks) / max-over-ranks device time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "shaded rays/sec (primary+indirect, fwd+bwd)"
+NUM_PIXELS, NUM_RAYS, NUM_SGS, IMG = 2048, 64, 128, 800
+SDF_FLOPS_PER_POINT = 3.671e6      # 1,835,520 MAC forward
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# synthetic scene / inputs
+# --------------------------------------------------------------------------------------------------------------
+def make_camera():
+    K = torch.eye(4)
+    K[0, 0] = K[1, 1] = 2.4 * IMG      # the init-sphere covers ~50 % of the frame
+    K[0, 2] = K[1, 2] = IMG / 2
+    pose = torch.eye(4)
+    pose[:3, 3] = torch.tensor([0.0, 0.0, -3.0])
+    return pose[None], K[None]
+
+
+def make_batch(seed, num_pixels=NUM_PIXELS, num_rays=NUM_RAYS, img=IMG):
+    """What SceneDataset hands the trainer for one iteration (scene_dataset.py:149-177,212-251): num_pixels/4 random
+    2x2 patches, one shared set of num_rays sub-pixel jitters, all-true object mask, GT rgb."""
+    g = torch.Generator().manual_seed(seed)
+    n_patch = num_pixels // 4
+    x0 = torch.randint(0, img - 1, (n_patch,), generator=g)
+    y0 = torch.randint(0, img - 1, (n_patch,), generator=g)
+    px = torch.stack([torch.stack([x0, y0], -1), torch.stack([x0 + 1, y0], -1),
+                      torch.stack([x0, y0 + 1], -1), torch.stack([x0 + 1, y0 + 1], -1)], 1).reshape(-1, 2).float()
+    jitter = torch.rand(num_rays, 2, generator=g) - 0.5
+    uv = (px.unsqueeze(1) + 0.5 + jitter.unsqueeze(0)).unsqueeze(0)          # [1, S, R, 2]
+    object_mask = torch.ones(1, num_pixels, dtype=torch.bool)
+    rgb = torch.rand(num_pixels, 3, generator=g)
+    return uv.contiguous(), object_mask, rgb
+
+
+def idr_loss(out, rgb_gt):
+    """The terms of the reference's IDRLoss that are live in step 2 (model/loss.py:162-186,255-264,278-320 with
+    conf.conf's weights): masked L1 on idr/sg rgb, background L2, 2x2 normal-smoothness.  Stays PyTorch."""
+    net, obj = out['network_object_mask'], out['object_mask']
+    m = net & obj
+    zero = out['sg_rgb_values'].sum() * 0
+    idr = (out['idr_rgb_values'][m] - rgb_gt[m]).abs().mean() if bool(m.any()) else zero
+    sg = (out['sg_rgb_values'][m] - rgb_gt[m]).abs().mean() if bool(m.any()) else zero
+    bg_m = (~net) & (~obj)
+    bg = ((out['sg_rgb_values'][bg_m] - rgb_gt[bg_m]) ** 2).mean() if bool(bg_m.any()) else zero
+    pm = m.reshape(-1, 4).all(-1)
+    ns = torch.var(out['normal_values'].view(-1, 4, 3), dim=1)[pm].mean() if bool(pm.any()) else zero
+    return 1.0 * idr + 1.0 * sg + 1.0 * bg + 1.0 * ns
+
+
+# --------------------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.samples, self.proc, self.gpu = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------
+def build_model(dev):
+    from nefii_b200.model.implicit_differentiable_renderer import IDRNetwork
+    from nefii_b200.utils.conf import default_model_conf
+    torch.manual_seed(0)
+    model = IDRNetwork(default_model_conf(num_lgt_sgs=NUM_SGS)).to(dev)
+    model.freeze_geometry()          # run_s2.sh --freeze_geometry
+    model.train()
+    return model
+
+
+class FlatGrads:
+    """All trainable gradients live in one flat fp32 buffer, so the data-parallel exchange is ONE NCCL all-reduce
+    (12.95 MB) instead of DDP's buckets."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, device=self.params[0].device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce(self, world):
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat)
+            self.flat.div_(world)
+
+
+def run_ours(args):
+    from nefii_b200 import _lib
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    model = build_model(dev)
+    pose, K = [t.to(dev) for t in make_camera()]
+    flat = FlatGrads(model.parameters())
+    idr_params = [p for p in model.rendering_network.parameters() if p.requires_grad]
+    sg_params = [p for p in model.envmap_material_network.parameters() if p.requires_grad]
+    opt_idr = torch.optim.Adam(idr_params, lr=5e-4)
+    opt_sg = torch.optim.Adam(sg_params, lr=5e-4)
+    n_steps = args.steps + args.warmup
+    # every rank renders its own pixel batch (weak scaling, as DDP with a fixed per-GPU num_pixels)
+    host_batches = [make_batch(1000 * rank + i) for i in range(n_steps)]
+    pinned = [[t.pin_memory() for t in b] for b in host_batches]
+    dev_batches = [[t.to(dev) for t in b] for b in host_batches]
+    ray_count = torch.zeros(1, device=dev, dtype=torch.float64)
+
+    def step(uv, obj, rgb, count_rays=True):
+        flat.zero()
+        out = model({'uv': uv, 'object_mask': obj, 'pose': pose, 'intrinsics': K})
+        loss = idr_loss(out, rgb)
+        loss.backward()
+        flat.all_reduce(world)
+        opt_idr.step()
+        opt_sg.step()
+        if count_rays:
+            n_hit = out['secondary_mask'].shape[1] if out['secondary_mask'] is not None else 0
+            ray_count.add_(uv.shape[1] * uv.shape[2] + 3 * n_hit)
+        return loss
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t)
+        return t.item()
+
+    # ---- device-resident timing ------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(*dev_batches[i], count_rays=False)
+    barrier()
+    launches0 = int(_lib.raw().nefii_launch_count())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for i in range(args.warmup, n_steps):
+            step(*dev_batches[i])
+        ev1.record()
+        barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = int(_lib.raw().nefii_launch_count()) - launches0
+    rays = sum_over_ranks(ray_count.item())
+    value = rays / (ms * 1e-3)
+
+    # ---- end to end through the public API: pinned host inputs -> device, loss read back, every step -------------
+    ray_count.zero_()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.warmup, n_steps):
+        uv, obj, rgb = [t.to(dev, non_blocking=True) for t in pinned[i]]
+        loss = step(uv, obj, rgb)
+        _ = loss.item()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    rays_e2e = sum_over_ranks(ray_count.item())
+    h2d = sum(t.numel() * t.element_size() for t in pinned[0])
+
+    # ---- roofline of the dominant kernel (tcgen05 layer GEMM): per-launch CUDA events over one more step ---------
+    lib = _lib.raw()
+    lib.nefii_gemm_profile_enable(1)
+    step(*dev_batches[-1], count_rays=False)
+    import ctypes
+    out3 = (ctypes.c_double * 3)()
+    lib.nefii_gemm_profile_fetch(out3)
+    lib.nefii_gemm_profile_enable(0)
+    gemm_ms, gemm_flops, gemm_launches = out3[0], out3[1], int(out3[2])
+    e_prof0, e_prof1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e_prof0.record()
+    step(*dev_batches[-1], count_rays=False)
+    e_prof1.record()
+    torch.cuda.synchronize()
+    step_ms = e_prof0.elapsed_time(e_prof1)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))     # kernel timed inside a long step -> sustained figure
+    achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {
+        "kernel": "gemm_split_bf16_kernel (tcgen05 kind::f16, 3 MMAs per fp32 product)",
+        "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf if peak_tf else None,
+        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
+        "tensor_issue_frac": 3 * achieved_tf / peak_tf if peak_tf else None,
+        "flops_per_launch_avg": gemm_flops / max(gemm_launches, 1), "launches_per_step": gemm_launches,
+        "kernel_share_of_step": gemm_ms / step_ms if step_ms > 0 else None,
+        "traffic": None,
+    }
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_port_throughput(px=128, rays=4, steps=1, warmup=0)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (MLPs: bf16x3 split on tcgen05, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "step-2 training iteration (BASELINE configs[2]): num_pixels=2048 x num_rays=64 = 131072 "
+                                   "primary rays/GPU + 3 secondary rays per hit, 128 SGs, 8x512 SDF MLP frozen, fwd+loss+bwd+Adam",
+                       "rays_per_step": rays / args.steps, "primary_rays_per_step_per_gpu": NUM_PIXELS * NUM_RAYS,
+                       "l2": "per-step working set (MLP activations, several GB) >> 126 MB L2; a different pixel batch every step",
+                       "parallelism": "dp%d (rays sharded by rank, one flat NCCL all-reduce of 3.2M grads)" % world},
+            "e2e": {"value": rays_e2e / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port) on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def cpu_port_throughput(px, rays, steps, warmup):
+    """Times oracle/pipeline.py (the restated reference, plain torch CPU ops) on a bounded sample of the same
+    workload: `px` pixels x `rays` rays, forward + loss + backward, all host threads."""
+    from oracle import pipeline, ref_harness as rh
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    om = rh.small_model(seed=0, n_sg=NUM_SGS, bumps=0.0)
+    om.lgtSGs.requires_grad_(True)
+    om.material.requires_grad_(True)
+    om.radiance.requires_grad_(True)
+    pose, K = make_camera()
+    total_rays, total_t = 0, 0.0
+    for i in range(warmup + steps):
+        uv, obj, rgb = make_batch(i, num_pixels=px, num_rays=rays)
+        g = torch.Generator().manual_seed(i)
+        U = torch.rand(px * rays, 7, generator=g)
+        vecs = [torch.rand(100, generator=g) for _ in range(2)]
+        t0 = time.perf_counter()
+        out = pipeline.forward_with_uv(om, uv, pose, K, obj, lambda n: U[:n], True, vecs[0], vecs[1])
+        loss = idr_loss(out, rgb)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            n_hit = out['secondary_mask'].shape[1] if out['secondary_mask'] is not None else 0
+            total_rays += px * rays + 3 * n_hit
+            total_t += dt
+    return {"value": total_rays / total_t, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": "%d px x %d rays per step, %d step(s), fwd+loss+bwd, torch CPU %d threads "
+                      "(oracle/pipeline.py restating the reference)" % (px, rays, steps, cores)}
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    n = args.steps + args.warmup
+    px = 64 if n > 6 else 128
+    cpu = cpu_port_throughput(px=px, rays=4, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "rays/s", "n_gpus": env_int("WORLD_SIZE", 1),
+        "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "step-2 training iteration (BASELINE configs[2]) on the host CPU, bounded sample: " + cpu["sample"]},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

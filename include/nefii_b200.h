@@ -27,6 +27,8 @@ extern "C" {
 const char* nefii_last_error(void);
 /* ABI version of this header (bumped on any signature change) */
 int nefii_abi_version(void);
+/* number of CUDA kernels this library has launched since load (bench.py reports the delta per timed region) */
+int64_t nefii_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * SG shading -- replaces render_with_sg, code/model/sg_render.py:164-295 (forward).
@@ -71,6 +73,12 @@ typedef struct nefii_gemm_desc {
 } nefii_gemm_desc;
 
 int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* desc /* host */);
+
+/* Measurement aid (bench.py roofline): while enabled, every nefii layer-GEMM launch is bracketed by CUDA events on its
+ * own stream.  fetch() synchronises those events and returns {total ms, total algorithmic flops (2*rows*n*k, each
+ * fp32 product counted once), number of launches}. */
+int nefii_gemm_profile_enable(int on);
+int nefii_gemm_profile_fetch(double* out3 /* host */);
 
 /* fp32 [rows, cols] (row stride ld_src) -> zero-padded bf16 hi/lo planes [rows_pad, cols_pad];
  * transpose != 0 writes the transpose.  Used to pack weights (and test inputs). */

@@ -16,9 +16,12 @@ c_void_p, c_int, c_float, c_longlong = ctypes.c_void_p, ctypes.c_int, ctypes.c_f
 # symbol -> argtypes; kept in sync with include/nefii_b200.h (tests/test_abi.py checks both ways)
 SIGNATURES = {
     "nefii_abi_version": [],
+    "nefii_launch_count": [],
     "nefii_sg_render_fwd": [c_void_p, c_int, c_int, c_int] + [c_void_p] * 10,
     "nefii_background_sg_fwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "nefii_gemm_split_bf16": [c_void_p, c_void_p],
+    "nefii_gemm_profile_enable": [c_int],
+    "nefii_gemm_profile_fetch": [c_void_p],
     "nefii_assemble_input": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int],
     "nefii_transpose_planes": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "nefii_last_layer_bwd": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
@@ -59,6 +62,7 @@ def _load():
         fn.argtypes = argtypes
         fn.restype = c_int
     lib.nefii_sdf_workspace_bytes.restype = c_longlong
+    lib.nefii_launch_count.restype = c_longlong
     lib.nefii_trace_workspace_bytes.restype = c_longlong
     return lib
 

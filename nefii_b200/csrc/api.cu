@@ -1,4 +1,7 @@
 // extern "C" surface of libnefii_b200.so -- see include/nefii_b200.h for the contract.
+#include <atomic>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 #include "../../include/nefii_b200.h"
 #include "mlp_gemm.cuh"
@@ -11,6 +14,10 @@ char* error_buffer() {
   static thread_local char buf[512] = {0};
   return buf;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -43,6 +50,7 @@ extern "C" {
 
 const char* nefii_last_error(void) { return nefii::error_buffer(); }
 int nefii_abi_version(void) { return 1; }
+int64_t nefii_launch_count(void) { return (int64_t)nefii::launches(); }
 
 int nefii_sg_render_fwd(void* stream, int n_rays, int n_sg, int n_mat, const float* lgt_sgs, const float* specular,
                         const float* roughness, const float* albedo, const float* normal, const float* view,
@@ -190,5 +198,8 @@ int nefii_reduce_splits(void* stream, const float* partial, int n_splits, int64_
                         float* out) {
   return nefii::reduce_splits((cudaStream_t)stream, partial, n_splits, (long long)stride, rows, ld_src, cols, out);
 }
+
+int nefii_gemm_profile_enable(int on) { return nefii::gemm_profile_enable(on); }
+int nefii_gemm_profile_fetch(double* out3) { return nefii::gemm_profile_fetch(out3); }
 
 }  // extern "C"

@@ -31,11 +31,15 @@ int set_error(int code, const char* fmt, ...);
 
 #define NEFII_LAUNCH_CHECK()                                                               \
   do {                                                                                     \
+    ::nefii::count_launch();                                                               \
     cudaError_t e__ = cudaGetLastError();                                                  \
     if (e__ != cudaSuccess)                                                                \
       return ::nefii::set_error(NEFII_ERR_CUDA, "kernel launch failed: %s (%s:%d)",        \
                                 cudaGetErrorString(e__), __FILE__, __LINE__);              \
   } while (0)
+
+// number of kernels this library has launched (nefii_launch_count); bumped by NEFII_LAUNCH_CHECK
+void count_launch();
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -14,6 +14,7 @@
 //                 output layer), overlapped with the MMAs of the next column chunk.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <vector>
 #include "mlp_gemm.cuh"
 
 namespace nefii {
@@ -534,6 +535,46 @@ __global__ void split_to_planes_kernel(const float* __restrict__ src, int rows, 
 
 }  // namespace
 
+namespace {
+struct ProfRec {
+  cudaEvent_t a, b;
+  double flops_per_row;
+  int rows_cap;
+  int* count_host;   // pinned; -1 when the launch had no device row count
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+int gemm_profile_enable(int on) {
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    cudaFreeHost(r.count_host);
+  }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return NEFII_OK;
+}
+
+int gemm_profile_fetch(double* out3) {
+  NEFII_CHECK_ARG(out3 != nullptr, "gemm_profile_fetch: null output");
+  double ms = 0, flops = 0;
+  for (auto& r : g_prof) {
+    NEFII_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    NEFII_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    int rows = r.rows_cap;
+    if (*r.count_host >= 0 && *r.count_host < rows) rows = *r.count_host;
+    if (rows > 0) {   // launches whose row count was 0 exit immediately: neither time nor work is attributed
+      ms += t;
+      flops += r.flops_per_row * rows;
+    }
+  }
+  out3[0] = ms; out3[1] = flops; out3[2] = (double)g_prof.size();
+  return NEFII_OK;
+}
+
 int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   NEFII_CHECK_ARG(p.a_hi && p.a_lo && p.b_hi && p.b_lo, "gemm_split_bf16: null operand");
   NEFII_CHECK_ARG(p.k_pad > 0 && p.k_pad % BK == 0 && p.k_pad <= p.a_ld && p.k_pad <= p.b_ld,
@@ -588,8 +629,23 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   NEFII_CHECK_ARG(splits == 1 || (p.epi.dst_f32 != nullptr && p.epi.dst.hi == nullptr && !fuse && p.epi.mode == 0 && p.epi.act == ACT_NONE),
                   "gemm_split_bf16: split-K needs a plain fp32 output");
   if (p.k_splits_used) *p.k_splits_used = splits;
+  ProfRec* rec = nullptr;
+  if (g_prof_on) {
+    ProfRec r;
+    NEFII_CUDA(cudaEventCreate(&r.a));
+    NEFII_CUDA(cudaEventCreate(&r.b));
+    NEFII_CUDA(cudaMallocHost(&r.count_host, sizeof(int)));
+    *r.count_host = -1;
+    r.rows_cap = p.rows_cap;
+    r.flops_per_row = 2.0 * (double)p.epi.n_valid * (double)p.k_pad;
+    if (p.count) NEFII_CUDA(cudaMemcpyAsync(r.count_host, p.count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    g_prof.push_back(r);
+    rec = &g_prof.back();
+    NEFII_CUDA(cudaEventRecord(rec->a, stream));
+  }
   fn<<<dim3(grid, splits), kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p.count, p.rows_cap, k_blocks, n_chunks,
                                                            kb_per, (long long)p.f32_split_stride, p.epi);
+  if (rec) NEFII_CUDA(cudaEventRecord(rec->b, stream));
   NEFII_LAUNCH_CHECK();
   return NEFII_OK;
 }

@@ -57,6 +57,11 @@ struct GemmProblem {
 
 int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p);
 
+// Per-launch device timing of the layer GEMM (bench.py roofline): while enabled every launch is bracketed by CUDA
+// events on its stream and its row count is copied back; fetch() -> {total ms, total algorithmic flops, launches}.
+int gemm_profile_enable(int on);
+int gemm_profile_fetch(double* out3);
+
 // fp32 [rows, cols] (row stride ld_src) -> zero-padded bf16 planes [rows_pad, cols_pad];
 // transpose=1 writes src^T.
 int split_to_planes(cudaStream_t stream, const float* src, int rows, int cols, int ld_src, int transpose,
