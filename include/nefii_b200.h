@@ -78,6 +78,10 @@ int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* desc /* host */);
  * own stream.  fetch() synchronises those events and returns {total ms, total algorithmic flops (2*rows*n*k, each
  * fp32 product counted once), number of launches}. */
 int nefii_gemm_profile_enable(int on);
+/* tuning knob: largest thread-block cluster (1, 2 or 4 CTAs sharing each weight tile by TMA multicast) the layer GEMM may use */
+int nefii_gemm_set_cluster(int cluster_size);
+/* development only: disables pieces of the GEMM pipeline (1 epilogue math, 2 TMA loads, 4 MMAs, 8 TMEM flush) for timing experiments; results are then garbage */
+int nefii_gemm_set_debug(int mask);
 int nefii_gemm_profile_fetch(double* out3 /* host */);
 
 /* fp32 [rows, cols] (row stride ld_src) -> zero-padded bf16 hi/lo planes [rows_pad, cols_pad];

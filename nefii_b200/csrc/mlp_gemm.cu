@@ -33,8 +33,9 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;  // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1,2: epilogue
 constexpr int kTmemCols = 512;
 constexpr int kMaxLast = 4;
+constexpr int kStageOutBytes = 2048;      // per epilogue warp: one 32 x 32 bf16 tile (64 B rows) for coalesced plane stores
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ +
-                              2 * BM * kMaxLast * sizeof(float);
+                              2 * BM * kMaxLast * sizeof(float) + (size_t)kEpiWarps * kStageOutBytes;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -70,6 +71,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -99,6 +119,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -126,12 +156,17 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN 
 
 // ---- branch-free activation helpers (fast intrinsics: the error they add, <= 1e-9 absolute on a
 // softplus output, is far below the bf16x3 product error; the SG kernels never use them) ----------
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 template <int ACT> __device__ __forceinline__ float act_fwd(float v) {
   if (ACT == ACT_SOFTPLUS100) {
-    const float t = 100.f * v;
-    const float e = __expf(fminf(t, 20.f));
-    const float l = (e < 1e-3f) ? e * (1.f - 0.5f * e) : __logf(1.f + e);
-    return (t > 20.f) ? v : 0.01f * l;
+    // softplus(beta=100, threshold=20): log1p(exp(100 v)) / 100, and v itself once 100 v > 20.
+    // 8 instructions: exp and log through the MUFU ex2 / lg2 units (absolute error of the result < 1e-9).
+    const float x = v * 144.26950408889634f;                  // 100 v log2(e)
+    const float e = fast_ex2(fminf(x, 28.853900817779268f));  // exp(min(100 v, 20))
+    const float h = fast_lg2(1.f + e) * 0.0069314718055994530f;   // ln(1 + e) / 100
+    return (x > 28.853900817779268f) ? v : h;
   } else if (ACT == ACT_RELU) {
     return fmaxf(v, 0.f);
   } else if (ACT == ACT_ELU) {
@@ -226,7 +261,47 @@ constexpr int kColsPerWarp = BN / 2;   // each epilogue warp owns one TMEM lane 
 // Final per-tile math on the fp32 sums of one 32-column group held in registers (v[0..31]).
 template <int MODE, int ACT, bool FUSE>
 __device__ __forceinline__ void finish_group(const GemmEpilogue& epi, float* v, int n0, long long row, bool row_ok,
-                                             float* part) {
+                                             float* part, unsigned char* stage_out, long long row_warp0, long long m_limit) {
+  // Fast path (the hidden layers of every MLP): a whole 32-column group of real outputs going to aligned planes only.
+  // No per-element predicates, vector bias loads, 16-byte stores.
+  if (MODE == 0 && !FUSE && epi.bias != nullptr && epi.dst.hi != nullptr && epi.dst_f32 == nullptr && n0 + 32 <= epi.n_valid &&
+      n0 + 32 <= epi.dst_ncols && ((epi.dst_col0 + n0) & 7) == 0 && (((size_t)epi.bias) & 15) == 0) {
+    const float4* b4 = reinterpret_cast<const float4*>(epi.bias + n0);
+    const float scale = epi.out_scale;
+    uint4 hq[4], lq[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
+      float o[8];
+      o[0] = act_fwd<ACT>(v[8 * g + 0] + ba.x) * scale; o[1] = act_fwd<ACT>(v[8 * g + 1] + ba.y) * scale;
+      o[2] = act_fwd<ACT>(v[8 * g + 2] + ba.z) * scale; o[3] = act_fwd<ACT>(v[8 * g + 3] + ba.w) * scale;
+      o[4] = act_fwd<ACT>(v[8 * g + 4] + bb.x) * scale; o[5] = act_fwd<ACT>(v[8 * g + 5] + bb.y) * scale;
+      o[6] = act_fwd<ACT>(v[8 * g + 6] + bb.z) * scale; o[7] = act_fwd<ACT>(v[8 * g + 7] + bb.w) * scale;
+      split8(o, hq[g], lq[g]);
+    }
+    // Transpose through shared memory so that each store instruction writes 8 rows x 64 contiguous bytes (whole
+    // sectors) instead of 32 rows x 16 bytes: lane = row on the way in, (row, 16-byte piece) = (8 i + lane / 4, lane % 4)
+    // on the way out.  Pieces are XOR-swizzled with the row so both directions are bank-conflict free.
+    const int lane = threadIdx.x & 31;
+    uint4* st = reinterpret_cast<uint4*>(stage_out);
+    const int r_out = lane >> 2, c_out = lane & 3;
+#pragma unroll
+    for (int plane = 0; plane < 2; ++plane) {
+      const uint4* q = plane == 0 ? hq : lq;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) st[lane * 4 + (g ^ ((lane >> 1) & 3))] = q[g];
+      __syncwarp();
+      __nv_bfloat16* base = (plane == 0 ? epi.dst.hi : epi.dst.lo) + epi.dst_col0 + n0 + 8 * c_out;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = 8 * i + r_out;
+        const uint4 val = st[r * 4 + (c_out ^ ((r >> 1) & 3))];
+        if (row_warp0 + r < m_limit) *reinterpret_cast<uint4*>(base + (row_warp0 + r) * epi.dst.ld) = val;
+      }
+      __syncwarp();
+    }
+    return;
+  }
   if (MODE == 0) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -304,12 +379,16 @@ __device__ __forceinline__ void finish_group(const GemmEpilogue& epi, float* v, 
 // sums (measured: -4 ulp at K=512, -39 ulp at K=2048, tools/diag_gpu.py trunc).  Every 64-wide K block is
 // therefore multiplied into a *fresh* TMEM buffer (the two small cross terms first, hi*hi last) and the
 // partial products are summed across K blocks by the epilogue warps in registers with round-to-nearest.
-template <int MODE, int ACT, bool FUSE>
+// CL > 1: thread-block cluster of CL CTAs working on CL consecutive row tiles.  They need the same weight tile at
+// the same time, so each CTA fetches 1/CL of it and TMA-multicasts it into every CTA of the cluster: the L2 -> SM
+// operand traffic per CTA drops from 96 KB to 32 + 64/CL KB per K block (the kernel is bound by that traffic,
+// profiles/r1_gemm_*.md).
+template <int MODE, int ACT, bool FUSE, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const int* __restrict__ count_ptr, int rows_cap, int k_blocks_total, int n_chunks, int kb_per_split,
-                       long long f32_split_stride, const __grid_constant__ GemmEpilogue epi_in) {
+                       long long f32_split_stride, int dbg, const __grid_constant__ GemmEpilogue epi_in) {
   const int m_tile = blockIdx.x;
   // split-K (weight gradients): CTA (x, y) reduces K blocks [y * kb_per_split, ...) into its own fp32 partial
   const int kb_begin = blockIdx.y * kb_per_split;
@@ -321,7 +400,10 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     int c = *count_ptr;
     if (c < m_limit) m_limit = c;
   }
-  if ((long long)m_tile * BM >= m_limit || k_blocks <= 0) return;   // uniform exit before any barrier / TMEM use
+  // uniform over the cluster: leave only if the cluster's FIRST tile is already past the valid rows
+  if ((long long)(m_tile - (m_tile % CL)) * BM >= m_limit || k_blocks <= 0) return;
+  const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMcMask = (uint16_t)((1u << CL) - 1u);
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -337,7 +419,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(&bars[0 + s]), 1);
-      mbar_init(smem_u32(&bars[2 + s]), 1);
+      mbar_init(smem_u32(&bars[2 + s]), CL);   // every CTA of the cluster reads the multicast weight tile
       mbar_init(smem_u32(&bars[4 + s]), 1);
       mbar_init(smem_u32(&bars[6 + s]), kEpiWarps);
     }
@@ -351,6 +433,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive / multicast write
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int total_kb = n_chunks * k_blocks;
@@ -368,13 +451,22 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(smem_u32(&bars[2 + stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars[0 + stage]);
+          if (dbg & 2) { mbar_arrive(full); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
           mbar_expect_tx(full, kStageBytes);
           unsigned char* st = tiles + (size_t)stage * kStageBytes;
           const int kx = (kb_begin + kb) * BK;
           tma_load_2d(smem_u32(st), &map_a_hi, full, kx, m_tile * BM);
           tma_load_2d(smem_u32(st + kATileBytes), &map_a_lo, full, kx, m_tile * BM);
-          tma_load_2d(smem_u32(st + 2 * kATileBytes), &map_b_hi, full, kx, nc * BN);
-          tma_load_2d(smem_u32(st + 2 * kATileBytes + kBTileBytes), &map_b_lo, full, kx, nc * BN);
+          if (CL == 1) {
+            tma_load_2d(smem_u32(st + 2 * kATileBytes), &map_b_hi, full, kx, nc * BN);
+            tma_load_2d(smem_u32(st + 2 * kATileBytes + kBTileBytes), &map_b_lo, full, kx, nc * BN);
+          } else {
+            constexpr int kRowsPer = BN / CL;                 // this CTA's slice of the weight tile
+            constexpr int kSliceBytes = kRowsPer * BK * 2;
+            const int row0 = nc * BN + (int)cta_rank * kRowsPer;
+            tma_load_2d_mc(smem_u32(st + 2 * kATileBytes + cta_rank * kSliceBytes), &map_b_hi, full, kx, row0, kMcMask);
+            tma_load_2d_mc(smem_u32(st + 2 * kATileBytes + kBTileBytes + cta_rank * kSliceBytes), &map_b_lo, full, kx, row0, kMcMask);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -395,6 +487,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
         const uint64_t a_lo = make_smem_desc(st + kATileBytes);
         const uint64_t b_hi = make_smem_desc(st + 2 * kATileBytes);
         const uint64_t b_lo = make_smem_desc(st + 2 * kATileBytes + kBTileBytes);
+        if (!(dbg & 4)) {
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step inside the swizzle row
@@ -406,7 +499,9 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
           tc_mma_bf16(tmem_d, a_hi + koff, b_hi + koff, kIdesc, 1);
         }
-        tc_commit(smem_u32(&bars[2 + stage]));   // frees the smem stage once these MMAs retire
+        }
+        if (CL == 1) tc_commit(smem_u32(&bars[2 + stage]));   // frees the smem stage once these MMAs retire
+        else tc_commit_mc(smem_u32(&bars[2 + stage]), kMcMask);   // ... in every CTA that multicasts into it
         tc_commit(smem_u32(&bars[4 + buf]));     // this K block's partial product is ready
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -422,6 +517,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     const long long row = (long long)m_tile * BM + row_in_tile;
     const bool row_ok = row < m_limit;
     float part[kMaxLast] = {0.f, 0.f, 0.f, 0.f};
+    unsigned char* stage_out = smem + (size_t)kStages * kStageBytes + 256 + 2 * BM * kMaxLast * sizeof(float) + (size_t)e * kStageOutBytes;
     const int n_loop = epi.dst_zero_to > epi.n_valid ? epi.dst_zero_to : epi.n_valid;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kColsPerWarp);
     float acc[kColsPerWarp];
@@ -431,21 +527,20 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
         const int buf = it & 1;
         mbar_wait(smem_u32(&bars[4 + buf]), ((uint32_t)it >> 1) & 1);
         tc_fence_after();
-        if (kb == 0) {
+        // four TMEM loads in flight per wait: the flush is latency-bound otherwise
+        if (!(dbg & 8))
 #pragma unroll
-          for (int c = 0; c < kColsPerWarp / 16; ++c) {
-            uint32_t r[16];
-            tc_ld16(t_lane + (uint32_t)(buf * BN + c * 16), r);
+        for (int hc = 0; hc < kColsPerWarp / 64; ++hc) {
+          uint32_t r[64];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[c * 16 + j] = __uint_as_float(r[j]);
-          }
-        } else {
+          for (int q = 0; q < 4; ++q) tc_ld16_nowait(t_lane + (uint32_t)(buf * BN + hc * 64 + q * 16), r + q * 16);
+          tc_wait_ld();
+          if (kb == 0) {
 #pragma unroll
-          for (int c = 0; c < kColsPerWarp / 16; ++c) {
-            uint32_t r[16];
-            tc_ld16(t_lane + (uint32_t)(buf * BN + c * 16), r);
+            for (int j = 0; j < 64; ++j) acc[hc * 64 + j] = __uint_as_float(r[j]);
+          } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[c * 16 + j] += __uint_as_float(r[j]);
+            for (int j = 0; j < 64; ++j) acc[hc * 64 + j] += __uint_as_float(r[j]);
           }
         }
         tc_fence_before();
@@ -455,7 +550,8 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
 #pragma unroll
       for (int c = 0; c < kColsPerWarp / 32; ++c) {
         const int n0 = nc * BN + half * kColsPerWarp + c * 32;
-        if (n0 < n_loop) finish_group<MODE, ACT, FUSE>(epi, acc + c * 32, n0, row, row_ok, part);
+        if (n0 < n_loop && !(dbg & 1))
+          finish_group<MODE, ACT, FUSE>(epi, acc + c * 32, n0, row, row_ok, part, stage_out, row - lane, (long long)m_limit);
       }
     }
 
@@ -476,6 +572,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -536,6 +633,9 @@ __global__ void split_to_planes_kernel(const float* __restrict__ src, int rows, 
 }  // namespace
 
 namespace {
+int g_debug = 0;          // development only: bit mask that disables pipeline pieces for timing experiments
+int g_cluster_pref = 1;   // largest TMA-multicast cluster the launcher may use (1, 2 or 4); measured on B200 (profiles/
+                          // r1_gemm_ablation.md): operand traffic is not the bound, multicast is 3-15 % slower -> off by default
 struct ProfRec {
   cudaEvent_t a, b;
   double flops_per_row;
@@ -545,6 +645,14 @@ struct ProfRec {
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 }  // namespace
+
+int gemm_set_cluster(int cl) {
+  NEFII_CHECK_ARG(cl == 1 || cl == 2 || cl == 4, "gemm_set_cluster: cluster size must be 1, 2 or 4");
+  g_cluster_pref = cl;
+  return NEFII_OK;
+}
+
+int gemm_set_debug(int mask) { g_debug = mask; return NEFII_OK; }
 
 int gemm_profile_enable(int on) {
   for (auto& r : g_prof) {
@@ -584,39 +692,51 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   NEFII_CHECK_ARG(p.epi.n_valid > 0 && p.epi.n_valid <= p.n_pad, "gemm_split_bf16: n_valid out of range");
   NEFII_CHECK_ARG(p.epi.n_last <= kMaxLast, "gemm_split_bf16: fused output layer supports at most %d outputs", kMaxLast);
   if (p.rows_cap <= 0) return NEFII_OK;
+  // cluster size: 4 when there are enough row tiles to keep every SM busy anyway, else 2, else 1
+  const int m_tiles = ceil_div(p.rows_cap, BM);
+  int cl = 1;
+  if (p.k_splits <= 1) {
+    if (m_tiles >= 4 * kNumSMs) cl = g_cluster_pref;
+    else if (m_tiles >= 2 * kNumSMs) cl = g_cluster_pref < 2 ? g_cluster_pref : 2;
+  }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if ((rc = make_map(&ma_hi, p.a_hi, p.rows_cap, p.a_ld, p.k_pad, BM))) return rc;
   if ((rc = make_map(&ma_lo, p.a_lo, p.rows_cap, p.a_ld, p.k_pad, BM))) return rc;
-  if ((rc = make_map(&mb_hi, p.b_hi, p.n_pad, p.b_ld, p.k_pad, BN))) return rc;
-  if ((rc = make_map(&mb_lo, p.b_lo, p.n_pad, p.b_ld, p.k_pad, BN))) return rc;
+  if ((rc = make_map(&mb_hi, p.b_hi, p.n_pad, p.b_ld, p.k_pad, BN / cl))) return rc;
+  if ((rc = make_map(&mb_lo, p.b_lo, p.n_pad, p.b_ld, p.k_pad, BN / cl))) return rc;
   const int n_chunks = ceil_div(p.epi.dst_zero_to > p.epi.n_valid ? p.epi.dst_zero_to : p.epi.n_valid, BN);
   NEFII_CHECK_ARG(n_chunks * BN <= p.n_pad, "gemm_split_bf16: dst_zero_to beyond n_pad");
   NEFII_CHECK_ARG(p.epi.mode == 0 || p.epi.sav_hi == nullptr || p.epi.sav_ld >= n_chunks * BN || p.epi.sav_ncols % 32 == 0,
                   "gemm_split_bf16: saved-activation rows must cover whole 32-column groups");
-  const int grid = ceil_div(p.rows_cap, BM);
-  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const int*, int, int, int, int, long long, GemmEpilogue);
+  const int grid = ceil_div(m_tiles, cl) * cl;
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const int*, int, int, int, int, long long, int, GemmEpilogue);
   KernelFn fn = nullptr;
   const bool fuse = p.epi.mode == 0 && p.epi.w_last != nullptr;
   NEFII_CHECK_ARG(!fuse || (p.epi.dst_last != nullptr && p.epi.n_last >= 1), "gemm_split_bf16: fused output layer needs dst_last");
   NEFII_CHECK_ARG(p.epi.seed.hi == nullptr || fuse, "gemm_split_bf16: seed planes need the fused output layer");
-  const int key = (fuse ? 8 : 0) + p.epi.mode * 4 + p.epi.act;
+  const int key = ((cl == 4) ? 24 : (cl == 2) ? 12 : 0) + (fuse ? 8 : 0) + p.epi.mode * 4 + p.epi.act;
+#define NEFII_GEMM_CASES(CLV, BASE)                                                              \
+    case BASE + 0: fn = gemm_split_bf16_kernel<0, ACT_NONE, false, CLV>; break;                  \
+    case BASE + 1: fn = gemm_split_bf16_kernel<0, ACT_SOFTPLUS100, false, CLV>; break;           \
+    case BASE + 2: fn = gemm_split_bf16_kernel<0, ACT_RELU, false, CLV>; break;                  \
+    case BASE + 3: fn = gemm_split_bf16_kernel<0, ACT_ELU, false, CLV>; break;                   \
+    case BASE + 4: fn = gemm_split_bf16_kernel<1, ACT_NONE, false, CLV>; break;                  \
+    case BASE + 5: fn = gemm_split_bf16_kernel<1, ACT_SOFTPLUS100, false, CLV>; break;           \
+    case BASE + 6: fn = gemm_split_bf16_kernel<1, ACT_RELU, false, CLV>; break;                  \
+    case BASE + 7: fn = gemm_split_bf16_kernel<1, ACT_ELU, false, CLV>; break;                   \
+    case BASE + 8: fn = gemm_split_bf16_kernel<0, ACT_NONE, true, CLV>; break;                   \
+    case BASE + 9: fn = gemm_split_bf16_kernel<0, ACT_SOFTPLUS100, true, CLV>; break;            \
+    case BASE + 10: fn = gemm_split_bf16_kernel<0, ACT_RELU, true, CLV>; break;                  \
+    case BASE + 11: fn = gemm_split_bf16_kernel<0, ACT_ELU, true, CLV>; break;
   switch (key) {
-    case 0: fn = gemm_split_bf16_kernel<0, ACT_NONE, false>; break;
-    case 1: fn = gemm_split_bf16_kernel<0, ACT_SOFTPLUS100, false>; break;
-    case 2: fn = gemm_split_bf16_kernel<0, ACT_RELU, false>; break;
-    case 3: fn = gemm_split_bf16_kernel<0, ACT_ELU, false>; break;
-    case 4: fn = gemm_split_bf16_kernel<1, ACT_NONE, false>; break;
-    case 5: fn = gemm_split_bf16_kernel<1, ACT_SOFTPLUS100, false>; break;
-    case 6: fn = gemm_split_bf16_kernel<1, ACT_RELU, false>; break;
-    case 7: fn = gemm_split_bf16_kernel<1, ACT_ELU, false>; break;
-    case 8: fn = gemm_split_bf16_kernel<0, ACT_NONE, true>; break;
-    case 9: fn = gemm_split_bf16_kernel<0, ACT_SOFTPLUS100, true>; break;
-    case 10: fn = gemm_split_bf16_kernel<0, ACT_RELU, true>; break;
-    case 11: fn = gemm_split_bf16_kernel<0, ACT_ELU, true>; break;
+    NEFII_GEMM_CASES(1, 0)
+    NEFII_GEMM_CASES(2, 12)
+    NEFII_GEMM_CASES(4, 24)
     default: return set_error(NEFII_ERR_ARG, "gemm_split_bf16: bad mode/act (%d/%d)", p.epi.mode, p.epi.act);
   }
-  static bool attr_set[12] = {};
+#undef NEFII_GEMM_CASES
+  static bool attr_set[36] = {};
   if (!attr_set[key]) {
     NEFII_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_set[key] = true;
@@ -643,8 +763,20 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
     rec = &g_prof.back();
     NEFII_CUDA(cudaEventRecord(rec->a, stream));
   }
-  fn<<<dim3(grid, splits), kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p.count, p.rows_cap, k_blocks, n_chunks,
-                                                           kb_per, (long long)p.f32_split_stride, p.epi);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid, splits);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NEFII_CUDA(cudaLaunchKernelEx(&cfg, fn, ma_hi, ma_lo, mb_hi, mb_lo, p.count, p.rows_cap, k_blocks, n_chunks, kb_per,
+                                  (long long)p.f32_split_stride, g_debug, p.epi));
+  }
   if (rec) NEFII_CUDA(cudaEventRecord(rec->b, stream));
   NEFII_LAUNCH_CHECK();
   return NEFII_OK;

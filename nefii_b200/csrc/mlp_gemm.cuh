@@ -59,6 +59,9 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p);
 
 // Per-launch device timing of the layer GEMM (bench.py roofline): while enabled every launch is bracketed by CUDA
 // events on its stream and its row count is copied back; fetch() -> {total ms, total algorithmic flops, launches}.
+// upper bound for the TMA-multicast cluster size the launcher picks (tuning / A-B measurements)
+int gemm_set_cluster(int cl);
+int gemm_set_debug(int mask);
 int gemm_profile_enable(int on);
 int gemm_profile_fetch(double* out3);
 

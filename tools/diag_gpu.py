@@ -105,6 +105,50 @@ def diag_sdf():
                 ((g32.double() - g64).norm(dim=-1) / g64.norm(dim=-1)).max().item()))
 
 
+def diag_cluster():
+    from nefii_b200 import ops, _lib
+    dev = torch.device("cuda:0")
+    rows, k, n = 262144, 512, 512
+    x = torch.randn(rows, k, device=dev) * 0.3
+    w = torch.randn(n, k, device=dev) / k ** 0.5
+    bias = torch.zeros(n, device=dev)
+    a = ops.split_to_planes(x)
+    b = ops.split_to_planes(w)
+    dst = (torch.empty(rows, n, device=dev, dtype=torch.bfloat16), torch.empty(rows, n, device=dev, dtype=torch.bfloat16))
+    ref = None
+    for cl in (1, 2, 4):
+        _lib.check(_lib.raw().nefii_gemm_set_cluster(cl))
+        fn = lambda: ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n)
+        ms = ev_time(fn)
+        got = (dst[0].float() + dst[1].float()).clone()
+        if ref is None:
+            ref = got
+        print("CLUSTER %d: %.4f ms %.1f TFLOP/s alg ; identical to cluster 1: %s" % (cl, ms, 2.0 * rows * n * k / ms / 1e9, torch.equal(got, ref)))
+    _lib.check(_lib.raw().nefii_gemm_set_cluster(1))
+
+
+def diag_ablate():
+    from nefii_b200 import ops, _lib
+    dev = torch.device("cuda:0")
+    rows, k, n = 262144, 512, 512
+    x = torch.randn(rows, k, device=dev) * 0.3
+    w = torch.randn(n, k, device=dev) / k ** 0.5
+    bias = torch.zeros(n, device=dev)
+    a = ops.split_to_planes(x)
+    b = ops.split_to_planes(w)
+    dst = (torch.empty(rows, n, device=dev, dtype=torch.bfloat16), torch.empty(rows, n, device=dev, dtype=torch.bfloat16))
+    names = {0: "full", 1: "no final math/stores", 8: "no flush", 9: "no flush, no final", 2: "no TMA", 4: "no MMA", 6: "no TMA, no MMA",
+             11: "no TMA, no flush, no final (MMA only)", 13: "TMA only (no MMA, flush, final)", 15: "barriers only", 3: "no TMA no final", 5: "no MMA no final"}
+    for cl in (1, 2):
+        _lib.check(_lib.raw().nefii_gemm_set_cluster(cl))
+        for mask in (0, 1, 8, 9, 2, 3, 4, 5, 6, 11, 13, 15):
+            _lib.check(_lib.raw().nefii_gemm_set_debug(mask))
+            ms = ev_time(lambda: ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n), iters=10)
+            print("ABLATE cl=%d mask=%2d %-42s %.4f ms" % (cl, mask, names[mask], ms))
+    _lib.check(_lib.raw().nefii_gemm_set_debug(0))
+    _lib.check(_lib.raw().nefii_gemm_set_cluster(1))
+
+
 def diag_gemmprof():
     from nefii_b200 import ops
     dev = torch.device("cuda:0")
