@@ -55,7 +55,99 @@ def main():
     print("wrote", sorted(os.listdir(OUT)))
 
 
-EXTRA = []
+def golden_tracer():
+    """The REAL RayTracing module on the analytic robot scene (eval + train) and on the seeded SDF MLP (eval)."""
+    import contextlib
+    import io
+    from model.ray_tracing import RayTracing
+    from . import mlp, ref_harness as rh, tracer
+    cfg = tracer.TraceConfig()
+    rt = RayTracing(**cfg.as_kwargs())
+    uv, pose, K = rh.camera_batch(32, 0, seed=3, focal_scale=1.6)
+    uv = uv + torch.rand(uv.shape, generator=torch.Generator().manual_seed(4)) - 0.5
+    dirs, loc = tracer.camera_rays(uv, pose, K)
+    obj = torch.ones(32 * 32, dtype=torch.bool)
+    obj[::7] = False
+    u = torch.rand(100, generator=torch.Generator().manual_seed(5))
+    out = dict(dirs=dirs.numpy(), cam_loc=loc.numpy(), object_mask=obj.numpy(), uniforms=u.numpy(), prims=tracer.robot_scene().numpy())
+    sdf = tracer.analytic_sdf(tracer.robot_scene())
+    for training in (False, True):
+        rt.train(training)
+        with rh.injected_rng(None, [u.clone()]):
+            p, m, t = rt(sdf=sdf, cam_loc=loc, object_mask=obj, ray_directions=dirs)
+        tag = "train" if training else "eval"
+        out["analytic_%s_points" % tag] = p.numpy()
+        out["analytic_%s_mask" % tag] = m.numpy()
+        out["analytic_%s_dists" % tag] = t.numpy()
+    params = mlp.sdf_init(seed=1, bumps=0.03)
+    with contextlib.redirect_stdout(io.StringIO()):
+        from model.implicit_differentiable_renderer import ImplicitNetwork
+        net = ImplicitNetwork(512, d_in=3, d_out=1, dims=[512] * 8, geometric_init=True, bias=0.6, skip_in=[4], weight_norm=True,
+                              multires=6, use_last_as_f=True)
+    net.load_state_dict(params.state_dict(""))
+    rt.train(False)
+    uv2, pose2, K2 = rh.camera_batch(24, 0, seed=6)
+    dirs2, loc2 = tracer.camera_rays(uv2, pose2, K2)
+    with torch.no_grad():
+        p, m, t = rt(sdf=lambda x: net(x)[:, 0], cam_loc=loc2, object_mask=torch.ones(24 * 24, dtype=torch.bool), ray_directions=dirs2)
+        x = torch.rand(256, 3, generator=torch.Generator().manual_seed(7)) * 1.6 - 0.8
+        y = net(x)
+    g = net.gradient(x.clone(), no_grad=True)[:, 0, :]
+    out.update(mlp_dirs=dirs2.numpy(), mlp_cam_loc=loc2.numpy(), mlp_points=p.numpy(), mlp_mask=m.numpy(), mlp_dists=t.numpy(),
+               mlp_x=x.numpy(), mlp_sdf=y[:, 0].numpy(), mlp_feat_first8=y[:, 1:9].numpy(), mlp_grad=g.detach().numpy())
+    np.savez_compressed(os.path.join(OUT, "tracer_mlp.npz"), **out)
+
+
+def golden_mis_and_pipeline():
+    """Sampling functions of the REAL path_tracing_render.py and one full IDRNetwork.forward (eval + train)."""
+    import unittest.mock as mock
+    import model.path_tracing_render as ptr
+    from . import ref_harness as rh
+    n = 512
+    normal, view, albedo = inputs.shading_inputs(n, seed=11)
+    g = torch.Generator().manual_seed(12)
+    rough = torch.rand(n, 1, generator=g) * 0.9 + 0.089
+    lgt = inputs.synthetic_light_sgs(128, seed=13)
+    u = torch.rand(n, 7, generator=g)
+    cols = [u[:, 0:1], u[:, 1:2], u[:, 2:3], u[:, 3:4], u[:, 4:5].unsqueeze(-1), u[:, 5:6], u[:, 6:7]]
+    it = iter(cols)
+    L = lgt.reshape(1, 128, 7).expand(n, 128, 7)
+    with mock.patch.object(torch, "rand", lambda shape, device=None: next(it).clone()):
+        w0, p0 = ptr.cos_sampling(normal)
+        w1, p1 = ptr.brdf_sampling(normal, rough, view)
+        w2, p2 = ptr.mix_sg_sampling(normal, L)
+    fns = [ptr.pdf_fn_cos, ptr.pdf_fn_brdf_gxx, ptr.pdf_fn_mix_sg]
+    wi = [w0, w1, w2]
+    pdf = [torch.clamp(p, min=1e-6) for p in (p0, p1, p2)]
+    mat = torch.stack([torch.stack([pdf[i] if i == j else fns[j](wi[i], normal, view, rough, L) for j in range(3)]) for i in range(3)])
+    out = dict(normal=normal.numpy(), view=view.numpy(), rough=rough.numpy(), lgt=lgt.numpy(), u=u.numpy(),
+               wi=torch.stack(wi).numpy(), pdf=torch.stack(pdf).numpy(), pdf_matrix=mat.numpy())
+    np.savez_compressed(os.path.join(OUT, "mis_sampling.npz"), **out)
+
+    om = rh.small_model(seed=0)
+    net = rh.build_reference_model(om)
+    uv, pose, K = rh.camera_batch(12, 2, seed=1)
+    S = uv.shape[1]
+    obj = torch.ones(1, S, dtype=torch.bool)
+    obj[0, ::5] = False
+    g = torch.Generator().manual_seed(7)
+    U = torch.rand(4096, 7, generator=g)
+    vecs = [torch.rand(100, generator=g) for _ in range(2)]
+    out = dict(uv=uv.numpy(), pose=pose.numpy(), intrinsics=K.numpy(), object_mask=obj.numpy(), U=U[:S * 2].numpy(),
+               vec0=vecs[0].numpy(), vec1=vecs[1].numpy())
+    for training in (False, True):
+        net.train(training)
+        with rh.injected_rng(lambda n_: U[:n_], [v.clone() for v in vecs]):
+            ref = net({'uv': uv, 'pose': pose, 'intrinsics': K, 'object_mask': obj})
+        tag = "train" if training else "eval"
+        for k in ('points', 'idr_rgb_values', 'sg_rgb_values', 'normal_values', 'sdf_output', 'network_object_mask',
+                  'sg_diffuse_rgb_values', 'sg_diffuse_albedo_values', 'sg_specular_rgb_values', 'sg_roughness_values',
+                  'secondary_points', 'secondary_mask', 'secondary_dir'):
+            out["%s_%s" % (tag, k)] = ref[k].detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "pipeline_small.npz"), **out)
+
+
+EXTRA = [golden_tracer, golden_mis_and_pipeline]
 
 if __name__ == "__main__":
     main()

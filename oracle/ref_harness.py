@@ -48,6 +48,8 @@ def injected_rng(u7_fn, uniform_vectors):
 
     def fake_rand(shape, device=None):
         n = shape[0]
+        if u7_fn is None:
+            raise RuntimeError('unexpected torch.rand call')
         if state["u7"] is None or state["col"] == 7:
             state["u7"], state["col"] = u7_fn(n), 0
         col = state["u7"][:, state["col"]].reshape(shape)
