@@ -82,6 +82,9 @@ int nefii_gemm_profile_enable(int on);
 int nefii_gemm_set_cluster(int cluster_size);
 /* development only: disables pieces of the GEMM pipeline (1 epilogue math, 2 TMA loads, 4 MMAs, 8 TMEM flush) for timing experiments; results are then garbage */
 int nefii_gemm_set_debug(int mask);
+/* accuracy / overlap knob of the layer GEMM: 64-wide K blocks accumulated inside TMEM before the partial sum moves to the fp32
+ * register accumulators (1 = most accurate; default 2) */
+int nefii_gemm_set_k_flush(int k_blocks);
 int nefii_gemm_profile_fetch(double* out3 /* host */);
 
 /* fp32 [rows, cols] (row stride ld_src) -> zero-padded bf16 hi/lo planes [rows_pad, cols_pad];

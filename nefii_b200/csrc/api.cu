@@ -202,6 +202,7 @@ int nefii_reduce_splits(void* stream, const float* partial, int n_splits, int64_
 int nefii_gemm_profile_enable(int on) { return nefii::gemm_profile_enable(on); }
 int nefii_gemm_set_cluster(int cl) { return nefii::gemm_set_cluster(cl); }
 int nefii_gemm_set_debug(int mask) { return nefii::gemm_set_debug(mask); }
+int nefii_gemm_set_k_flush(int k) { return nefii::gemm_set_k_flush(k); }
 int nefii_gemm_profile_fetch(double* out3) { return nefii::gemm_profile_fetch(out3); }
 
 }  // extern "C"

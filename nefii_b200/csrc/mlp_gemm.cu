@@ -388,8 +388,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const int* __restrict__ count_ptr, int rows_cap, int k_blocks_total, int n_chunks, int kb_per_split,
-                       long long f32_split_stride, int dbg, const __grid_constant__ GemmEpilogue epi_in) {
-  const int m_tile = blockIdx.x;
+                       long long f32_split_stride, int dbg, int k_flush, const __grid_constant__ GemmEpilogue epi_in) {
+  // Persistent over row tiles: CTA x handles tiles x, x + gridDim.x, ... so that the final epilogue math of one tile
+  // overlaps the MMAs of the next (the pipelines and barrier phases simply keep running across tiles).
+  const int m_tile0 = blockIdx.x;
+  const int tile_stride = gridDim.x;
   // split-K (weight gradients): CTA (x, y) reduces K blocks [y * kb_per_split, ...) into its own fp32 partial
   const int kb_begin = blockIdx.y * kb_per_split;
   const int k_blocks = min(k_blocks_total, kb_begin + kb_per_split) - kb_begin;
@@ -401,7 +404,8 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     if (c < m_limit) m_limit = c;
   }
   // uniform over the cluster: leave only if the cluster's FIRST tile is already past the valid rows
-  if ((long long)(m_tile - (m_tile % CL)) * BM >= m_limit || k_blocks <= 0) return;
+  if ((long long)(m_tile0 - (m_tile0 % CL)) * BM >= m_limit || k_blocks <= 0) return;
+  static_assert(CL == 1, "the persistent tile loop assumes one CTA per cluster");
   const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t kMcMask = (uint16_t)((1u << CL) - 1u);
 
@@ -436,7 +440,6 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive / multicast write
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_kb = n_chunks * k_blocks;
 
   // Register re-partitioning (168 regs/thread at launch): the role warpgroup keeps 40, each epilogue
   // warpgroup grows to 232 so the 128 fp32 partial sums per thread stay in registers.
@@ -447,6 +450,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      for (int m_tile = m_tile0; (long long)m_tile * BM < m_limit; m_tile += tile_stride)
       for (int nc = 0; nc < n_chunks; ++nc) {
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(smem_u32(&bars[2 + stage]), phase ^ 1);
@@ -476,34 +480,46 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < total_kb; ++it) {
-        const int buf = it & 1;
-        mbar_wait(smem_u32(&bars[6 + buf]), (((uint32_t)it >> 1) & 1) ^ 1);   // partial sums of 2 blocks ago were read
-        mbar_wait(smem_u32(&bars[0 + stage]), phase);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-        const uint32_t st = smem_u32(tiles + (size_t)stage * kStageBytes);
-        const uint64_t a_hi = make_smem_desc(st);
-        const uint64_t a_lo = make_smem_desc(st + kATileBytes);
-        const uint64_t b_hi = make_smem_desc(st + 2 * kATileBytes);
-        const uint64_t b_lo = make_smem_desc(st + 2 * kATileBytes + kBTileBytes);
-        if (!(dbg & 4)) {
+      // K blocks are accumulated in TMEM in groups of k_flush ("partials"); each partial goes to a fresh buffer and is
+      // added to the register accumulators by the epilogue warps (bounds the tensor core's truncation bias), and the two
+      // buffers let the MMAs of up to two partials run ahead of the epilogue's final math.
+      const int parts_per_chunk = (k_blocks + k_flush - 1) / k_flush;
+      uint32_t pcount = 0;
+      for (int m_tile = m_tile0; (long long)m_tile * BM < m_limit; m_tile += tile_stride)
+      for (int nc = 0; nc < n_chunks; ++nc) {
+        for (int pi = 0; pi < parts_per_chunk; ++pi, ++pcount) {
+          const int buf = pcount & 1;
+          mbar_wait(smem_u32(&bars[6 + buf]), ((pcount >> 1) & 1) ^ 1);   // the partial of two groups ago was read
+          const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+          const int kb_end = min(k_blocks, (pi + 1) * k_flush);
+          for (int kb = pi * k_flush; kb < kb_end; ++kb) {
+            mbar_wait(smem_u32(&bars[0 + stage]), phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(tiles + (size_t)stage * kStageBytes);
+            const uint64_t a_hi = make_smem_desc(st);
+            const uint64_t a_lo = make_smem_desc(st + kATileBytes);
+            const uint64_t b_hi = make_smem_desc(st + 2 * kATileBytes);
+            const uint64_t b_lo = make_smem_desc(st + 2 * kATileBytes + kBTileBytes);
+            const uint32_t fresh = (kb == pi * k_flush) ? 0u : 1u;
+            if (!(dbg & 4)) {
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step inside the swizzle row
-          tc_mma_bf16(tmem_d, a_hi + koff, b_lo + koff, kIdesc, k != 0);
-          tc_mma_bf16(tmem_d, a_lo + koff, b_hi + koff, kIdesc, 1);
-        }
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step inside the swizzle row
+                tc_mma_bf16(tmem_d, a_hi + koff, b_lo + koff, kIdesc, (k != 0) ? 1u : fresh);
+                tc_mma_bf16(tmem_d, a_lo + koff, b_hi + koff, kIdesc, 1);
+              }
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-          tc_mma_bf16(tmem_d, a_hi + koff, b_hi + koff, kIdesc, 1);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                tc_mma_bf16(tmem_d, a_hi + koff, b_hi + koff, kIdesc, 1);
+              }
+            }
+            if (CL == 1) tc_commit(smem_u32(&bars[2 + stage]));   // frees the smem stage once these MMAs retire
+            else tc_commit_mc(smem_u32(&bars[2 + stage]), kMcMask);   // ... in every CTA that multicasts into it
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(smem_u32(&bars[4 + buf]));     // this partial product is ready
         }
-        }
-        if (CL == 1) tc_commit(smem_u32(&bars[2 + stage]));   // frees the smem stage once these MMAs retire
-        else tc_commit_mc(smem_u32(&bars[2 + stage]), kMcMask);   // ... in every CTA that multicasts into it
-        tc_commit(smem_u32(&bars[4 + buf]));     // this K block's partial product is ready
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -514,18 +530,20 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int half = e >> 2;            // which 128-column half of the 256-column chunk
     const int row_in_tile = quarter * 32 + lane;
-    const long long row = (long long)m_tile * BM + row_in_tile;
-    const bool row_ok = row < m_limit;
-    float part[kMaxLast] = {0.f, 0.f, 0.f, 0.f};
     unsigned char* stage_out = smem + (size_t)kStages * kStageBytes + 256 + 2 * BM * kMaxLast * sizeof(float) + (size_t)e * kStageOutBytes;
     const int n_loop = epi.dst_zero_to > epi.n_valid ? epi.dst_zero_to : epi.n_valid;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kColsPerWarp);
     float acc[kColsPerWarp];
-    int it = 0;
+    const int parts_per_chunk = (k_blocks + k_flush - 1) / k_flush;
+    uint32_t pcount = 0;
+    for (int m_tile = m_tile0; (long long)m_tile * BM < m_limit; m_tile += tile_stride) {
+    const long long row = (long long)m_tile * BM + row_in_tile;
+    const bool row_ok = row < m_limit;
+    float part[kMaxLast] = {0.f, 0.f, 0.f, 0.f};
     for (int nc = 0; nc < n_chunks; ++nc) {
-      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-        const int buf = it & 1;
-        mbar_wait(smem_u32(&bars[4 + buf]), ((uint32_t)it >> 1) & 1);
+      for (int pi = 0; pi < parts_per_chunk; ++pi, ++pcount) {
+        const int buf = pcount & 1;
+        mbar_wait(smem_u32(&bars[4 + buf]), (pcount >> 1) & 1);
         tc_fence_after();
         // four TMEM loads in flight per wait: the flush is latency-bound otherwise
         if (!(dbg & 8))
@@ -535,7 +553,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
 #pragma unroll
           for (int q = 0; q < 4; ++q) tc_ld16_nowait(t_lane + (uint32_t)(buf * BN + hc * 64 + q * 16), r + q * 16);
           tc_wait_ld();
-          if (kb == 0) {
+          if (pi == 0) {
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[hc * 64 + j] = __uint_as_float(r[j]);
           } else {
@@ -567,7 +585,9 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           epi.dst_last[(size_t)row * epi.n_last + q] = y;
         }
       }
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");   // s_last is reused by the next tile
     }
+    }   // tile loop
   }
 
   tc_fence_before();
@@ -633,6 +653,7 @@ __global__ void split_to_planes_kernel(const float* __restrict__ src, int rows, 
 }  // namespace
 
 namespace {
+int g_k_flush = 2;        // K blocks (of 64) accumulated inside TMEM before the sum moves to registers; see gemm_set_k_flush
 int g_debug = 0;          // development only: bit mask that disables pipeline pieces for timing experiments
 int g_cluster_pref = 1;   // largest TMA-multicast cluster the launcher may use (1, 2 or 4); measured on B200 (profiles/
                           // r1_gemm_ablation.md): operand traffic is not the bound, multicast is 3-15 % slower -> off by default
@@ -653,6 +674,11 @@ int gemm_set_cluster(int cl) {
 }
 
 int gemm_set_debug(int mask) { g_debug = mask; return NEFII_OK; }
+int gemm_set_k_flush(int k) {
+  NEFII_CHECK_ARG(k >= 1 && k <= 64, "gemm_set_k_flush: out of range");
+  g_k_flush = k;
+  return NEFII_OK;
+}
 
 int gemm_profile_enable(int on) {
   for (auto& r : g_prof) {
@@ -695,10 +721,7 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   // cluster size: 4 when there are enough row tiles to keep every SM busy anyway, else 2, else 1
   const int m_tiles = ceil_div(p.rows_cap, BM);
   int cl = 1;
-  if (p.k_splits <= 1) {
-    if (m_tiles >= 4 * kNumSMs) cl = g_cluster_pref;
-    else if (m_tiles >= 2 * kNumSMs) cl = g_cluster_pref < 2 ? g_cluster_pref : 2;
-  }
+  (void)g_cluster_pref;   // TMA-multicast clusters measured slower (profiles/r1_gemm_ablation.md); persistent kernel is CL = 1
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if ((rc = make_map(&ma_hi, p.a_hi, p.rows_cap, p.a_ld, p.k_pad, BM))) return rc;
@@ -709,8 +732,9 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   NEFII_CHECK_ARG(n_chunks * BN <= p.n_pad, "gemm_split_bf16: dst_zero_to beyond n_pad");
   NEFII_CHECK_ARG(p.epi.mode == 0 || p.epi.sav_hi == nullptr || p.epi.sav_ld >= n_chunks * BN || p.epi.sav_ncols % 32 == 0,
                   "gemm_split_bf16: saved-activation rows must cover whole 32-column groups");
-  const int grid = ceil_div(m_tiles, cl) * cl;
-  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const int*, int, int, int, int, long long, int, GemmEpilogue);
+  int grid = ceil_div(m_tiles, cl) * cl;
+  if (grid > kNumSMs) grid = kNumSMs;   // persistent CTAs: one per SM, looping over row tiles
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const int*, int, int, int, int, long long, int, int, GemmEpilogue);
   KernelFn fn = nullptr;
   const bool fuse = p.epi.mode == 0 && p.epi.w_last != nullptr;
   NEFII_CHECK_ARG(!fuse || (p.epi.dst_last != nullptr && p.epi.n_last >= 1), "gemm_split_bf16: fused output layer needs dst_last");
@@ -731,8 +755,6 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
     case BASE + 11: fn = gemm_split_bf16_kernel<0, ACT_ELU, true, CLV>; break;
   switch (key) {
     NEFII_GEMM_CASES(1, 0)
-    NEFII_GEMM_CASES(2, 12)
-    NEFII_GEMM_CASES(4, 24)
     default: return set_error(NEFII_ERR_ARG, "gemm_split_bf16: bad mode/act (%d/%d)", p.epi.mode, p.epi.act);
   }
 #undef NEFII_GEMM_CASES
@@ -775,7 +797,7 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     NEFII_CUDA(cudaLaunchKernelEx(&cfg, fn, ma_hi, ma_lo, mb_hi, mb_lo, p.count, p.rows_cap, k_blocks, n_chunks, kb_per,
-                                  (long long)p.f32_split_stride, g_debug, p.epi));
+                                  (long long)p.f32_split_stride, g_debug, g_k_flush, p.epi));
   }
   if (rec) NEFII_CUDA(cudaEventRecord(rec->b, stream));
   NEFII_LAUNCH_CHECK();

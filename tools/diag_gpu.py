@@ -127,6 +127,37 @@ def diag_cluster():
     _lib.check(_lib.raw().nefii_gemm_set_cluster(1))
 
 
+def diag_kflush():
+    from nefii_b200 import ops, _lib
+    from oracle import mlp
+    dev = torch.device("cuda:0")
+    rows, k, n = 262144, 512, 512
+    x = torch.randn(rows, k, device=dev) * 0.3
+    w = torch.randn(n, k, device=dev) / k ** 0.5
+    bias = torch.zeros(n, device=dev)
+    a = ops.split_to_planes(x); b = ops.split_to_planes(w)
+    dst = (torch.empty(rows, n, device=dev, dtype=torch.bfloat16), torch.empty(rows, n, device=dev, dtype=torch.bfloat16))
+    xp = (torch.rand(4096, 512, device=dev) + 0.5).bfloat16().float(); wp = (torch.rand(256, 512, device=dev) + 0.5).bfloat16().float()
+    ap = ops.split_to_planes(xp); bp = ops.split_to_planes(wp)
+    refp = xp.double() @ wp.double().t()
+    params = mlp.sdf_init(seed=1, bumps=0.3)
+    net = ops.SdfMlp(device=dev)
+    net.set_weights([t.to(dev) for t in params.W], [t.to(dev) for t in params.b])
+    pts = torch.rand(131072, 3, device=dev) * 1.8 - 0.9
+    r64 = mlp.sdf_forward(params.to(dev, torch.float64), pts.double())[:, 0]
+    for kf in (1, 2, 4, 8):
+        _lib.check(_lib.raw().nefii_gemm_set_k_flush(kf))
+        ms = ev_time(lambda: ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n), iters=10)
+        out = torch.zeros(4096, 256, device=dev)
+        ops.gemm_split_bf16(ap, bp, 512, 256, dst_f32=out, f32_begin=0, f32_end=256)
+        err = (out.double() - refp) / refp
+        sdf, _, _ = net.eval(pts)
+        e = sdf.double() - r64
+        print("KFLUSH %d: %.4f ms %.1f TFLOP/s alg | all-positive K=512 bias %.2f ulp | SDF err mean %.2e (signed %.2e) max %.2e" % (
+            kf, ms, 2.0 * rows * n * k / ms / 1e9, err.mean().item() / 2 ** -24, e.abs().mean().item(), e.mean().item(), e.abs().max().item()))
+    _lib.check(_lib.raw().nefii_gemm_set_k_flush(2))
+
+
 def diag_ablate():
     from nefii_b200 import ops, _lib
     dev = torch.device("cuda:0")
