@@ -49,9 +49,17 @@ def test_forward_matches_oracle_pipeline(cuda_device, training, rays):
     assert int((a & b).sum()) > 100
     assert torch.equal(mine['object_mask'], ref['object_mask'])
     sel = agree
-    # depth abs 1e-4 (north_star) on the pixels whose rays took the same branches
-    assert ((mine['points'] - ref['points'])[sel].abs().max(-1)[0] < 1e-4).float().mean().item() > 0.97
+    # depth abs 1e-4 (north_star) on the surface pixels whose rays took the same branches.  Non-hit lanes in train mode hold
+    # the arg-min over 100 random depths (minimal_sdf_points): the arg-min may jump between two near-equal samples, so
+    # there the minimum VALUE (sdf_output) is compared instead of its position.
+    hit = sel & a
+    assert ((mine['points'] - ref['points'])[hit].abs().max(-1)[0] < 1e-4).float().mean().item() > 0.99
+    miss = sel & ~a
+    if bool(miss.any()):
+        assert (mine['sdf_output'] - ref['sdf_output'])[miss].abs().max().item() < 1e-4
     for k in KEYS:
+        if k == 'points':
+            continue
         x, y = mine[k][sel].float(), ref[k][sel].float()
         err = (x - y).abs() / (y.abs() + 1e-3)
         p95 = err.flatten().kthvalue(max(1, int(0.95 * err.numel())))[0].item()
