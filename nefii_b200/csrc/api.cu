@@ -30,6 +30,8 @@ int set_error(int code, const char* fmt, ...) {
 int sg_render_fwd(cudaStream_t, int, int, int, const float*, const float*, const float*, const float*, const float*,
                   const float*, const float*, float*, float*, float*);
 int background_sg_fwd(cudaStream_t, int, int, const float*, const float*, float*);
+int sg_render_bwd(cudaStream_t, int, int, int, const float*, const float*, const float*, const float*, const float*, const float*,
+                  const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*);
 int mis_sample(cudaStream_t, int, int, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*);
 int mis_shade_fwd(cudaStream_t, int, int, const float*, const float*, int, const float*, const float*, const float*, const float*,
                   const float*, const float*, const float*, const unsigned char*, const float*, float*, float*, float*, float*);
@@ -204,5 +206,14 @@ int nefii_gemm_set_cluster(int cl) { return nefii::gemm_set_cluster(cl); }
 int nefii_gemm_set_debug(int mask) { return nefii::gemm_set_debug(mask); }
 int nefii_gemm_set_k_flush(int k) { return nefii::gemm_set_k_flush(k); }
 int nefii_gemm_profile_fetch(double* out3) { return nefii::gemm_profile_fetch(out3); }
+
+int nefii_sg_render_bwd(void* stream, int n_rays, int n_sg, int n_mat, const float* lgt_sgs, const float* specular,
+                        const float* roughness, const float* albedo, const float* normal, const float* view,
+                        const float* out_specular, const float* out_diffuse, const float* g_rgb, const float* g_specular,
+                        const float* g_diffuse, float* g_lgt_acc, float* g_roughness, float* g_specular_refl, float* g_albedo) {
+  return nefii::sg_render_bwd((cudaStream_t)stream, n_rays, n_sg, n_mat, lgt_sgs, specular, roughness, albedo, normal, view,
+                              out_specular, out_diffuse, g_rgb, g_specular, g_diffuse, g_lgt_acc, g_roughness, g_specular_refl,
+                              g_albedo);
+}
 
 }  // extern "C"

@@ -42,7 +42,7 @@ template <typename T> NEFII_HD void load_mix_lobe(const T* raw7, MixLobe<T>& L) 
   L.sharp = m_abs(raw7[3]);
   L.amp[0] = m_abs(raw7[4]); L.amp[1] = m_abs(raw7[5]); L.amp[2] = m_abs(raw7[6]);
   L.energy = sgm::sum3(L.amp[0], L.amp[1], L.amp[2]);
-  L.c = L.sharp / (K<T>::two_pi * (T(1) - m_exp(T(-2) * L.sharp)));
+  L.c = L.sharp / (K<T>::two_pi() * (T(1) - m_exp(T(-2) * L.sharp)));
 }
 
 NEFII_HD float m_fma(float a, float b, float c) { return fmaf(a, b, c); }
@@ -76,7 +76,7 @@ template <typename T> NEFII_HD void spherical(T theta, T phi, T* out) {
 }
 
 template <typename T> NEFII_HD T pdf_cos(const T* wi, const T* n) {
-  return clamp_min(dot3(wi, n), K<T>::eps) * (T(1) / K<T>::pi);
+  return clamp_min(dot3(wi, n), K<T>::eps()) * (T(1) / K<T>::pi());
 }
 
 template <typename T> NEFII_HD T pdf_ggx(const T* wi, const T* n, const T* v, T rough) {
@@ -87,18 +87,18 @@ template <typename T> NEFII_HD T pdf_ggx(const T* wi, const T* n, const T* v, T 
     h[i] = h[i] / hn;
     if (h[i] != h[i]) h[i] = n[i];   // wi == -view: NaN half vector -> normal (path_tracing_render.py:110-111)
   }
-  const T c = clamp_min(dot3(h, n), K<T>::eps);
+  const T c = clamp_min(dot3(h, n), K<T>::eps());
   const T r4 = m_pow(rough, T(4));                         // roughness ** 4 (torch: powf for exponents other than 2, 3)
   const T c2 = c * c;
   const T root = c2 + (T(1) - c2) / r4;
-  const T pdf_h = c / (((K<T>::pi * r4) * root) * root);
-  const T hv = clamp_min(dot3(h, v), K<T>::eps);
+  const T pdf_h = c / (((K<T>::pi() * r4) * root) * root);
+  const T hv = clamp_min(dot3(h, v), K<T>::eps());
   return pdf_h / (T(4) * hv);
 }
 
 // normalisation of the mixture weights for a given normal: sum_k energy_k * max(n . axis_k, 1e-6)
 template <typename T> NEFII_HD T mix_weight(const MixLobe<T>& L, const T* n) {
-  return L.energy * clamp_min(dot3(n, L.axis), K<T>::eps);
+  return L.energy * clamp_min(dot3(n, L.axis), K<T>::eps());
 }
 
 template <typename T> NEFII_HD T pdf_mix(const MixLobe<T>* lobes, int n_sg, const T* wi, const T* n, T wsum) {
@@ -121,15 +121,15 @@ NEFII_HD void sample_point(const MixLobe<T>* lobes, int n_sg, const T* n, const 
   // cosine-weighted (path_tracing_render.py:128-156)
   {
     const T theta = m_acos(m_sqrt(T(1) - u[0]));
-    const T phi = K<T>::two_pi * u[1];
+    const T phi = K<T>::two_pi() * u[1];
     spherical(theta, phi, local);
     to_frame(local, n, wi[0]);
-    pdf[0] = m_cos(theta) * (T(1) / K<T>::pi);
+    pdf[0] = m_cos(theta) * (T(1) / K<T>::pi());
   }
   // GGX half vector (:61-103)
   {
     const T theta = m_atan((rough * rough) * m_sqrt(u[2] / (T(1) - u[2])));
-    const T phi = K<T>::two_pi * u[3];
+    const T phi = K<T>::two_pi() * u[3];
     spherical(theta, phi, local);
     T h[3];
     to_frame(local, n, h);
@@ -153,22 +153,22 @@ NEFII_HD void sample_point(const MixLobe<T>* lobes, int n_sg, const T* n, const 
     }
     if (pick < 0) pick = 0;   // torch.max over an all-false row returns index 0
     const MixLobe<T>& L = lobes[pick];
-    const T inner = clamp_min(T(1) - (L.sharp * u[5]) / (K<T>::two_pi * L.c), K<T>::eps);
+    const T inner = clamp_min(T(1) - (L.sharp * u[5]) / (K<T>::two_pi() * L.c), K<T>::eps());
     const T theta = m_acos(((T(1) / L.sharp) * m_log(inner)) + T(1));
-    const T phi = K<T>::two_pi * u[6];
+    const T phi = K<T>::two_pi() * u[6];
     spherical(theta, phi, local);
     to_frame(local, L.axis, wi[2]);
     pdf[2] = pdf_mix(lobes, n_sg, wi[2], n, wsum);
   }
 #pragma unroll
-  for (int i = 0; i < 3; ++i) pdf[i] = clamp_min(pdf[i], K<T>::eps);
+  for (int i = 0; i < 3; ++i) pdf[i] = clamp_min(pdf[i], K<T>::eps());
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     mat[i][0] = (i == 0) ? pdf[0] : pdf_cos(wi[i], n);
     mat[i][1] = (i == 1) ? pdf[1] : pdf_ggx(wi[i], n, v, rough);
     mat[i][2] = (i == 2) ? pdf[2] : pdf_mix(lobes, n_sg, wi[i], n, wsum);
     const T total = ((T(0) + mat[i][0] * mat[i][0]) + mat[i][1] * mat[i][1]) + mat[i][2] * mat[i][2];
-    weight[i] = (mat[i][i] * mat[i][i]) / clamp_min(total, K<T>::eps);
+    weight[i] = (mat[i][i] * mat[i][i]) / clamp_min(total, K<T>::eps());
   }
 }
 
@@ -208,19 +208,19 @@ NEFII_HD void shade_sample(const ShadeGeom<T>& g, T rough, const T* spec_refl, c
   const T r4 = r2 * r2;
   const T nh2 = g.nh * g.nh;
   const T root = nh2 + (T(1) - nh2) / r4;
-  const T D = T(1) / (((K<T>::pi * r4) * root) * root);
+  const T D = T(1) / (((K<T>::pi() * r4) * root) * root);
   const T k = ((rough + T(1)) * (rough + T(1))) * T(0.125);
-  const T G1 = g.d1 / ((g.d1 * (T(1) - k) + k) + K<T>::eps);
-  const T G2 = g.d2 / ((g.d2 * (T(1) - k) + k) + K<T>::eps);
+  const T G1 = g.d1 / ((g.d1 * (T(1) - k) + k) + K<T>::eps());
+  const T G2 = g.d2 / ((g.d2 * (T(1) - k) + k) + K<T>::eps());
   const T G = G1 * G2;
-  const T den = (T(4) * g.d1) * g.d2 + K<T>::eps;
+  const T den = (T(4) * g.d1) * g.d2 + K<T>::eps();
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const T F = spec_refl[c] + (T(1) - spec_refl[c]) * g.E;
     const T fs = ((F * D) * G) / den;
     const T la = light[c] * vis + (T(1) - vis) * indirect[c];
     const T s = (((weight * la) * fs) * g.cosn) / pdf;
-    const T d = (((weight * la) * (albedo[c] * (T(1) / K<T>::pi))) * g.cosn) / pdf;
+    const T d = (((weight * la) * (albedo[c] * (T(1) / K<T>::pi()))) * g.cosn) / pdf;
     spec3[c] = clamp_min(s, T(0));
     diff3[c] = clamp_min(d, T(0));
   }
@@ -236,13 +236,13 @@ NEFII_HD void shade_sample_bwd(const ShadeGeom<T>& g, T rough, const T* spec_ref
   const T r4 = r2 * r2;
   const T nh2 = g.nh * g.nh;
   const T root = nh2 + (T(1) - nh2) / r4;
-  const T D = T(1) / (((K<T>::pi * r4) * root) * root);
+  const T D = T(1) / (((K<T>::pi() * r4) * root) * root);
   const T k = ((rough + T(1)) * (rough + T(1))) * T(0.125);
-  const T den1 = (g.d1 * (T(1) - k) + k) + K<T>::eps;
-  const T den2 = (g.d2 * (T(1) - k) + k) + K<T>::eps;
+  const T den1 = (g.d1 * (T(1) - k) + k) + K<T>::eps();
+  const T den2 = (g.d2 * (T(1) - k) + k) + K<T>::eps();
   const T G1 = g.d1 / den1, G2 = g.d2 / den2;
   const T G = G1 * G2;
-  const T den = (T(4) * g.d1) * g.d2 + K<T>::eps;
+  const T den = (T(4) * g.d1) * g.d2 + K<T>::eps();
   const T q = (weight * g.cosn) / pdf;
   T g_DG = T(0);
 #pragma unroll
@@ -250,7 +250,7 @@ NEFII_HD void shade_sample_bwd(const ShadeGeom<T>& g, T rough, const T* spec_ref
     const T F = spec_refl[c] + (T(1) - spec_refl[c]) * g.E;
     const T fs = ((F * D) * G) / den;
     const T la = light[c] * vis + (T(1) - vis) * indirect[c];
-    const T a_pi = albedo[c] * (T(1) / K<T>::pi);
+    const T a_pi = albedo[c] * (T(1) / K<T>::pi());
     const T s = (((weight * la) * fs) * g.cosn) / pdf;
     const T d = (((weight * la) * a_pi) * g.cosn) / pdf;
     const T ms = (s >= T(0)) ? gs[c] : T(0);       // clamp(min=0) passes the gradient where the input is >= 0
@@ -258,7 +258,7 @@ NEFII_HD void shade_sample_bwd(const ShadeGeom<T>& g, T rough, const T* spec_ref
     const T g_la = ms * q * fs + md * q * a_pi;
     g_light[c] = g_la * vis;
     g_indirect[c] = g_la * (T(1) - vis);
-    g_albedo[c] += md * q * la * (T(1) / K<T>::pi);
+    g_albedo[c] += md * q * la * (T(1) / K<T>::pi());
     const T g_fs = ms * q * la;
     const T g_F = g_fs * (D * G) / den;
     g_spec_refl[c] += g_F * (T(1) - g.E);

@@ -10,6 +10,7 @@
 // reciprocal(x) * scalar (Tensor.__rtruediv__); both are reproduced literally below.
 #pragma once
 #include <cmath>
+#include <type_traits>
 
 #if defined(__CUDACC__)
 #define NEFII_HD __host__ __device__ __forceinline__
@@ -20,13 +21,13 @@
 namespace nefii {
 namespace sgm {
 
-template <typename T> struct K {
-  static constexpr T eps = T(1e-6);
-  static constexpr T cos_mu = T(32.7080);
-  static constexpr T cos_lambda = T(0.0315);
-  static constexpr T cos_alpha = T(31.7003);
-  static constexpr T two_pi = T(6.283185307179586);
-  static constexpr T pi = T(3.141592653589793);
+template <typename T> struct K {   // functions, not static members: T may be a dual number inside device code
+  static NEFII_HD T eps() { return T(1e-6); }
+  static NEFII_HD T cos_mu() { return T(32.7080); }
+  static NEFII_HD T cos_lambda() { return T(0.0315); }
+  static NEFII_HD T cos_alpha() { return T(31.7003); }
+  static NEFII_HD T two_pi() { return T(6.283185307179586); }
+  static NEFII_HD T pi() { return T(3.141592653589793); }
 };
 
 NEFII_HD float m_exp(float x) { return expf(x); }
@@ -50,7 +51,7 @@ template <typename T> NEFII_HD T dot3(const T* a, const T* b) { return sum3(a[0]
 template <typename T> NEFII_HD T norm3(const T* a) { return m_sqrt(sum3(a[0] * a[0], a[1] * a[1], a[2] * a[2])); }
 
 // v / (|v| + 1e-6)
-template <typename T> NEFII_HD void unit3(const T* v, T* out, T eps = K<T>::eps) {
+template <typename T> NEFII_HD void unit3(const T* v, T* out, T eps = K<T>::eps()) {
   T d = norm3(v) + eps;
   out[0] = v[0] / d; out[1] = v[1] / d; out[2] = v[2] / d;
 }
@@ -68,11 +69,11 @@ template <typename T> struct HemiCoef { T t, ea, lower, upper; };
 
 template <typename T> NEFII_HD HemiCoef<T> hemi_coef(T sharp_in) {
   HemiCoef<T> c;
-  T sharp = sharp_in + K<T>::eps;
+  T sharp = sharp_in + K<T>::eps();
   T inv = T(1) / sharp;
   c.t = m_sqrt(sharp) * (T(1.6988) + T(10.8438) * inv) / ((T(1) + T(6.2201) * inv) + (T(10.2415) * inv) * inv);
   c.ea = m_exp(-c.t);
-  T rs = (T(1) / sharp) * K<T>::two_pi;      // 2*pi / sharp  == reciprocal(sharp) * 2pi
+  T rs = (T(1) / sharp) * K<T>::two_pi();      // 2*pi / sharp  == reciprocal(sharp) * 2pi
   c.lower = rs * (m_exp(-sharp) - m_exp(T(-2) * sharp));
   c.upper = rs * (T(1) - m_exp(-sharp));
   return c;
@@ -116,7 +117,7 @@ NEFII_HD void sg_product(T ratio, const T* axis1, const T* axis2, T sharp2, T* a
 // sg_render.py:243-252.  `hc2` = hemi_coef(sharp) (may be hoisted by the caller).
 template <typename T>
 NEFII_HD void cosine_lobe_integral(const T* n, const T* axis, T sharp, const T* amp, const HemiCoef<T>& hc2, T* out3) {
-  T ratio = (T(1) / sharp) * K<T>::cos_lambda;   // python float / tensor
+  T ratio = (T(1) / sharp) * K<T>::cos_lambda();   // python float / tensor
   T axis_p[3], sharp_p, e;
   sg_product(ratio, n, axis, sharp, axis_p, sharp_p, e);
   T c1 = dot3(axis_p, n);
@@ -125,8 +126,8 @@ NEFII_HD void cosine_lobe_integral(const T* n, const T* axis, T sharp, const T* 
   T h2 = hemi_eval(hc2, c2);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    T amp_p = (K<T>::cos_mu * amp[c]) * e;
-    out3[c] = amp_p * h1 - (amp[c] * K<T>::cos_alpha) * h2;
+    T amp_p = (K<T>::cos_mu() * amp[c]) * e;
+    out3[c] = amp_p * h1 - (amp[c] * K<T>::cos_alpha()) * h2;
   }
 }
 
@@ -141,13 +142,13 @@ template <typename T>
 NEFII_HD void make_brdf_lobe(const T* n, const T* v, T rough, const T* spec3, BrdfLobe<T>& B) {
   T inv_r4 = T(1) / (((rough * rough) * rough) * rough);
   T b_sharp = T(2) * inv_r4;
-  T b_amp = inv_r4 * (T(1) / K<T>::pi);          // tensor / np.pi on CUDA
+  T b_amp = inv_r4 * (T(1) / K<T>::pi());          // tensor / np.pi on CUDA
   T nv = clamp_min(dot3(n, v), T(0));
   T w[3];
   T two_nv = T(2) * nv;
   w[0] = two_nv * n[0] - v[0]; w[1] = two_nv * n[1] - v[1]; w[2] = two_nv * n[2] - v[2];
   unit3(w, B.axis);
-  B.sharp = b_sharp / (T(4) * nv + K<T>::eps);
+  B.sharp = b_sharp / (T(4) * nv + K<T>::eps());
   T h[3] = {B.axis[0] + v[0], B.axis[1] + v[1], B.axis[2] + v[2]};
   T hu[3];
   unit3(h, hu);
@@ -156,10 +157,10 @@ NEFII_HD void make_brdf_lobe(const T* n, const T* v, T rough, const T* spec3, Br
   T d1 = clamp_min(dot3(B.axis, n), T(0));
   T d2 = clamp_min(dot3(v, n), T(0));
   T k = ((rough + T(1)) * (rough + T(1))) * T(0.125);
-  T g1 = d1 / ((d1 * (T(1) - k) + k) + K<T>::eps);
-  T g2 = d2 / ((d2 * (T(1) - k) + k) + K<T>::eps);
+  T g1 = d1 / ((d1 * (T(1) - k) + k) + K<T>::eps());
+  T g2 = d2 / ((d2 * (T(1) - k) + k) + K<T>::eps());
   T g = g1 * g2;
-  T den = (T(4) * d1) * d2 + K<T>::eps;
+  T den = (T(4) * d1) * d2 + K<T>::eps();
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     T f = spec3[c] + (T(1) - spec3[c]) * fexp;

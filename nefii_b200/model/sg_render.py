@@ -29,12 +29,38 @@ class _RenderWithSG(torch.autograd.Function):
             _lib.stream_ptr(n.device), N, M, K, _lib.dptr(lgt), _lib.dptr(spec), _lib.dptr(rough), _lib.dptr(a),
             _lib.dptr(n), _lib.dptr(v), _lib.dptr(bw, allow_none=True),
             _lib.dptr(out[0]), _lib.dptr(out[1]), _lib.dptr(out[2])))
-        ctx.mark_non_differentiable(out)
+        if blending_weights is None:
+            ctx.save_for_backward(lgt, spec, rough, a, n, v, out)
+        ctx.has_blend = blending_weights is not None
+        ctx.shapes = (specular_reflectance.shape, roughness.shape, diffuse_albedo.shape)
         return out
 
     @staticmethod
-    def backward(ctx, grad_out):  # pragma: no cover - filled in by the backward kernel milestone
-        raise NotImplementedError("render_with_sg backward is not built yet")
+    def backward(ctx, grad_out):
+        if ctx.has_blend:
+            raise NotImplementedError("nefii_b200: render_with_sg backward with blending_weights is not implemented")
+        if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+            raise _lib.NefiiError("nefii_b200: gradients w.r.t. normals / view directions need a trainable geometry, which is "
+                                  "outside the accelerated path")
+        lgt, spec, rough, a, n, v, out = ctx.saved_tensors
+        lib = _lib.raw()
+        dev = n.device
+        N, M, K = n.shape[0], lgt.shape[0], spec.shape[0]
+        g = _lib.f32c(grad_out)
+        acc = torch.zeros(M, 7, device=dev)
+        g_rough = torch.zeros(K, device=dev)
+        g_spec = torch.zeros(K, 3, device=dev)
+        g_alb = torch.zeros(N, 3, device=dev)
+        g_lgt = torch.zeros_like(lgt)
+        if N:
+            _lib.check(lib.nefii_sg_render_bwd(
+                _lib.stream_ptr(dev), N, M, K, lgt.data_ptr(), spec.data_ptr(), rough.data_ptr(), a.data_ptr(), n.data_ptr(),
+                v.data_ptr(), out[1].data_ptr(), out[2].data_ptr(), g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(),
+                acc.data_ptr(), g_rough.data_ptr(), g_spec.data_ptr(), g_alb.data_ptr()))
+            _lib.check(lib.nefii_sg_param_grad(_lib.stream_ptr(dev), M, lgt.data_ptr(), acc.data_ptr(), 1e-6, g_lgt.data_ptr(), 0))
+        spec_shape, rough_shape, alb_shape = ctx.shapes
+        g_spec_in = g_spec if spec_shape[-1] == 3 else g_spec.sum(-1, keepdim=True)
+        return g_lgt, g_spec_in.reshape(spec_shape), g_rough.reshape(rough_shape), g_alb.reshape(alb_shape), None, None, None
 
 
 def render_with_sg(lgtSGs, specular_reflectance, roughness, diffuse_albedo, normal, viewdirs,

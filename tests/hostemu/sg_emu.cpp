@@ -17,7 +17,7 @@ static void sg_render_fwd_t(int n_rays, int n_sg, int n_mat, const T* lgt, const
     const T* n = normal + 3 * r;
     const T* v = view + 3 * r;
     T a_pi[3];
-    for (int c = 0; c < 3; ++c) a_pi[c] = albedo[3 * r + c] * (T(1) / K<T>::pi);
+    for (int c = 0; c < 3; ++c) a_pi[c] = albedo[3 * r + c] * (T(1) / K<T>::pi());
     T s_acc[3] = {0, 0, 0}, d_acc[3] = {0, 0, 0};
     for (int k = 0; k < n_mat; ++k) {
       BrdfLobe<T> B;
@@ -58,4 +58,34 @@ void emu_sg_render_fwd_f64(int n_rays, int n_sg, int n_mat, const double* lgt, c
                            double* out_rgb, double* out_spec, double* out_diff) {
   sg_render_fwd_t<double>(n_rays, n_sg, n_mat, lgt, spec, rough, albedo, normal, view, blend, out_rgb, out_spec, out_diff);
 }
+}
+
+// ---- backward of render_with_sg through forward-mode duals (same code path as csrc/sg_render.cu: sg_render_bwd) ----
+#include "sg_bwd_math.cuh"
+
+extern "C" void emu_sg_render_bwd_f64(int n_rays, int n_sg, int n_mat, const double* lgt, const double* spec, const double* rough,
+                                      const double* albedo, const double* normal, const double* view,
+                                      const double* g_spec, const double* g_diff, double* acc /*[M,7]*/, double* g_rough /*[K]*/,
+                                      double* g_specrefl /*[K,3]*/, double* g_albedo /*[N,3]*/) {
+  for (int r = 0; r < n_rays; ++r) {
+    // the reference clamps the summed specular / diffuse radiance at 0: recompute the sums for the masks
+    double out_rgb[3], out_s[3], out_d[3];
+    sg_render_fwd_t<double>(1, n_sg, n_mat, lgt, spec, rough, albedo + 3 * r, normal + 3 * r, view + 3 * r, nullptr, out_rgb, out_s, out_d);
+    double gs[3], gd[3];
+    for (int c = 0; c < 3; ++c) {
+      gs[c] = out_s[c] > 0 ? g_spec[3 * r + c] : 0.0;
+      gd[c] = out_d[c] > 0 ? g_diff[3 * r + c] : 0.0;
+    }
+    double ga[3] = {0, 0, 0};
+    for (int m = 0; m < n_sg; ++m) {
+      for (int k = 0; k < n_mat; ++k) {
+        double gr = 0, gsr[3] = {0, 0, 0};
+        nefii::sgb::specular_term_bwd<double>(normal + 3 * r, view + 3 * r, lgt + 7 * m, rough[k], spec + 3 * k, gs, acc + 7 * m, gr, gsr);
+        g_rough[k] += gr;
+        for (int c = 0; c < 3; ++c) g_specrefl[3 * k + c] += gsr[c];
+      }
+      nefii::sgb::diffuse_term_bwd<double>(normal + 3 * r, lgt + 7 * m, albedo + 3 * r, (double)n_mat, gd, acc + 7 * m, ga);
+    }
+    for (int c = 0; c < 3; ++c) g_albedo[3 * r + c] = ga[c];
+  }
 }

@@ -55,3 +55,36 @@ def test_f32_close_to_oracle(emu):
     outs, refs = _run(emu, torch.float32, lgt, torch.full((1, 3), 0.04), torch.tensor([[0.5]]), albedo, normal, view)
     for o, r in zip(outs, refs):
         assert torch.allclose(o, r, rtol=2e-3, atol=1e-4)
+
+
+def test_backward_f64_matches_autograd_of_oracle(emu):
+    """render_with_sg backward via forward-mode duals over the forward math (csrc/sg_bwd_math.cuh) == autograd through the oracle."""
+    dt = torch.float64
+    n, M, K = 120, 24, 2
+    normal, view, albedo = [x.to(dt) for x in inputs.shading_inputs(n, seed=8)]
+    lgt = inputs.synthetic_light_sgs(M, seed=9).to(dt)
+    lgt[3, 3] = -lgt[3, 3]          # abs() branches of the raw parameters
+    lgt[5, 4:] = -lgt[5, 4:]
+    spec = torch.tensor([[0.04, 0.05, 0.06], [0.1, 0.2, 0.3]], dtype=dt)
+    rough = torch.tensor([[0.35], [0.7]], dtype=dt)
+    g = torch.Generator().manual_seed(3)
+    g_spec = torch.rand(n, 3, generator=g, dtype=dt)
+    g_diff = torch.rand(n, 3, generator=g, dtype=dt)
+    leaves = [t.clone().requires_grad_(True) for t in (lgt, spec, rough, albedo)]
+    ref = sg.render_with_sg(leaves[0], leaves[1], leaves[2], leaves[3], normal, view)
+    ((ref["sg_specular_rgb"] * g_spec).sum() + (ref["sg_diffuse_rgb"] * g_diff).sum()).backward()
+    acc = torch.zeros(M, 7, dtype=dt)
+    g_rough = torch.zeros(K, dtype=dt)
+    g_sr = torch.zeros(K, 3, dtype=dt)
+    g_alb = torch.zeros(n, 3, dtype=dt)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    emu.emu_sg_render_bwd_f64(n, M, K, p(lgt), p(spec), p(rough), p(albedo.contiguous()), p(normal.contiguous()), p(view.contiguous()),
+                              p(g_spec), p(g_diff), p(acc), p(g_rough), p(g_sr), p(g_alb))
+    ln = lgt[:, :3].norm(dim=-1, keepdim=True)
+    d = ln + 1e-6
+    g_axis = acc[:, :3] / d - lgt[:, :3] * (lgt[:, :3] * acc[:, :3]).sum(-1, keepdim=True) / (ln * d * d)
+    g_raw = torch.cat([g_axis, acc[:, 3:4] * torch.sign(lgt[:, 3:4]), acc[:, 4:] * torch.sign(lgt[:, 4:])], dim=-1)
+    assert torch.allclose(g_raw, leaves[0].grad, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(g_sr, leaves[1].grad, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(g_rough, leaves[2].grad[:, 0], rtol=1e-6, atol=1e-9)
+    assert torch.allclose(g_alb, leaves[3].grad, rtol=1e-6, atol=1e-9)

@@ -83,3 +83,27 @@ def test_background_sg(cuda_device):
     ref = sg.background_sg(lgt, d)
     # only the order of the sum over the 128 lobes differs from the oracle
     assert torch.allclose(out, ref, rtol=1e-4, atol=1e-6), (out - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("rough", [0.3, 0.8])
+def test_backward_matches_oracle_autograd(cuda_device, rough):
+    """north_star: gradients within rel 1e-3 (lgtSGs, roughness, specular reflectance, albedo)."""
+    from nefii_b200.model.sg_render import render_with_sg
+    dev = cuda_device
+    n = 3000
+    normal, view, albedo = [x.to(dev) for x in inputs.shading_inputs(n, seed=21)]
+    lgt = inputs.synthetic_light_sgs(128, seed=22).to(dev)
+    spec = torch.tensor([[0.04, 0.05, 0.06]], device=dev)
+    r = torch.tensor([[rough]], device=dev)
+    gy = torch.rand(n, 3, generator=torch.Generator().manual_seed(1)).to(dev)
+
+    def run(fn):
+        leaves = [t.clone().requires_grad_(True) for t in (lgt, spec, r, albedo)]
+        out = fn(leaves[0], leaves[1], leaves[2], leaves[3], normal, view)
+        (out["sg_rgb"] * gy).sum().backward()
+        return [t.grad for t in leaves]
+
+    got, want = run(render_with_sg), run(sg.render_with_sg)
+    for a, b, name in zip(got, want, ("lgtSGs", "specular", "roughness", "albedo")):
+        rel = (a - b).norm().item() / (b.norm().item() + 1e-20)
+        assert rel < 1e-3, (name, rel)
