@@ -268,6 +268,29 @@ def run_ours(args):
     torch.cuda.synchronize()
     step_ms = e_prof0.elapsed_time(e_prof1)
 
+    # ---- extra (BASELINE metric tail "ms/frame 800x800"): novel-view render, eval mode, 1 ray per pixel, this rank's share ----
+    frame_ms = None
+    try:
+        model.eval()
+        ii, jj = torch.meshgrid(torch.arange(IMG, device=dev).float(), torch.arange(IMG, device=dev).float(), indexing="xy")
+        uv_all = (torch.stack([ii, jj], -1).reshape(1, -1, 2) + 0.5)[:, rank::world]       # pixels strided over ranks
+        obj_all = torch.ones(1, uv_all.shape[1], dtype=torch.bool, device=dev)
+        chunk = 1 << 18                                                                       # memory_capacity_level 18
+        def render_frame():
+            with torch.no_grad():
+                for s0 in range(0, uv_all.shape[1], chunk):
+                    model({'uv': uv_all[:, s0:s0 + chunk], 'object_mask': obj_all[:, s0:s0 + chunk], 'pose': pose, 'intrinsics': K})
+        render_frame()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        render_frame()
+        f1.record()
+        barrier()
+        frame_ms = max_over_ranks(f0.elapsed_time(f1))
+    finally:
+        model.train()
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -302,6 +325,7 @@ def run_ours(args):
             "e2e": {"value": rays_e2e / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
+            "ms_per_frame_800x800": frame_ms,
             "clocks": clocks.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu,

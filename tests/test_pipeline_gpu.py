@@ -45,7 +45,7 @@ def test_forward_matches_oracle_pipeline(cuda_device, training, rays):
                                        training, vecs[0], vecs[1])
     a, b = mine['network_object_mask'], ref['network_object_mask']
     agree = a == b
-    assert agree.float().mean().item() > 0.99, agree.float().mean().item()
+    assert agree.float().mean().item() > 0.998, agree.float().mean().item()      # measured: 0 mismatches (tools/diag_gpu.py pipeline)
     assert int((a & b).sum()) > 100
     assert torch.equal(mine['object_mask'], ref['object_mask'])
     sel = agree
@@ -53,7 +53,7 @@ def test_forward_matches_oracle_pipeline(cuda_device, training, rays):
     # the arg-min over 100 random depths (minimal_sdf_points): the arg-min may jump between two near-equal samples, so
     # there the minimum VALUE (sdf_output) is compared instead of its position.
     hit = sel & a
-    assert ((mine['points'] - ref['points'])[hit].abs().max(-1)[0] < 1e-4).float().mean().item() > 0.99
+    assert ((mine['points'] - ref['points'])[hit].abs().max(-1)[0] < 1e-4).float().mean().item() > 0.995
     miss = sel & ~a
     if bool(miss.any()):
         assert (mine['sdf_output'] - ref['sdf_output'])[miss].abs().max().item() < 1e-4
@@ -63,7 +63,8 @@ def test_forward_matches_oracle_pipeline(cuda_device, training, rays):
         x, y = mine[k][sel].float(), ref[k][sel].float()
         err = (x - y).abs() / (y.abs() + 1e-3)
         p95 = err.flatten().kthvalue(max(1, int(0.95 * err.numel())))[0].item()
-        assert p95 < 2e-3, (k, p95)
+        # idr_rgb = (raw MLP output)^2 of a random-init net: tiny values, the relative error of the square is amplified
+        assert p95 < (8e-3 if k == 'idr_rgb_values' else 5e-4), (k, p95)
     # secondary rays: same directions (bit-exact sampler) wherever the primary hit point agrees
     if mine['secondary_dir'] is not None and mine['secondary_dir'].shape == ref['secondary_dir'].shape:
         d = (mine['secondary_dir'] - ref['secondary_dir']).abs().amax(-1)
@@ -146,3 +147,29 @@ def test_forward_with_point_entry(cuda_device):
         nrm = pipeline.unit(omlp.sdf_gradient(om.sdf, points.reshape(-1, 3)))
         ref = omlp.radiance_forward(om.radiance, points.reshape(-1, 3), nrm, pipeline.unit(-dirs.reshape(-1, 3)), feats)
     assert torch.allclose(res['idr_rgb_values'], ref.reshape(n, R, 3).mean(1), rtol=2e-3, atol=2e-4)
+
+
+def test_degenerate_batches(cuda_device):
+    """All rays miss (background only, gradient reaches lgtSGs through the environment lookup) and a one-ray batch."""
+    dev = cuda_device
+    net, om = _build(dev, seed=3)
+    net.train(True)
+    uv, pose, K = rh.camera_batch(8, 2, seed=1, cam=(0.0, 0.0, -3.0))
+    pose = pose.clone()
+    pose[0, :3, :3] = torch.diag(torch.tensor([1.0, 1.0, -1.0]))          # look away from the object
+    S = uv.shape[1]
+    inp = dict(uv=uv.to(dev), pose=pose.to(dev), intrinsics=K.to(dev), object_mask=torch.zeros(1, S, dtype=torch.bool, device=dev))
+    out = net(inp)
+    assert not out['network_object_mask'].any()
+    assert out['secondary_points'] is None
+    assert torch.isfinite(out['sg_rgb_values']).all()
+    out['sg_rgb_values'].sum().backward()
+    g = net.envmap_material_network.lgtSGs.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+    # a single pixel, single ray, eval mode
+    net.eval()
+    one = dict(uv=torch.tensor([[[4.0, 4.0]]], device=dev), pose=rh.camera_batch(8, 0)[1].to(dev), intrinsics=K.to(dev),
+               object_mask=torch.ones(1, 1, dtype=torch.bool, device=dev))
+    with torch.no_grad():
+        o = net(one)
+    assert o['sg_rgb_values'].shape == (1, 3) and torch.isfinite(o['sg_rgb_values']).all()

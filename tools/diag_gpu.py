@@ -356,6 +356,41 @@ def diag_dotorder():
         ((r / 3.141592653589793) == r / torch.tensor(3.141592653589793, device=dev)).float().mean().item()))
 
 
+def diag_pipeline():
+    from oracle import pipeline, ref_harness as rh
+    from nefii_b200.model.implicit_differentiable_renderer import IDRNetwork
+    from nefii_b200.utils.conf import default_model_conf
+    dev = torch.device("cuda:0")
+    om = rh.small_model(seed=0)
+    torch.manual_seed(0)
+    net = IDRNetwork(default_model_conf()).to(dev)
+    rh.load_oracle_weights(net, om)
+    om = om.to(dev)
+    for training, rays, n_side in ((False, 0, 64), (True, 4, 48)):
+        net.train(training)
+        uv, pose, K = rh.camera_batch(n_side, rays, seed=3)
+        S = uv.shape[1]
+        obj = torch.ones(1, S, dtype=torch.bool)
+        g = torch.Generator().manual_seed(103)
+        U = torch.rand(S * max(rays, 1), 7, generator=g).to(dev)
+        vecs = [torch.rand(100, generator=g) for _ in range(2)]
+        inp = dict(uv=uv.to(dev), pose=pose.to(dev), intrinsics=K.to(dev), object_mask=obj.to(dev))
+        with torch.no_grad():
+            mine = net.forward_with_uv(inp, uniforms=U, trace_uniforms=vecs[0])
+            ref = pipeline.forward_with_uv(om, inp['uv'], inp['pose'], inp['intrinsics'], inp['object_mask'], lambda n: U[:n], training, vecs[0], vecs[1])
+        a, b = mine['network_object_mask'], ref['network_object_mask']
+        agree = a == b
+        hit = agree & a
+        print("PIPE train=%d rays/px=%d pixels=%d: mask agree %.5f (%d mismatches), hits %d" % (training, max(rays, 1), S, agree.float().mean().item(), int((~agree).sum()), int(hit.sum())))
+        print("   depth |dp| on hits: median %.2e p99 %.2e max %.2e" % tuple(((mine['points'] - ref['points'])[hit].abs().amax(-1)).quantile(torch.tensor([0.5, 0.99, 1.0], device=dev)).tolist()))
+        for k in ('normal_values', 'idr_rgb_values', 'sg_rgb_values', 'sg_diffuse_rgb_values', 'sg_specular_rgb_values', 'sg_roughness_values', 'sg_diffuse_albedo_values'):
+            x, y = mine[k][hit].float(), ref[k][hit].float()
+            rel = ((x - y).abs() / (y.abs() + 1e-3)).flatten()
+            print("   %-26s rel err median %.2e p95 %.2e p99 %.2e max %.2e" % ((k,) + tuple(rel.quantile(torch.tensor([0.5, 0.95, 0.99, 1.0], device=dev)).tolist())))
+        if mine['secondary_mask'] is not None and mine['secondary_mask'].shape == ref['secondary_mask'].shape:
+            print("   secondary mask agree %.5f" % (mine['secondary_mask'] == ref['secondary_mask']).float().mean().item())
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["sg", "gemm"]
     print(torch.cuda.get_device_name(0))
