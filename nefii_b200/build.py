@@ -58,7 +58,6 @@ def build(verbose=False):
         for _, log in results:
             sys.stderr.write(log)
     if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"]
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
                "--cudart", "shared", "-o", LIB] + objs
         p = subprocess.run(cmd, capture_output=True, text=True)

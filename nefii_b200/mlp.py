@@ -91,7 +91,7 @@ class _DenseMlp(torch.autograd.Function):
             wp = ops.split_to_planes(W, rows_pad=ops.round_up(out_dim, 256), cols_pad=k_pad)
             packed.append(W)
             bias = _lib.f32c(bs[l])
-            a = acts[-1] if need_grad else acts[-1]
+            a = acts[-1]
             if l < n_hidden - 1:
                 dst = _planes(n, ops.round_up(out_dim, 64), dev)
                 ops.gemm_split_bf16(a, wp, k_pad, out_dim, act=act, bias=bias, dst=dst, dst_ncols=out_dim,
