@@ -169,10 +169,11 @@ def diag_ablate():
     b = ops.split_to_planes(w)
     dst = (torch.empty(rows, n, device=dev, dtype=torch.bfloat16), torch.empty(rows, n, device=dev, dtype=torch.bfloat16))
     names = {0: "full", 1: "no final math/stores", 8: "no flush", 9: "no flush, no final", 2: "no TMA", 4: "no MMA", 6: "no TMA, no MMA",
-             11: "no TMA, no flush, no final (MMA only)", 13: "TMA only (no MMA, flush, final)", 15: "barriers only", 3: "no TMA no final", 5: "no MMA no final"}
-    for cl in (1, 2):
+             11: "no TMA, no flush, no final (MMA only)", 13: "TMA only (no MMA, flush, final)", 15: "barriers only", 3: "no TMA no final", 5: "no MMA no final",
+             16: "final math only (no staging, no stores)", 32: "no global stores", 22: "epilogue alone, math only", 38: "epilogue alone, no global stores"}
+    for cl in (1,):
         _lib.check(_lib.raw().nefii_gemm_set_cluster(cl))
-        for mask in (0, 1, 8, 9, 2, 3, 4, 5, 6, 11, 13, 15):
+        for mask in (0, 1, 8, 9, 2, 3, 4, 5, 6, 11, 13, 15, 16, 32, 22, 38):
             _lib.check(_lib.raw().nefii_gemm_set_debug(mask))
             ms = ev_time(lambda: ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n), iters=10)
             print("ABLATE cl=%d mask=%2d %-42s %.4f ms" % (cl, mask, names[mask], ms))
