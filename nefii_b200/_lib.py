@@ -25,6 +25,7 @@ SIGNATURES = {
     "nefii_gemm_set_cluster": [c_int],
     "nefii_gemm_set_debug": [c_int],
     "nefii_gemm_set_k_flush": [c_int],
+    "nefii_gemm_set_k_flush_head": [c_int],
     "nefii_gemm_profile_fetch": [c_void_p],
     "nefii_assemble_input": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int],
     "nefii_transpose_planes": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

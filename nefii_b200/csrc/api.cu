@@ -205,6 +205,7 @@ int nefii_gemm_profile_enable(int on) { return nefii::gemm_profile_enable(on); }
 int nefii_gemm_set_cluster(int cl) { return nefii::gemm_set_cluster(cl); }
 int nefii_gemm_set_debug(int mask) { return nefii::gemm_set_debug(mask); }
 int nefii_gemm_set_k_flush(int k) { return nefii::gemm_set_k_flush(k); }
+int nefii_gemm_set_k_flush_head(int k) { return nefii::gemm_set_k_flush_head(k); }
 int nefii_gemm_profile_fetch(double* out3) { return nefii::gemm_profile_fetch(out3); }
 
 int nefii_sg_render_bwd(void* stream, int n_rays, int n_sg, int n_mat, const float* lgt_sgs, const float* specular,

@@ -14,6 +14,7 @@
 //                 output layer), overlapped with the MMAs of the next column chunk.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <vector>
 #include "mlp_gemm.cuh"
 
@@ -25,10 +26,22 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int kStages = 2;
 constexpr int kATileBytes = BM * BK * 2;   // 16 KB
-constexpr int kBTileBytes = BN * BK * 2;   // 32 KB
-constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;  // 96 KB
+// Operand ring.  CL = 1: one CTA multiplies its 128 rows by the whole 256-row weight tile (96 KB per stage, 2 stages).
+// CL = 2: a CTA pair (cta_group::2, one 256 x 256 x 16 MMA across two SMs): each CTA stages its own 128 rows of A and
+// HALF of the weight tile, the tensor cores read the other half from the peer's shared memory -- 64 KB per stage, 3 stages,
+// and a third less shared-memory traffic per FLOP (the single-CTA kernel is bound by exactly that, profiles/r1_gemm_*.md).
+template <int CL> struct Ring {
+  static constexpr int kStages = CL == 2 ? 3 : 2;
+  static constexpr int kBRows = BN / CL;
+  static constexpr int kBTileBytes = kBRows * BK * 2;
+  static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
+};
+constexpr int kRingBytes = 196608;
+static_assert(Ring<1>::kStages * Ring<1>::kStageBytes == kRingBytes && Ring<2>::kStages * Ring<2>::kStageBytes == kRingBytes, "ring size");
+constexpr int kMaxStages = 3;
+// mbarriers: [0..2] operand stage full, [3..5] stage empty, [6..7] TMEM partial full, [8..9] TMEM partial empty
+constexpr int kBarFull = 0, kBarEmpty = kMaxStages, kBarTFull = 2 * kMaxStages, kBarTEmpty = 2 * kMaxStages + 2;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;  // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1,2: epilogue
 constexpr int kTmemCols = 512;
@@ -40,7 +53,8 @@ constexpr int kBiasSmemFloats = 512;      // the bias of layers up to 512 output
 // (SWIZZLE_128B atoms); dynamic shared memory starts at the CTA window's base, the kernel traps if that ever changes.
 constexpr size_t kTailBytes = (size_t)kEpiWarps * kStageOutBytes + kBiasSmemFloats * sizeof(float);
 static_assert(kTailBytes >= 2 * BM * kMaxLast * sizeof(float), "fused-layer partials alias the staging area");
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 256 /*barriers*/ + kTailBytes;
+constexpr int kBarBytes = 512;            // barriers + TMEM slot; keeps the staging tiles 512-byte aligned (SWIZZLE_64B pattern)
+constexpr size_t kSmemBytes = (size_t)kRingBytes + kBarBytes + kTailBytes;
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,12 +91,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, uint16_t mask) {
+// CTA-pair load: lands in this CTA's shared memory, completes bytes on the LEADER CTA's barrier (bit 24 of a
+// shared::cluster address selects the odd CTA of a pair; clearing it names the same barrier in the even one).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "h"(mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(x), "r"(y)
       : "memory");
 }
+// plane stores of whole 32-row tiles: bulk tensor store from the staged (64 B-swizzled) tile, one instruction per plane
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -92,9 +118,20 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+// commit of a CTA pair's MMAs: one arrive on the barrier at this offset in each CTA of the mask
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar), "r"(rank)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -107,6 +144,16 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
@@ -159,6 +206,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M=128, N=256
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// CTA pair: M = 256 (128 rows in each CTA's TMEM), N = 256
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 // ---- branch-free activation helpers (fast intrinsics: the error they add, <= 1e-9 absolute on a
 // softplus output, is far below the bf16x3 product error; the SG kernels never use them) ----------
@@ -280,10 +329,15 @@ struct FastStore {
   __nv_bfloat16* p_lo;
   long long stride8;            // 8 rows, in elements
   unsigned ok_mask;             // bit i: row_warp0 + 8 i + lane / 4 is a valid row
+  const CUtensorMap* map_hi;    // bulk-store path (whole 32-row tiles): the planes as 2-D tensors, origin at dst_col0
+  const CUtensorMap* map_lo;
+  uint32_t st_u32;              // staging base (shared-window address)
+  int y0;                       // row_warp0
 };
 
-template <int ACT>
+template <int ACT, bool TMA>
 __device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bias4, int n_span0, float scale, const FastStore& fs, int dbg) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int c = 0; c < kColsPerWarp / 32; ++c) {
     const float* v = acc + c * 32;
@@ -302,11 +356,24 @@ __device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bia
       if (hq[0].x == 0x7fc07fc1u && lq[3].w == 0x12345678u) fs.p_hi[c] = __float2bfloat16(1.f);
       continue;
     }
+    if (lane == 0) bulk_wait_read_all();   // an earlier bulk store may still be reading the staging tile
     __syncwarp();     // the previous group's tiles have been read
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       fs.st_in[g ^ fs.sw_in] = hq[g];
       fs.st_in[128 + (g ^ fs.sw_in)] = lq[g];
+    }
+    if (TMA) {
+      // the staged layout IS the tensor map's SWIZZLE_64B layout (16-byte piece ^= (row >> 1) & 3): one bulk store per
+      // plane writes the 32 x 64 B tile; the warp goes straight on to the next group's math
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0 && !(dbg & 32)) {
+        tma_store_2d(fs.map_hi, fs.st_u32, n_span0 + c * 32, fs.y0);
+        tma_store_2d(fs.map_lo, fs.st_u32 + 2048, n_span0 + c * 32, fs.y0);
+        bulk_commit();
+      }
+      continue;
     }
     __syncwarp();
     uint4 oh[4], ol[4];
@@ -410,14 +477,27 @@ __device__ __forceinline__ void finish_group(const GemmEpilogue& epi, float* v, 
 // sums (measured: -4 ulp at K=512, -39 ulp at K=2048, tools/diag_gpu.py trunc).  Every 64-wide K block is
 // therefore multiplied into a *fresh* TMEM buffer (the two small cross terms first, hi*hi last) and the
 // partial products are summed across K blocks by the epilogue warps in registers with round-to-nearest.
-// CL > 1: thread-block cluster of CL CTAs working on CL consecutive row tiles.  They need the same weight tile at
-// the same time, so each CTA fetches 1/CL of it and TMA-multicasts it into every CTA of the cluster: the L2 -> SM
-// operand traffic per CTA drops from 96 KB to 32 + 64/CL KB per K block (the kernel is bound by that traffic,
-// profiles/r1_gemm_*.md).
+// CL = 2: the CTAs of a pair (cluster of 2, consecutive row tiles) run ONE tcgen05.mma.cta_group::2 stream issued by the
+// even CTA; both load operands (completing on the leader's barrier), both run their own epilogue on their own TMEM.
+// Partial schedule of one column chunk: the first two partials take `head` K blocks each, the rest `tail`.  Only two
+// partials fit in TMEM, so the MMAs of everything after the second partial wait for the epilogue's final math of the
+// previous chunk: longer head partials move work under that math, shorter tail partials bound the truncation error.
+struct PartSched {
+  int head, tail, k_blocks;
+  __device__ __forceinline__ int count() const {
+    return k_blocks <= 2 * head ? (k_blocks + head - 1) / head : 2 + (k_blocks - 2 * head + tail - 1) / tail;
+  }
+  __device__ __forceinline__ int begin(int p) const {
+    const int b = p <= 2 ? p * head : 2 * head + (p - 2) * tail;
+    return b < k_blocks ? b : k_blocks;
+  }
+};
+
 template <int MODE, int ACT, bool FUSE, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                       const __grid_constant__ CUtensorMap map_d_hi, const __grid_constant__ CUtensorMap map_d_lo, int store_tma,
                        const int* __restrict__ count_ptr, int rows_cap, int k_blocks_total, int n_chunks, int kb_per_split,
                        long long f32_split_stride, int dbg, int k_flush, const __grid_constant__ GemmEpilogue epi_in) {
   // Persistent over row tiles: CTA x handles tiles x, x + gridDim.x, ... so that the final epilogue math of one tile
@@ -435,19 +515,23 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     if (c < m_limit) m_limit = c;
   }
   // uniform over the cluster: leave only if the cluster's FIRST tile is already past the valid rows
-  if ((long long)(m_tile0 - (m_tile0 % CL)) * BM >= m_limit || k_blocks <= 0) return;
-  static_assert(CL == 1, "the persistent tile loop assumes one CTA per cluster");
-  const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
-  constexpr uint16_t kMcMask = (uint16_t)((1u << CL) - 1u);
+  static_assert(CL == 1 || CL == 2, "single CTA or a cta_group::2 pair");
+  using R = Ring<CL>;
+  constexpr int kStages = R::kStages;
+  constexpr int kStageBytes = R::kStageBytes;
+  constexpr int kBTileBytes = R::kBTileBytes;
+  const int cta_rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  // every loop below runs while the PAIR's first tile is live, so both CTAs of a pair take the same trips
+  if ((long long)(m_tile0 - cta_rank) * BM >= m_limit || k_blocks <= 0) return;
+#define NEFII_TILE_LIVE(t) ((long long)((t) - cta_rank) * BM < m_limit)
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw;   // no integer round-trip: keeps every access below a shared-window (LDS/STS) access
   if (smem_u32(smem_raw) & 1023u) __trap();
   unsigned char* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
-  // bars[0..1] smem full, [2..3] smem empty, [4..5] tmem full, [6..7] tmem empty ; then the TMEM base slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* s_last = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes + 256);   // [2][BM][kMaxLast]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kRingBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  float* s_last = reinterpret_cast<float*>(smem + (size_t)kRingBytes + kBarBytes);   // [2][BM][kMaxLast]
 
   // Warp roles: warps 0..7 epilogue, warp 8 TMA producer, warp 9 MMA issuer (+TMEM alloc), warps 10, 11 idle.  The role
   // warps carry the highest warp ids of their schedulers: the issue arbiter prefers the highest id, and the single
@@ -458,18 +542,23 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(&bars[0 + s]), 1);
-      mbar_init(smem_u32(&bars[2 + s]), CL);   // every CTA of the cluster reads the multicast weight tile
-      mbar_init(smem_u32(&bars[4 + s]), 1);
-      mbar_init(smem_u32(&bars[6 + s]), kEpiWarps);
+      mbar_init(smem_u32(&bars[kBarFull + s]), 1);    // the (leader's) producer arrives once, TMA completes the bytes
+      mbar_init(smem_u32(&bars[kBarEmpty + s]), 1);   // one commit (multicast to both CTAs of a pair)
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bars[kBarTFull + b]), 1);
+      mbar_init(smem_u32(&bars[kBarTEmpty + b]), kEpiWarps * CL);   // the leader hears from both CTAs' epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (role == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CL == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {   // the same warp of both CTAs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -486,26 +575,27 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int m_tile = m_tile0; (long long)m_tile * BM < m_limit; m_tile += tile_stride)
+      for (int m_tile = m_tile0; NEFII_TILE_LIVE(m_tile); m_tile += tile_stride)
       for (int nc = 0; nc < n_chunks; ++nc) {
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(smem_u32(&bars[2 + stage]), phase ^ 1);
-          const uint32_t full = smem_u32(&bars[0 + stage]);
-          if (dbg & 2) { mbar_arrive(full); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
-          mbar_expect_tx(full, kStageBytes);
+          mbar_wait(smem_u32(&bars[kBarEmpty + stage]), phase ^ 1);
+          const uint32_t full = smem_u32(&bars[kBarFull + stage]);
+          if (dbg & 2) { if (cta_rank == 0) mbar_arrive(full); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
           unsigned char* st = tiles + (size_t)stage * kStageBytes;
           const int kx = (kb_begin + kb) * BK;
-          tma_load_2d(smem_u32(st), &map_a_hi, full, kx, m_tile * BM);
-          tma_load_2d(smem_u32(st + kATileBytes), &map_a_lo, full, kx, m_tile * BM);
           if (CL == 1) {
+            mbar_expect_tx(full, kStageBytes);
+            tma_load_2d(smem_u32(st), &map_a_hi, full, kx, m_tile * BM);
+            tma_load_2d(smem_u32(st + kATileBytes), &map_a_lo, full, kx, m_tile * BM);
             tma_load_2d(smem_u32(st + 2 * kATileBytes), &map_b_hi, full, kx, nc * BN);
             tma_load_2d(smem_u32(st + 2 * kATileBytes + kBTileBytes), &map_b_lo, full, kx, nc * BN);
           } else {
-            constexpr int kRowsPer = BN / CL;                 // this CTA's slice of the weight tile
-            constexpr int kSliceBytes = kRowsPer * BK * 2;
-            const int row0 = nc * BN + (int)cta_rank * kRowsPer;
-            tma_load_2d_mc(smem_u32(st + 2 * kATileBytes + cta_rank * kSliceBytes), &map_b_hi, full, kx, row0, kMcMask);
-            tma_load_2d_mc(smem_u32(st + 2 * kATileBytes + kBTileBytes + cta_rank * kSliceBytes), &map_b_lo, full, kx, row0, kMcMask);
+            if (cta_rank == 0) mbar_expect_tx(full, 2 * kStageBytes);   // both CTAs' bytes land on the leader's barrier
+            const int brow = nc * BN + cta_rank * R::kBRows;            // this CTA's half of the weight tile
+            tma_load_2d_pair(smem_u32(st), &map_a_hi, full, kx, m_tile * BM);
+            tma_load_2d_pair(smem_u32(st + kATileBytes), &map_a_lo, full, kx, m_tile * BM);
+            tma_load_2d_pair(smem_u32(st + 2 * kATileBytes), &map_b_hi, full, kx, brow);
+            tma_load_2d_pair(smem_u32(st + 2 * kATileBytes + kBTileBytes), &map_b_lo, full, kx, brow);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -513,48 +603,57 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     }
   } else if (role == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       // K blocks are accumulated in TMEM in groups of k_flush ("partials"); each partial goes to a fresh buffer and is
       // added to the register accumulators by the epilogue warps (bounds the tensor core's truncation bias), and the two
       // buffers let the MMAs of up to two partials run ahead of the epilogue's final math.
-      const int parts_per_chunk = (k_blocks + k_flush - 1) / k_flush;
+      const PartSched sched{(k_flush >> 8) ? (k_flush >> 8) : (k_flush & 255), k_flush & 255, k_blocks};
+      const int parts_per_chunk = sched.count();
       uint32_t pcount = 0;
-      for (int m_tile = m_tile0; (long long)m_tile * BM < m_limit; m_tile += tile_stride)
+      for (int m_tile = m_tile0; NEFII_TILE_LIVE(m_tile); m_tile += tile_stride)
       for (int nc = 0; nc < n_chunks; ++nc) {
         for (int pi = 0; pi < parts_per_chunk; ++pi, ++pcount) {
           const int buf = pcount & 1;
-          mbar_wait(smem_u32(&bars[6 + buf]), ((pcount >> 1) & 1) ^ 1);   // the partial of two groups ago was read
+          mbar_wait(smem_u32(&bars[kBarTEmpty + buf]), ((pcount >> 1) & 1) ^ 1);   // the partial of two groups ago was read
           const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-          const int kb_end = min(k_blocks, (pi + 1) * k_flush);
-          for (int kb = pi * k_flush; kb < kb_end; ++kb) {
-            mbar_wait(smem_u32(&bars[0 + stage]), phase);
+          const int kb_first = sched.begin(pi), kb_end = sched.begin(pi + 1);
+          for (int kb = kb_first; kb < kb_end; ++kb) {
+            mbar_wait(smem_u32(&bars[kBarFull + stage]), phase);
             tc_fence_after();
             const uint32_t st = smem_u32(tiles + (size_t)stage * kStageBytes);
             const uint64_t a_hi = make_smem_desc(st);
             const uint64_t a_lo = make_smem_desc(st + kATileBytes);
             const uint64_t b_hi = make_smem_desc(st + 2 * kATileBytes);
             const uint64_t b_lo = make_smem_desc(st + 2 * kATileBytes + kBTileBytes);
-            const uint32_t fresh = (kb == pi * k_flush) ? 0u : 1u;
+            const uint32_t fresh = (kb == kb_first) ? 0u : 1u;
             if (!(dbg & 4)) {
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
                 const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step inside the swizzle row
-                tc_mma_bf16(tmem_d, a_hi + koff, b_lo + koff, kIdesc, (k != 0) ? 1u : fresh);
-                tc_mma_bf16(tmem_d, a_lo + koff, b_hi + koff, kIdesc, 1);
+                if (CL == 1) {
+                  tc_mma_bf16(tmem_d, a_hi + koff, b_lo + koff, kIdesc, (k != 0) ? 1u : fresh);
+                  tc_mma_bf16(tmem_d, a_lo + koff, b_hi + koff, kIdesc, 1);
+                } else {
+                  tc_mma_bf16_pair(tmem_d, a_hi + koff, b_lo + koff, kIdescPair, (k != 0) ? 1u : fresh);
+                  tc_mma_bf16_pair(tmem_d, a_lo + koff, b_hi + koff, kIdescPair, 1);
+                }
               }
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
                 const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-                tc_mma_bf16(tmem_d, a_hi + koff, b_hi + koff, kIdesc, 1);
+                if (CL == 1) tc_mma_bf16(tmem_d, a_hi + koff, b_hi + koff, kIdesc, 1);
+                else tc_mma_bf16_pair(tmem_d, a_hi + koff, b_hi + koff, kIdescPair, 1);
               }
             }
-            if (CL == 1) tc_commit(smem_u32(&bars[2 + stage]));   // frees the smem stage once these MMAs retire
-            else tc_commit_mc(smem_u32(&bars[2 + stage]), kMcMask);   // ... in every CTA that multicasts into it
+            // frees the operand stage (in both CTAs of a pair) once these MMAs retire
+            if (CL == 1) tc_commit(smem_u32(&bars[kBarEmpty + stage]));
+            else tc_commit_pair(smem_u32(&bars[kBarEmpty + stage]), 3);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          tc_commit(smem_u32(&bars[4 + buf]));     // this partial product is ready
+          if (CL == 1) tc_commit(smem_u32(&bars[kBarTFull + buf]));     // this partial product is ready
+          else tc_commit_pair(smem_u32(&bars[kBarTFull + buf]), 3);       // ... in both CTAs' TMEM
         }
       }
     }
@@ -566,7 +665,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int half = e >> 2;            // which 128-column half of the 256-column chunk
     const int row_in_tile = quarter * 32 + lane;
-    unsigned char* tail = smem + (size_t)kStages * kStageBytes + 256;
+    unsigned char* tail = smem + (size_t)kRingBytes + kBarBytes;
     uint4* stage_out = reinterpret_cast<uint4*>(tail + (size_t)e * kStageOutBytes);
     float* s_bias = reinterpret_cast<float*>(tail + (size_t)kEpiWarps * kStageOutBytes);
     // plain hidden layer writing aligned planes: bias staged in shared memory, spans take finish_span_fast
@@ -581,12 +680,16 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     fs.st_in = stage_out + lane * 4;
     fs.st_out = stage_out + (lane >> 2) * 4 + ((lane & 3) ^ ((lane >> 3) & 3));
     fs.stride8 = 8ll * epi.dst.ld;
+    fs.map_hi = &map_d_hi;
+    fs.map_lo = &map_d_lo;
+    fs.st_u32 = smem_u32(stage_out);
     const int n_loop = epi.dst_zero_to > epi.n_valid ? epi.dst_zero_to : epi.n_valid;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kColsPerWarp);
     float acc[kColsPerWarp];
-    const int parts_per_chunk = (k_blocks + k_flush - 1) / k_flush;
+    const PartSched sched{(k_flush >> 8) ? (k_flush >> 8) : (k_flush & 255), k_flush & 255, k_blocks};
+    const int parts_per_chunk = sched.count();
     uint32_t pcount = 0;
-    for (int m_tile = m_tile0; (long long)m_tile * BM < m_limit; m_tile += tile_stride) {
+    for (int m_tile = m_tile0; NEFII_TILE_LIVE(m_tile); m_tile += tile_stride) {
     const long long row = (long long)m_tile * BM + row_in_tile;
     const bool row_ok = row < m_limit;
     float part[kMaxLast] = {0.f, 0.f, 0.f, 0.f};
@@ -597,11 +700,12 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       fs.ok_mask = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) fs.ok_mask |= (r0 + 8 * i < m_limit) ? (1u << i) : 0u;
+      fs.y0 = (int)(row - lane);
     }
     for (int nc = 0; nc < n_chunks; ++nc) {
       for (int pi = 0; pi < parts_per_chunk; ++pi, ++pcount) {
         const int buf = pcount & 1;
-        mbar_wait(smem_u32(&bars[4 + buf]), (pcount >> 1) & 1);
+        mbar_wait(smem_u32(&bars[kBarTFull + buf]), (pcount >> 1) & 1);
         tc_fence_after();
         // four TMEM loads in flight per wait: the flush is latency-bound otherwise
         if (!(dbg & 8))
@@ -621,12 +725,19 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars[6 + buf]));
+        if (lane == 0) {
+          if (CL == 1) mbar_arrive(smem_u32(&bars[kBarTEmpty + buf]));
+          else mbar_arrive_cluster(smem_u32(&bars[kBarTEmpty + buf]), 0);   // the leader issues the pair's MMAs
+        }
       }
       const int n_span0 = nc * BN + half * kColsPerWarp;
       if (dbg & 1) continue;
       if (fast_layer && n_span0 + kColsPerWarp <= epi.n_valid && n_span0 + kColsPerWarp <= epi.dst_ncols) {
-        finish_span_fast<ACT>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg);
+        // whole 32-row tiles leave by bulk tensor store; the ragged last tile keeps per-row predicates
+        if (store_tma && row - lane + 32 <= m_limit)
+          finish_span_fast<ACT, true>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg);
+        else
+          finish_span_fast<ACT, false>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg);
         continue;
       }
 #pragma unroll
@@ -651,6 +762,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");   // s_last is reused by the next tile
     }
     }   // tile loop
+    if (lane == 0) bulk_wait_all();   // this warp's bulk stores have left shared memory and are on their way
   }
 
   tc_fence_before();
@@ -658,8 +770,10 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   if (CL > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (role == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (CL == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
+#undef NEFII_TILE_LIVE
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -693,6 +807,21 @@ int make_map(CUtensorMap* map, const void* base, int rows, int ld, int k_extent,
   return NEFII_OK;
 }
 
+// [rows, cols] bf16 plane view (row stride ld) for the epilogue's 32 x 32 bulk stores out of 64 B-swizzled staging tiles
+int make_store_map(CUtensorMap* map, const void* base, int rows, int ld, int cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(NEFII_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(NEFII_ERR_CUDA, "cuTensorMapEncodeTiled (store) failed (%d) rows=%d ld=%d cols=%d", (int)r, rows, ld, cols);
+  return NEFII_OK;
+}
+
 __global__ void split_to_planes_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, int transpose,
                                        float scale, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                        int rows_pad, int cols_pad) {
@@ -717,9 +846,15 @@ __global__ void split_to_planes_kernel(const float* __restrict__ src, int rows, 
 
 namespace {
 int g_k_flush = 2;        // K blocks (of 64) accumulated inside TMEM before the sum moves to registers; see gemm_set_k_flush
+int g_store_tma = getenv("NEFII_GEMM_NO_TMA_STORE") ? 0 : 1;   // development switch for A/B timing
+int g_k_flush_head = 2;   // ... for the first two partials of a column chunk (gemm_set_k_flush_head)
 int g_debug = 0;          // development only: bit mask that disables pipeline pieces for timing experiments
-int g_cluster_pref = 1;   // largest TMA-multicast cluster the launcher may use (1, 2 or 4); measured on B200 (profiles/
-                          // r1_gemm_ablation.md): operand traffic is not the bound, multicast is 3-15 % slower -> off by default
+// 1: single-CTA kernel, 2: cta_group::2 pairs (nefii_gemm_set_cluster; NEFII_GEMM_CLUSTER overrides the default at load)
+int env_cluster_pref() {
+  const char* e = getenv("NEFII_GEMM_CLUSTER");
+  return (e && e[0] == '2') ? 2 : 1;
+}
+int g_cluster_pref = env_cluster_pref();
 struct ProfRec {
   cudaEvent_t a, b;
   double flops_per_row;
@@ -731,7 +866,7 @@ std::vector<ProfRec> g_prof;
 }  // namespace
 
 int gemm_set_cluster(int cl) {
-  NEFII_CHECK_ARG(cl == 1 || cl == 2 || cl == 4, "gemm_set_cluster: cluster size must be 1, 2 or 4");
+  NEFII_CHECK_ARG(cl == 1 || cl == 2, "gemm_set_cluster: 1 (single CTA) or 2 (cta_group::2 pair)");
   g_cluster_pref = cl;
   return NEFII_OK;
 }
@@ -740,6 +875,12 @@ int gemm_set_debug(int mask) { g_debug = mask; return NEFII_OK; }
 int gemm_set_k_flush(int k) {
   NEFII_CHECK_ARG(k >= 1 && k <= 64, "gemm_set_k_flush: out of range");
   g_k_flush = k;
+  g_k_flush_head = k;
+  return NEFII_OK;
+}
+int gemm_set_k_flush_head(int k) {
+  NEFII_CHECK_ARG(k >= 1 && k <= 64, "gemm_set_k_flush_head: out of range");
+  g_k_flush_head = k;
   return NEFII_OK;
 }
 
@@ -781,10 +922,8 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   NEFII_CHECK_ARG(p.epi.n_valid > 0 && p.epi.n_valid <= p.n_pad, "gemm_split_bf16: n_valid out of range");
   NEFII_CHECK_ARG(p.epi.n_last <= kMaxLast, "gemm_split_bf16: fused output layer supports at most %d outputs", kMaxLast);
   if (p.rows_cap <= 0) return NEFII_OK;
-  // cluster size: 4 when there are enough row tiles to keep every SM busy anyway, else 2, else 1
   const int m_tiles = ceil_div(p.rows_cap, BM);
-  int cl = 1;
-  (void)g_cluster_pref;   // TMA-multicast clusters measured slower (profiles/r1_gemm_ablation.md); persistent kernel is CL = 1
+  const int cl = (g_cluster_pref == 2 && m_tiles >= 2) ? 2 : 1;   // CTA pairs need two row tiles to work on
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if ((rc = make_map(&ma_hi, p.a_hi, p.rows_cap, p.a_ld, p.k_pad, BM))) return rc;
@@ -792,17 +931,26 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   if ((rc = make_map(&mb_hi, p.b_hi, p.n_pad, p.b_ld, p.k_pad, BN / cl))) return rc;
   if ((rc = make_map(&mb_lo, p.b_lo, p.n_pad, p.b_ld, p.k_pad, BN / cl))) return rc;
   const int n_chunks = ceil_div(p.epi.dst_zero_to > p.epi.n_valid ? p.epi.dst_zero_to : p.epi.n_valid, BN);
+  // plain hidden layers (the kernel's fast_layer): the output planes as tensors for the epilogue's bulk stores
+  CUtensorMap md_hi = ma_hi, md_lo = ma_lo;
+  int store_tma = 0;
+  if (g_store_tma && p.epi.mode == 0 && p.epi.w_last == nullptr && p.epi.bias != nullptr && p.epi.dst.hi != nullptr && p.epi.dst_f32 == nullptr &&
+      (p.epi.dst_col0 & 7) == 0 && (p.epi.dst.ld & 7) == 0 && n_chunks * BN <= kBiasSmemFloats && p.epi.dst_ncols >= 32) {
+    if ((rc = make_store_map(&md_hi, p.epi.dst.hi + p.epi.dst_col0, p.rows_cap, p.epi.dst.ld, p.epi.dst_ncols))) return rc;
+    if ((rc = make_store_map(&md_lo, p.epi.dst.lo + p.epi.dst_col0, p.rows_cap, p.epi.dst.ld, p.epi.dst_ncols))) return rc;
+    store_tma = 1;
+  }
   NEFII_CHECK_ARG(n_chunks * BN <= p.n_pad, "gemm_split_bf16: dst_zero_to beyond n_pad");
   NEFII_CHECK_ARG(p.epi.mode == 0 || p.epi.sav_hi == nullptr || p.epi.sav_ld >= n_chunks * BN || p.epi.sav_ncols % 32 == 0,
                   "gemm_split_bf16: saved-activation rows must cover whole 32-column groups");
   int grid = ceil_div(m_tiles, cl) * cl;
-  if (grid > kNumSMs) grid = kNumSMs;   // persistent CTAs: one per SM, looping over row tiles
-  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const int*, int, int, int, int, long long, int, int, GemmEpilogue);
+  if (grid > kNumSMs) grid = kNumSMs / cl * cl;   // persistent CTAs: one per SM, looping over row tiles
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, int, const int*, int, int, int, int, long long, int, int, GemmEpilogue);
   KernelFn fn = nullptr;
   const bool fuse = p.epi.mode == 0 && p.epi.w_last != nullptr;
   NEFII_CHECK_ARG(!fuse || (p.epi.dst_last != nullptr && p.epi.n_last >= 1), "gemm_split_bf16: fused output layer needs dst_last");
   NEFII_CHECK_ARG(p.epi.seed.hi == nullptr || fuse, "gemm_split_bf16: seed planes need the fused output layer");
-  const int key = ((cl == 4) ? 24 : (cl == 2) ? 12 : 0) + (fuse ? 8 : 0) + p.epi.mode * 4 + p.epi.act;
+  const int key = ((cl == 2) ? 12 : 0) + (fuse ? 8 : 0) + p.epi.mode * 4 + p.epi.act;
 #define NEFII_GEMM_CASES(CLV, BASE)                                                              \
     case BASE + 0: fn = gemm_split_bf16_kernel<0, ACT_NONE, false, CLV>; break;                  \
     case BASE + 1: fn = gemm_split_bf16_kernel<0, ACT_SOFTPLUS100, false, CLV>; break;           \
@@ -818,6 +966,7 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
     case BASE + 11: fn = gemm_split_bf16_kernel<0, ACT_ELU, true, CLV>; break;
   switch (key) {
     NEFII_GEMM_CASES(1, 0)
+    NEFII_GEMM_CASES(2, 12)
     default: return set_error(NEFII_ERR_ARG, "gemm_split_bf16: bad mode/act (%d/%d)", p.epi.mode, p.epi.act);
   }
 #undef NEFII_GEMM_CASES
@@ -859,8 +1008,8 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
     attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NEFII_CUDA(cudaLaunchKernelEx(&cfg, fn, ma_hi, ma_lo, mb_hi, mb_lo, p.count, p.rows_cap, k_blocks, n_chunks, kb_per,
-                                  (long long)p.f32_split_stride, g_debug, g_k_flush, p.epi));
+    NEFII_CUDA(cudaLaunchKernelEx(&cfg, fn, ma_hi, ma_lo, mb_hi, mb_lo, md_hi, md_lo, store_tma, p.count, p.rows_cap, k_blocks, n_chunks, kb_per,
+                                  (long long)p.f32_split_stride, g_debug, g_k_flush | (g_k_flush_head << 8), p.epi));
   }
   if (rec) NEFII_CUDA(cudaEventRecord(rec->b, stream));
   NEFII_LAUNCH_CHECK();

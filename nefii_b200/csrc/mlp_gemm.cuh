@@ -65,6 +65,7 @@ int gemm_set_debug(int mask);
 // accuracy / overlap knob: number of 64-wide K blocks accumulated inside TMEM (truncating adder) before the partial sum is
 // added to the fp32 register accumulators (round to nearest).  1 = most accurate, 2 = default, >= K/64 = everything in TMEM.
 int gemm_set_k_flush(int k);
+int gemm_set_k_flush_head(int k);
 int gemm_profile_enable(int on);
 int gemm_profile_fetch(double* out3);
 

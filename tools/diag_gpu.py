@@ -145,16 +145,17 @@ def diag_kflush():
     net.set_weights([t.to(dev) for t in params.W], [t.to(dev) for t in params.b])
     pts = torch.rand(131072, 3, device=dev) * 1.8 - 0.9
     r64 = mlp.sdf_forward(params.to(dev, torch.float64), pts.double())[:, 0]
-    for kf in (1, 2, 4, 8):
+    for kf, head in ((1, 1), (2, 2), (2, 3), (1, 3), (2, 4), (4, 4), (8, 8)):
         _lib.check(_lib.raw().nefii_gemm_set_k_flush(kf))
+        _lib.check(_lib.raw().nefii_gemm_set_k_flush_head(head))
         ms = ev_time(lambda: ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n), iters=10)
         out = torch.zeros(4096, 256, device=dev)
         ops.gemm_split_bf16(ap, bp, 512, 256, dst_f32=out, f32_begin=0, f32_end=256)
         err = (out.double() - refp) / refp
         sdf, _, _ = net.eval(pts)
         e = sdf.double() - r64
-        print("KFLUSH %d: %.4f ms %.1f TFLOP/s alg | all-positive K=512 bias %.2f ulp | SDF err mean %.2e (signed %.2e) max %.2e" % (
-            kf, ms, 2.0 * rows * n * k / ms / 1e9, err.mean().item() / 2 ** -24, e.abs().mean().item(), e.mean().item(), e.abs().max().item()))
+        print("KFLUSH %d head %d: %.4f ms %.1f TFLOP/s alg | all-positive K=512 bias %.2f ulp | SDF err mean %.2e (signed %.2e) max %.2e" % (
+            kf, head, ms, 2.0 * rows * n * k / ms / 1e9, err.mean().item() / 2 ** -24, e.abs().mean().item(), e.mean().item(), e.abs().max().item()))
     _lib.check(_lib.raw().nefii_gemm_set_k_flush(2))
 
 
@@ -171,7 +172,7 @@ def diag_ablate():
     names = {0: "full", 1: "no final math/stores", 8: "no flush", 9: "no flush, no final", 2: "no TMA", 4: "no MMA", 6: "no TMA, no MMA",
              11: "no TMA, no flush, no final (MMA only)", 13: "TMA only (no MMA, flush, final)", 15: "barriers only", 3: "no TMA no final", 5: "no MMA no final",
              16: "final math only (no staging, no stores)", 32: "no global stores", 22: "epilogue alone, math only", 38: "epilogue alone, no global stores"}
-    for cl in (1,):
+    for cl in (1, 2):
         _lib.check(_lib.raw().nefii_gemm_set_cluster(cl))
         for mask in (0, 1, 8, 9, 2, 3, 4, 5, 6, 11, 13, 15, 16, 32, 22, 38):
             _lib.check(_lib.raw().nefii_gemm_set_debug(mask))
