@@ -52,7 +52,8 @@ constexpr int kBiasSmemFloats = 512;      // the bias of layers up to 512 output
 // fused output layer's row partials (FUSE kernels never take the staged path).  The ring must start 1024-byte aligned
 // (SWIZZLE_128B atoms); dynamic shared memory starts at the CTA window's base, the kernel traps if that ever changes.
 constexpr size_t kTailBytes = (size_t)kEpiWarps * kStageOutBytes + kBiasSmemFloats * sizeof(float);
-static_assert(kTailBytes >= 2 * BM * kMaxLast * sizeof(float), "fused-layer partials alias the staging area");
+static_assert(kTailBytes >= 2 * BM * kMaxLast * sizeof(float) + (1 + kMaxLast) * kBiasSmemFloats * sizeof(float),
+              "fused-layer partials, bias and output weights alias the staging area");
 constexpr int kBarBytes = 512;            // barriers + TMEM slot; keeps the staging tiles 512-byte aligned (SWIZZLE_64B pattern)
 constexpr size_t kSmemBytes = (size_t)kRingBytes + kBarBytes + kTailBytes;
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
@@ -396,6 +397,27 @@ __device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bia
   }
 }
 
+// Fast path of the fused output layer when nothing but the n_last dot products leaves the tile (the SDF value of the
+// tracer's evaluations): activation and FMA only, bias and output weights read as broadcast 16-byte loads from the copies
+// staged in shared memory (s_w: [kMaxLast][kBiasSmemFloats]).
+template <int ACT>
+__device__ __forceinline__ void finish_span_fused_fast(const float* acc, const float4* s_bias4, const float4* s_w4, int n_span0,
+                                                       int n_last, float* part) {
+#pragma unroll
+  for (int g = 0; g < kColsPerWarp / 4; ++g) {
+    const float4 b = s_bias4[n_span0 / 4 + g];
+    const float h0 = act_fwd<ACT>(acc[4 * g + 0] + b.x), h1 = act_fwd<ACT>(acc[4 * g + 1] + b.y);
+    const float h2 = act_fwd<ACT>(acc[4 * g + 2] + b.z), h3 = act_fwd<ACT>(acc[4 * g + 3] + b.w);
+#pragma unroll
+    for (int q = 0; q < kMaxLast; ++q) {
+      if (q < n_last) {
+        const float4 w = s_w4[q * (kBiasSmemFloats / 4) + n_span0 / 4 + g];
+        part[q] = fmaf(h3, w.w, fmaf(h2, w.z, fmaf(h1, w.y, fmaf(h0, w.x, part[q]))));
+      }
+    }
+  }
+}
+
 // Final per-tile math on the fp32 sums of one 32-column group held in registers (v[0..31]).
 template <int MODE, int ACT, bool FUSE>
 __device__ __forceinline__ void finish_group(const GemmEpilogue& epi, float* v, int n0, long long row, bool row_ok,
@@ -675,6 +697,19 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       for (int i = threadIdx.x; i < n_chunks * BN; i += kEpiWarps * 32) s_bias[i] = i < epi.n_valid ? __ldg(epi.bias + i) : 0.f;
       asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
     }
+    // fused output layer with only its dot products as output: bias and output weights staged behind the row partials
+    float* s_fbias = reinterpret_cast<float*>(tail + 2 * BM * kMaxLast * sizeof(float));
+    float* s_fw = s_fbias + kBiasSmemFloats;
+    const bool fast_fused = MODE == 0 && FUSE && epi.bias != nullptr && epi.dst.hi == nullptr && epi.dst_f32 == nullptr &&
+                            epi.seed.hi == nullptr && n_chunks * BN <= kBiasSmemFloats;
+    if (fast_fused) {
+      for (int i = threadIdx.x; i < n_chunks * BN; i += kEpiWarps * 32) {
+        s_fbias[i] = i < epi.n_valid ? __ldg(epi.bias + i) : 0.f;
+        for (int q = 0; q < kMaxLast; ++q)
+          s_fw[q * kBiasSmemFloats + i] = (q < epi.n_last && i < epi.n_valid) ? __ldg(epi.w_last + (size_t)q * epi.w_last_ld + i) : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+    }
     FastStore fs;
     fs.sw_in = (lane >> 1) & 3;
     fs.st_in = stage_out + lane * 4;
@@ -738,6 +773,11 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           finish_span_fast<ACT, true>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg);
         else
           finish_span_fast<ACT, false>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg);
+        continue;
+      }
+      if (fast_fused && n_span0 + kColsPerWarp <= epi.n_valid) {
+        finish_span_fused_fast<ACT>(acc, reinterpret_cast<const float4*>(s_fbias), reinterpret_cast<const float4*>(s_fw), n_span0,
+                                    epi.n_last, part);
         continue;
       }
 #pragma unroll

@@ -19,32 +19,77 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// value j of the positional encoding of point p (embedder.py:22-36)
-__device__ __forceinline__ float pe_value(const float* p, int j) {
-  if (j < 3) return p[j];
-  const int k = (j - 3) / 6, r = (j - 3) % 6;
-  const float a = p[r % 3] * exp2f((float)k);
-  return r < 3 ? sinf(a) : cosf(a);
-}
+// Writes PE(x) * scale into plane columns [col0, col0 + d_pe) and zeros up to col0 + zero_to.
+// One lane per point: 3 x n_freqs sincosf calls give the whole encoding of a row (layout of embedder.py:22-36:
+// [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...], 3 components each); the warp's 32 rows are staged in shared memory and
+// written back with consecutive lanes on consecutive columns (16-byte stores when the destination allows it).
+constexpr int kEncWarps = 4;
+constexpr int kEncMaxWidth = 64;
+constexpr int kEncStride = kEncMaxWidth + 1;   // odd stride: conflict-free row-major writes by lane = row
 
-// writes PE(x) * scale into plane columns [col0, col0 + d_pe) and zeros up to col0 + zero_to
-__global__ void encode_kernel(const float* __restrict__ x, const int* __restrict__ count, int rows_cap, int d_pe,
-                              float scale, Planes dst, int col0, int zero_to) {
+__global__ void __launch_bounds__(kEncWarps * 32)
+encode_kernel(const float* __restrict__ x, const int* __restrict__ count, int rows_cap, int n_freqs, float scale, Planes dst,
+              int col0, int zero_to) {
+  __shared__ float s_v[kEncWarps][32 * kEncStride];
   int limit = rows_cap;
   if (count) limit = min(limit, *count);
+  const int d_pe = 3 + 6 * n_freqs;
   const int width = max(d_pe, zero_to);
-  const long long total = (long long)limit * width;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int row = (int)(i / width), j = (int)(i % width);
-    float v = 0.f;
-    if (j < d_pe) {
-      float p[3] = {x[(size_t)row * 3 + 0], x[(size_t)row * 3 + 1], x[(size_t)row * 3 + 2]};
-      v = pe_value(p, j) * scale;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sv = s_v[warp];
+  const bool vec = ((col0 | dst.ld | width) & 7) == 0;
+  const int n_groups = (limit + 31) / 32;
+  for (int grp = blockIdx.x * kEncWarps + warp; grp < n_groups; grp += gridDim.x * kEncWarps) {
+    const int row0 = grp * 32;
+    const int row = row0 + lane;
+    if (row < limit) {
+      const float p[3] = {x[(size_t)row * 3 + 0], x[(size_t)row * 3 + 1], x[(size_t)row * 3 + 2]};
+      float* o = sv + lane * kEncStride;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[c] = p[c] * scale;
+      for (int k = 0; k < n_freqs; ++k) {
+        const float f = exp2f((float)k);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float sn, cs;
+          sincosf(p[c] * f, &sn, &cs);
+          o[3 + 6 * k + c] = sn * scale;
+          o[6 + 6 * k + c] = cs * scale;
+        }
+      }
+      for (int j = d_pe; j < width; ++j) o[j] = 0.f;
     }
-    __nv_bfloat16 h, l;
-    split2(v, h, l);
-    dst.hi[(size_t)row * dst.ld + col0 + j] = h;
-    dst.lo[(size_t)row * dst.ld + col0 + j] = l;
+    __syncwarp();
+    const int n_rows = min(32, limit - row0);
+    if (vec) {
+      const int per_row = width / 8;
+      for (int e = lane; e < n_rows * per_row; e += 32) {
+        const int r = e / per_row, c0 = (e % per_row) * 8;
+        const float* v = sv + r * kEncStride + c0;
+        uint32_t wh[4], wl[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+          const float2 hf = __bfloat1622float2(h2);
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * q] - hf.x, v[2 * q + 1] - hf.y);
+          wh[q] = *reinterpret_cast<const uint32_t*>(&h2);
+          wl[q] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        const size_t off = (size_t)(row0 + r) * dst.ld + col0 + c0;
+        *reinterpret_cast<uint4*>(dst.hi + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+        *reinterpret_cast<uint4*>(dst.lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      }
+    } else {
+      for (int e = lane; e < n_rows * width; e += 32) {
+        const int r = e / width, j = e % width;
+        __nv_bfloat16 h, l;
+        split2(sv[r * kEncStride + j], h, l);
+        const size_t off = (size_t)(row0 + r) * dst.ld + col0 + j;
+        dst.hi[off] = h;
+        dst.lo[off] = l;
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -226,8 +271,9 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
   auto in_of = [&](int l) -> Planes& { return with_grad ? act[l - 1] : act[(l - 1) & 1]; };
 
   const int ew_blocks = kNumSMs * 8;
+  const int enc_blocks = kNumSMs * 6;
   int rc;
-  encode_kernel<<<ew_blocks, 256, 0, stream>>>(x, count, rows_cap, s.d_pe, 1.f, in0, 0, 64);
+  encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, 1.f, in0, 0, 64);
   NEFII_LAUNCH_CHECK();
 
   // ---------------------------------------------------------------- forward
@@ -236,7 +282,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
   for (int l = 0; l < H; ++l) {
     if (l + 1 == skip) {
       // the skip layer's input = [h / sqrt2 | PE / sqrt2]; its PE columns are free from now on
-      encode_kernel<<<ew_blocks, 256, 0, stream>>>(x, count, rows_cap, s.d_pe, kInvSqrt2, in_of(skip), W - s.d_pe, 0);
+      encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, kInvSqrt2, in_of(skip), W - s.d_pe, 0);
       NEFII_LAUNCH_CHECK();
     }
     GemmProblem g{};
