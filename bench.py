@@ -62,19 +62,28 @@ def make_batch(seed, num_pixels=NUM_PIXELS, num_rays=NUM_RAYS, img=IMG):
     return uv.contiguous(), object_mask, rgb
 
 
+LOSS_CONF = dict(idr_rgb_weight=1.0, sg_rgb_weight=1.0, eikonal_weight=0.1, mask_weight=100.0, alpha=50.0, normalsmooth_weight=1.0,
+                 r_patch=1.0, loss_type='L1', env_loss_type='L2', background_rgb_weight=1.0)     # reference confs_sg/conf.conf:24-35
+_crit = None
+
+
 def idr_loss(out, rgb_gt):
-    """The terms of the reference's IDRLoss that are live in step 2 (model/loss.py:162-186,255-264,278-320 with
-    conf.conf's weights): masked L1 on idr/sg rgb, background L2, 2x2 normal-smoothness.  Stays PyTorch."""
-    net, obj = out['network_object_mask'], out['object_mask']
-    m = net & obj
-    zero = out['sg_rgb_values'].sum() * 0
-    idr = (out['idr_rgb_values'][m] - rgb_gt[m]).abs().mean() if bool(m.any()) else zero
-    sg = (out['sg_rgb_values'][m] - rgb_gt[m]).abs().mean() if bool(m.any()) else zero
-    bg_m = (~net) & (~obj)
-    bg = ((out['sg_rgb_values'][bg_m] - rgb_gt[bg_m]) ** 2).mean() if bool(bg_m.any()) else zero
-    pm = m.reshape(-1, 4).all(-1)
-    ns = torch.var(out['normal_values'].view(-1, 4, 3), dim=1)[pm].mean() if bool(pm.any()) else zero
-    return 1.0 * idr + 1.0 * sg + 1.0 * bg + 1.0 * ns
+    """The reference's IDRLoss with conf.conf's weights (model/loss.py:278-320) through the fused CUDA loss
+    (nefii_b200/model/loss.py: one launch forward, one backward, no host round trips)."""
+    global _crit
+    if _crit is None:
+        from nefii_b200.model.loss import IDRLoss
+        _crit = IDRLoss(**LOSS_CONF)
+    return _crit(out, {'rgb': rgb_gt})['loss']
+
+
+def idr_loss_cpu(out, rgb_gt):
+    """The same loss for the CPU arm: the oracle's restatement of IDRLoss (plain torch ops, like the reference)."""
+    from oracle import loss as oloss
+    terms = oloss.idr_loss_terms(out['idr_rgb_values'], out['sg_rgb_values'], rgb_gt, out['normal_values'], out['sdf_output'],
+                                 out['network_object_mask'], out['object_mask'], alpha=LOSS_CONF['alpha'], r_patch=1,
+                                 loss_type='L1', env_loss_type='L2')
+    return oloss.idr_loss(terms)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -306,12 +315,16 @@ def run_ours(args):
         "tensor_issue_frac": 3 * achieved_tf / peak_tf if peak_tf else None,
         "flops_per_launch_avg": gemm_flops / max(gemm_launches, 1), "launches_per_step": gemm_launches,
         "kernel_share_of_step": gemm_ms / step_ms if step_ms > 0 else None,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of a 131072-row hidden-layer launch
+        # (profiles/r1_gemm_ncu_final.md): 500.5 MB = 3818 B/row against 4096 B/row algorithmic (hi+lo bf16 planes in and out);
+        # scaled to this run's average launch so that it is per launch like `achieved`
+        "traffic": NCU_DRAM_BYTES_PER_ROW * (gemm_flops / max(gemm_launches, 1)) / (2.0 * 512 * 512),
+        "traffic_source": "ncu dram bytes per row of the hidden-layer GEMM (3818 B/row, algorithmic 4096 B/row) x rows of the average launch",
     }
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_port_throughput(px=128, rays=4, steps=1, warmup=0)
+        cpu = cpu_port_throughput(px=1024, rays=8, steps=1, warmup=0)     # ~16k rays: 10-30 s of host time
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -339,6 +352,9 @@ def run_ours(args):
 # --------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle port) on the host cores
 # --------------------------------------------------------------------------------------------------------------
+NCU_DRAM_BYTES_PER_ROW = 3818.0
+
+
 def cpu_port_throughput(px, rays, steps, warmup):
     """Times oracle/pipeline.py (the restated reference, plain torch CPU ops) on a bounded sample of the same
     workload: `px` pixels x `rays` rays, forward + loss + backward, all host threads."""
@@ -358,7 +374,7 @@ def cpu_port_throughput(px, rays, steps, warmup):
         vecs = [torch.rand(100, generator=g) for _ in range(2)]
         t0 = time.perf_counter()
         out = pipeline.forward_with_uv(om, uv, pose, K, obj, lambda n: U[:n], True, vecs[0], vecs[1])
-        loss = idr_loss(out, rgb)
+        loss = idr_loss_cpu(out, rgb)
         loss.backward()
         dt = time.perf_counter() - t0
         if i >= warmup:
@@ -375,8 +391,8 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.steps + args.warmup
-    px = 64 if n > 6 else 128
-    cpu = cpu_port_throughput(px=px, rays=4, steps=args.steps, warmup=args.warmup)
+    px = 256 if n > 6 else 512           # ~4k / ~8k rays per step: the whole run stays within a few minutes
+    cpu = cpu_port_throughput(px=px, rays=8, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "rays/s", "n_gpus": env_int("WORLD_SIZE", 1),
         "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -222,6 +222,27 @@ int nefii_last_layer_bwd(void* stream, int act, int rows, int width, int n_out, 
 int nefii_reduce_splits(void* stream, const float* partial, int n_splits, int64_t stride, int rows, int ld_src, int cols,
                         float* out);
 
+
+/* ---- IDRLoss, the step right after the rendering path (reference code/model/loss.py:122-320) -----------------
+ * One launch for the five terms live in the step-2 recipe, means formed on the device (an empty mask yields 0 like the
+ * reference's `mask.sum() == 0` early-outs, without their host round trips):
+ *   terms[0] idr_rgb_loss, [1] sg_rgb_loss   image loss over net & obj                       (loss.py:162-174)
+ *   terms[2] background_rgb_loss             env image loss over ~net & ~obj                 (loss.py:176-186)
+ *   terms[3] mask_loss                       (1/alpha) BCE(-alpha sdf, obj) over ~(net&obj), / n   (loss.py:228-235)
+ *   terms[4] normalsmooth_loss               mean unbiased variance of the normals of fully masked patches of `patch`
+ *                                            consecutive pixels (4 r_patch^2; 0 or 1 = off)  (loss.py:255-264)
+ *   terms[5..7] the three mask counts (pixels in net&obj, pixels in ~net&~obj, whole patches) -- inputs of the backward.
+ * loss_type / env_loss_type: 0 L1, 1 L2 (MSE), 2 smooth L1 (image loss only).  All pointers device; masks uint8 [n];
+ * rgb / normal [n,3]; sdf [n]; terms [8]. */
+int nefii_idr_loss_fwd(void* stream, int n, int patch, const float* idr_rgb, const float* sg_rgb, const float* rgb_gt,
+                       const float* normal, const float* sdf_output, const uint8_t* net_mask, const uint8_t* obj_mask,
+                       int loss_type, int env_loss_type, float alpha, float* terms);
+/* gradients of sum_k g_terms[k] * terms[k] (k < 5, device) w.r.t. the inputs; every output pointer may be null */
+int nefii_idr_loss_bwd(void* stream, int n, int patch, const float* idr_rgb, const float* sg_rgb, const float* rgb_gt,
+                       const float* normal, const float* sdf_output, const uint8_t* net_mask, const uint8_t* obj_mask,
+                       int loss_type, int env_loss_type, float alpha, const float* terms, const float* g_terms,
+                       float* g_idr_rgb, float* g_sg_rgb, float* g_normal, float* g_sdf_output);
+
 #ifdef __cplusplus
 }
 #endif

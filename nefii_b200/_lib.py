@@ -47,6 +47,8 @@ SIGNATURES = {
     "nefii_sdf_workspace_bytes": [c_void_p, c_int, c_int],
     "nefii_sdf_eval": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p],
     "nefii_split_to_planes": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int],
+    "nefii_idr_loss_fwd": [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_int, c_int, c_float, c_void_p],
+    "nefii_idr_loss_bwd": [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_int, c_int, c_float] + [c_void_p] * 6,
 }
 
 

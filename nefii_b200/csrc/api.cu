@@ -7,6 +7,7 @@
 #include "mlp_gemm.cuh"
 #include "sdf_mlp.cuh"
 #include "tracer.cuh"
+#include "loss.cuh"
 
 namespace nefii {
 
@@ -215,6 +216,20 @@ int nefii_sg_render_bwd(void* stream, int n_rays, int n_sg, int n_mat, const flo
   return nefii::sg_render_bwd((cudaStream_t)stream, n_rays, n_sg, n_mat, lgt_sgs, specular, roughness, albedo, normal, view,
                               out_specular, out_diffuse, g_rgb, g_specular, g_diffuse, g_lgt_acc, g_roughness, g_specular_refl,
                               g_albedo);
+}
+
+int nefii_idr_loss_fwd(void* stream, int n, int patch, const float* idr_rgb, const float* sg_rgb, const float* rgb_gt,
+                       const float* normal, const float* sdf_output, const uint8_t* net_mask, const uint8_t* obj_mask,
+                       int loss_type, int env_loss_type, float alpha, float* terms) {
+  return nefii::idr_loss_fwd((cudaStream_t)stream, n, patch, idr_rgb, sg_rgb, rgb_gt, normal, sdf_output, net_mask, obj_mask,
+                             loss_type, env_loss_type, alpha, terms);
+}
+int nefii_idr_loss_bwd(void* stream, int n, int patch, const float* idr_rgb, const float* sg_rgb, const float* rgb_gt,
+                       const float* normal, const float* sdf_output, const uint8_t* net_mask, const uint8_t* obj_mask,
+                       int loss_type, int env_loss_type, float alpha, const float* terms, const float* g_terms,
+                       float* g_idr_rgb, float* g_sg_rgb, float* g_normal, float* g_sdf_output) {
+  return nefii::idr_loss_bwd((cudaStream_t)stream, n, patch, idr_rgb, sg_rgb, rgb_gt, normal, sdf_output, net_mask, obj_mask,
+                             loss_type, env_loss_type, alpha, terms, g_terms, g_idr_rgb, g_sg_rgb, g_normal, g_sdf_output);
 }
 
 }  // extern "C"

@@ -55,6 +55,45 @@ def main():
     print("wrote", sorted(os.listdir(OUT)))
 
 
+def reference_idr_loss(inp, **conf):
+    """The REAL model.loss.IDRLoss on oracle.loss.loss_inputs() -> (output dict, grads of idr/sg/normal/sdf)."""
+    import contextlib
+    import io
+    from model.loss import IDRLoss
+    with contextlib.redirect_stdout(io.StringIO()):
+        crit = IDRLoss(**conf)
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in ("idr_rgb", "sg_rgb", "normal", "sdf_output")}
+    outs = {'idr_rgb_values': leaves['idr_rgb'], 'sg_rgb_values': leaves['sg_rgb'], 'normal_values': leaves['normal'],
+            'sdf_output': leaves['sdf_output'], 'network_object_mask': inp['net_mask'], 'object_mask': inp['obj_mask'],
+            'grad_theta': None, 'sg_roughness_values': torch.zeros(inp['idr_rgb'].shape[0], 1),
+            'sg_specular_rgb_values': torch.zeros_like(inp['sg_rgb'])}
+    res = crit(outs, {'rgb': inp['rgb_gt'].unsqueeze(0)})
+    res['loss'].backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    return res, grads
+
+
+LOSS_CONF = dict(idr_rgb_weight=1.0, sg_rgb_weight=1.0, eikonal_weight=0.1, mask_weight=100.0, alpha=50.0, normalsmooth_weight=1.0,
+                 r_patch=1.0, loss_type='L1', env_loss_type='L2', background_rgb_weight=1.0)     # confs_sg/conf.conf:24-35
+
+
+def golden_loss():
+    """IDRLoss of the step-2 recipe (conf.conf loss{}) and an L2 / smooth-L1 variant, outputs and input gradients."""
+    from oracle import loss as oloss
+    out = {}
+    for tag, seed, conf in (("conf", 0, LOSS_CONF), ("l2", 1, dict(LOSS_CONF, loss_type='L2', env_loss_type='L1')),
+                            ("smooth", 2, dict(LOSS_CONF, loss_type='L1_smooth'))):
+        inp = oloss.loss_inputs(n_pixels=512, seed=seed)
+        res, grads = reference_idr_loss(inp, **conf)
+        for k, v in inp.items():
+            out["%s_in_%s" % (tag, k)] = v.numpy()
+        for k in ('loss', 'idr_rgb_loss', 'sg_rgb_loss', 'mask_loss', 'normalsmooth_loss', 'background_rgb_loss'):
+            out["%s_%s" % (tag, k)] = res[k].detach().numpy()
+        for k, v in grads.items():
+            out["%s_grad_%s" % (tag, k)] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "idr_loss.npz"), **out)
+
+
 def golden_tracer():
     """The REAL RayTracing module on the analytic robot scene (eval + train) and on the seeded SDF MLP (eval)."""
     import contextlib
@@ -147,7 +186,7 @@ def golden_mis_and_pipeline():
     np.savez_compressed(os.path.join(OUT, "pipeline_small.npz"), **out)
 
 
-EXTRA = [golden_tracer, golden_mis_and_pipeline]
+EXTRA = [golden_tracer, golden_mis_and_pipeline, golden_loss]
 
 if __name__ == "__main__":
     main()

@@ -70,7 +70,8 @@ def install():
         return
     if not available():
         raise RuntimeError("reference checkout not found at %s" % REF_ROOT)
-    for name in ("imageio", "imageio.plugins", "imageio.plugins.freeimage", "skimage"):
+    # kornia: imported by model/loss.py for the SSIM term only (weight 0 in the step-2 recipe, never called here)
+    for name in ("imageio", "imageio.plugins", "imageio.plugins.freeimage", "skimage", "kornia"):
         if name not in sys.modules:
             sys.modules[name] = types.ModuleType(name)
     sys.modules["imageio"].plugins = sys.modules["imageio.plugins"]
