@@ -281,21 +281,25 @@ def run_ours(args):
     frame_ms = None
     try:
         model.eval()
-        ii, jj = torch.meshgrid(torch.arange(IMG, device=dev).float(), torch.arange(IMG, device=dev).float(), indexing="xy")
-        uv_all = (torch.stack([ii, jj], -1).reshape(1, -1, 2) + 0.5)[:, rank::world]       # pixels strided over ranks
-        obj_all = torch.ones(1, uv_all.shape[1], dtype=torch.bool, device=dev)
-        chunk = 1 << 18                                                                       # memory_capacity_level 18
+        from nefii_b200.utils import general
+        ii, jj = torch.meshgrid(torch.arange(IMG).float(), torch.arange(IMG).float(), indexing="xy")
+        uv_host = (torch.stack([ii, jj], -1).reshape(1, -1, 2) + 0.5).pin_memory()
+        obj_all = torch.ones(1, IMG * IMG, dtype=torch.bool, device=dev)
+
         def render_frame():
-            with torch.no_grad():
-                for s0 in range(0, uv_all.shape[1], chunk):
-                    model({'uv': uv_all[:, s0:s0 + chunk], 'object_mask': obj_all[:, s0:s0 + chunk], 'pose': pose, 'intrinsics': K})
+            # scripts/render.py:283-360: uv upload, 2**18-ray chunks dealt round robin to the ranks, the 11 output planes
+            # gathered onto rank 0 (one fixed-shape NCCL gather)
+            uv_all = uv_host.to(dev, non_blocking=True)
+            return general.render_frame(model, {'uv': uv_all, 'object_mask': obj_all, 'pose': pose, 'intrinsics': K}, IMG * IMG,
+                                        num_rays=1, memory_capacity_level=18)
         render_frame()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        render_frame()
+        frame = render_frame()
         f1.record()
         barrier()
+        del frame
         frame_ms = max_over_ranks(f0.elapsed_time(f1))
     finally:
         model.train()
