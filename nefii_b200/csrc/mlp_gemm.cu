@@ -7,11 +7,12 @@
 // per K step recover ~16 mantissa bits per operand (measured against the fp32 oracle in
 // tests/test_gemm.py and reported in DESIGN.md).
 //
-// One CTA owns a 128-row tile of points and loops over the output columns in chunks of 256:
-//   warp 0      : TMA producer (A/B hi+lo tiles, 128B swizzle, 2-stage mbarrier ring)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (2 x 256-column accumulators)
-//   warps 4..11 : epilogue (tcgen05.ld -> bias/activation/derivative -> bf16 planes / fp32 / fused
-//                 output layer), overlapped with the MMAs of the next column chunk.
+// Persistent CTAs (one per SM) loop over 128-row tiles of points and, per tile, over the output columns in chunks of 256:
+//   warps 0..7  : epilogue (tcgen05.ld of every partial sum into fp32 registers -> bias / activation / derivative ->
+//                 bf16 planes by bulk tensor store / fp32 / fused output layer), overlapped with the MMAs of the next chunk
+//   warp 8      : TMA producer (A/B hi+lo tiles, 128B swizzle, mbarrier ring)
+//   warp 9      : TMEM allocator + single-thread tcgen05.mma issuer (2 x 256-column partial-sum buffers)
+// Two instantiations: single CTA (cta_group::1, M = 128) and CTA pairs (cta_group::2, M = 256 over two SMs).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdlib>
@@ -159,20 +160,6 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -183,17 +170,6 @@ __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row atoms of 1024 B).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;

@@ -270,7 +270,6 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
   // input planes of hidden layer l (l >= 1)
   auto in_of = [&](int l) -> Planes& { return with_grad ? act[l - 1] : act[(l - 1) & 1]; };
 
-  const int ew_blocks = kNumSMs * 8;
   const int enc_blocks = kNumSMs * 6;
   int rc;
   encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, 1.f, in0, 0, 64);
