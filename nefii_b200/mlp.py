@@ -56,9 +56,25 @@ def segment_width(segments):
     return sum((3 + 6 * f) if f >= 0 else t.shape[-1] for t, f in segments)
 
 
+def encode_segments(segments):
+    """fp32 [N, d_in] of what assemble_input writes as planes: per segment the raw tensor or its positional encoding
+    [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...] (reference embedder.py:22-36)."""
+    cols = []
+    for t, f in segments:
+        t = t.detach().float()
+        cols.append(t)
+        for k in range(max(f, 0)):
+            cols += [torch.sin(t * float(2 ** k)), torch.cos(t * float(2 ** k))]
+    return torch.cat(cols, dim=-1)
+
+
 class _DenseMlp(torch.autograd.Function):
+    """skip = 0: plain stack.  skip = s > 0: the input of hidden layer s is cat([h_{s-1}, input]) * skip_scale
+    (ImplicitNetwork.forward, implicit_differentiable_renderer.py:97-101: `x = torch.cat([x, input], 1) / np.sqrt(2)`);
+    layer s-1 then has width - d_in outputs."""
+
     @staticmethod
-    def forward(ctx, act, seg_freqs, n_hidden, *tensors):
+    def forward(ctx, act, seg_freqs, n_hidden, skip, skip_scale, want_hidden, *tensors):
         n_seg = len(seg_freqs)
         seg_src = tensors[:n_seg]
         params = tensors[n_seg:]
@@ -74,10 +90,12 @@ class _DenseMlp(torch.autograd.Function):
         need_grad = any(p.requires_grad for p in params)
         y = torch.empty(n, n_out, device=dev, dtype=torch.float32)
         ctx.n_seg = n_seg
+        hidden = torch.empty(n if want_hidden else 0, Ws[-1].shape[1], device=dev, dtype=torch.float32)
+        ctx.mark_non_differentiable(hidden)
         if n == 0:
             ctx.empty = True
             ctx.shapes = [p.shape for p in params]
-            return y
+            return y, hidden
         k0 = ops.round_up(d_in, 64)
         in0, _keep = assemble_input(segments, k0)
         w_last = _lib.f32c(Ws[-1])
@@ -92,12 +110,22 @@ class _DenseMlp(torch.autograd.Function):
             packed.append(W)
             bias = _lib.f32c(bs[l])
             a = acts[-1]
-            if l < n_hidden - 1:
+            if skip and l == skip - 1:
+                # [h * scale | input * scale | 0]: the GEMM writes the first out_dim columns, the encoding goes next to them
+                assert l < n_hidden - 1
+                wide = ops.round_up(out_dim + d_in, 64)
+                dst = (torch.zeros(n, wide, device=dev, dtype=torch.bfloat16), torch.zeros(n, wide, device=dev, dtype=torch.bfloat16))
+                enc = encode_segments(segments) * skip_scale
+                enc_hi = enc.to(torch.bfloat16)
+                dst[0][:, out_dim:out_dim + d_in] = enc_hi
+                dst[1][:, out_dim:out_dim + d_in] = (enc - enc_hi.float()).to(torch.bfloat16)
+                ops.gemm_split_bf16(a, wp, k_pad, out_dim, act=act, bias=bias, out_scale=skip_scale, dst=dst, dst_ncols=out_dim)
+            elif l < n_hidden - 1:
                 dst = _planes(n, ops.round_up(out_dim, 64), dev)
                 ops.gemm_split_bf16(a, wp, k_pad, out_dim, act=act, bias=bias, dst=dst, dst_ncols=out_dim,
                                     dst_zero_to=ops.round_up(out_dim, 64))
             else:
-                dst = _planes(n, ops.round_up(out_dim, 64), dev) if need_grad else None
+                dst = _planes(n, ops.round_up(out_dim, 64), dev) if (need_grad or want_hidden) else None
                 ops.gemm_split_bf16(a, wp, k_pad, out_dim, act=act, bias=bias, dst=dst, dst_ncols=out_dim if dst else 0,
                                     dst_zero_to=ops.round_up(out_dim, 64) if dst else 0,
                                     w_last=w_last, b_last=b_last, dst_last=y)
@@ -109,15 +137,19 @@ class _DenseMlp(torch.autograd.Function):
         ctx.empty = False
         if need_grad:
             ctx.act, ctx.n_hidden, ctx.n = act, n_hidden, n
+            ctx.skip, ctx.skip_scale = skip, skip_scale
             ctx.acts = acts                # in0, h_1 .. h_L (planes)
             ctx.weights = packed           # effective fp32 hidden weights
             ctx.w_last = w_last
             ctx.needs = [p.requires_grad for p in params]
-        return y
+        if want_hidden:
+            # the last hidden activation (ImplicitNetwork's feature vector), rebuilt from its two bf16 planes; no gradient
+            torch.add(dst[0][:, :hidden.shape[1]].float(), dst[1][:, :hidden.shape[1]].float(), out=hidden)
+        return y, hidden
 
     @staticmethod
-    def backward(ctx, gy):
-        n_lead = 3
+    def backward(ctx, gy, _g_hidden=None):
+        n_lead = 6
         if ctx.empty:
             return (None,) * (n_lead + ctx.n_seg) + tuple(torch.zeros(s, device=gy.device) for s in ctx.shapes)
         act, L, n = ctx.act, ctx.n_hidden, ctx.n
@@ -156,9 +188,17 @@ class _DenseMlp(torch.autograd.Function):
             grads_w[l], grads_b[l] = gW, gb
             if l > 0:
                 wt = ops.split_to_planes(W, rows_pad=ops.round_up(in_dim, 256), cols_pad=ops.round_up(out_dim, 64), transpose=True)
-                G_prev = _planes(n, ops.round_up(in_dim, 64), dev)
-                ops.gemm_split_bf16(G, wt, ops.round_up(out_dim, 64), in_dim, mode=1, act=act, dst=G_prev, dst_ncols=in_dim,
-                                    dst_zero_to=ops.round_up(in_dim, 64), sav=h_prev, sav_ncols=in_dim)
+                if ctx.skip and l == ctx.skip:
+                    # only the h part of this layer's input carries on; it was stored scaled, and d(h * scale)/dh = scale
+                    prev_dim = ctx.weights[l - 1].shape[0]
+                    G_prev = _planes(n, ops.round_up(prev_dim, 64), dev)
+                    ops.gemm_split_bf16(G, wt, ops.round_up(out_dim, 64), prev_dim, mode=1, act=act, out_scale=ctx.skip_scale,
+                                        dst=G_prev, dst_ncols=prev_dim, dst_zero_to=ops.round_up(prev_dim, 64), sav=h_prev,
+                                        sav_ncols=prev_dim, sav_scale=1.0 / ctx.skip_scale)
+                else:
+                    G_prev = _planes(n, ops.round_up(in_dim, 64), dev)
+                    ops.gemm_split_bf16(G, wt, ops.round_up(out_dim, 64), in_dim, mode=1, act=act, dst=G_prev, dst_ncols=in_dim,
+                                        dst_zero_to=ops.round_up(in_dim, 64), sav=h_prev, sav_ncols=in_dim)
                 G = G_prev
         out = [None] * (n_lead + ctx.n_seg)
         for l in range(L):
@@ -168,9 +208,10 @@ class _DenseMlp(torch.autograd.Function):
         return tuple(out)
 
 
-def dense_mlp(segments, weights, biases, act):
+def dense_mlp(segments, weights, biases, act, skip=0, skip_scale=1.0, want_hidden=False):
     """segments: [(tensor [N,w], n_freqs | -1)], weights/biases: hidden layers then the output layer.
-    Returns the output layer's raw result [N, n_out] (n_out <= 4)."""
+    Returns the output layer's raw result [N, n_out] (n_out <= 4); with want_hidden also the last hidden activation
+    [N, width] (fp32, detached).  skip / skip_scale: see _DenseMlp."""
     seg_src = [t for t, _ in segments]
     for t in seg_src:
         if t.requires_grad:
@@ -180,4 +221,5 @@ def dense_mlp(segments, weights, biases, act):
     params = []
     for w, b in zip(weights, biases):
         params += [w, b]
-    return _DenseMlp.apply(act, seg_freqs, len(weights) - 1, *seg_src, *params)
+    y, hidden = _DenseMlp.apply(act, seg_freqs, len(weights) - 1, int(skip), float(skip_scale), bool(want_hidden), *seg_src, *params)
+    return (y, hidden) if want_hidden else y

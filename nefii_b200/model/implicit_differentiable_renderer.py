@@ -124,8 +124,28 @@ class ImplicitNetwork(nn.Module):
         net = self._sync(x.device)
         return net.eval(x.detach(), want_feat=want_feat, want_grad=want_grad)
 
+    def _trainable(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _forward_trainable(self, input):
+        """Step-1 geometry fitting (training/geometry_train.py:366-376: `geometry_model(points)[:, 0:1]` against sampled SDF
+        values): the same layers on the trainable tcgen05 stack (nefii_b200/mlp.py: forward keeps the activation planes,
+        backward = weight-gradient and data-gradient GEMMs), skip concat included; gradients reach every lin*.weight_g /
+        weight_v / bias through torch's weight-norm fold.  The feature columns are returned detached (nothing in step 1
+        reads them); d sdf/dx with create_graph (the eikonal term) is not built -- gradient() raises for it."""
+        from ..mlp import dense_mlp
+        layers = self._layers()
+        ws = [_effective_weight(l) for l in layers]
+        bs = [l.bias for l in layers]
+        skip = self.skip_in[0] if len(self.skip_in) else 0
+        y, feat = dense_mlp([(input.detach(), self.multires if self.multires > 0 else -1)], ws, bs, ops.ACT_SOFTPLUS100, skip=skip,
+                            skip_scale=float(1.0 / np.sqrt(2)), want_hidden=True)
+        return torch.cat([y, feat], dim=-1)
+
     # ---- reference API -----------------------------------------------------------------------------
     def forward(self, input, compute_grad=False):
+        if self._trainable():
+            return self._forward_trainable(input)
         sdf, feat, _ = self.evaluate(input, want_feat=True)
         return torch.cat([sdf.unsqueeze(-1), feat], dim=-1)
 
