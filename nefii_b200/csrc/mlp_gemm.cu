@@ -27,20 +27,33 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int kATileBytes = BM * BK * 2;   // 16 KB
+#ifndef NEFII_GEMM_BK1
+#define NEFII_GEMM_BK1 64
+#endif
+#ifndef NEFII_GEMM_BK2
+#define NEFII_GEMM_BK2 64
+#endif
 // Operand ring.  CL = 1: one CTA multiplies its 128 rows by the whole 256-row weight tile (96 KB per stage, 2 stages).
 // CL = 2: a CTA pair (cta_group::2, one 256 x 256 x 16 MMA across two SMs): each CTA stages its own 128 rows of A and
 // HALF of the weight tile, the tensor cores read the other half from the peer's shared memory -- 64 KB per stage, 3 stages,
 // and a third less shared-memory traffic per FLOP (the single-CTA kernel is bound by exactly that, profiles/r1_gemm_*.md).
-template <int CL> struct Ring {
-  static constexpr int kStages = CL == 2 ? 3 : 2;
-  static constexpr int kBRows = BN / CL;
-  static constexpr int kBTileBytes = kBRows * BK * 2;
-  static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
-};
+// A 64-wide K block (the unit of the host interface and of the partial-sum schedule) travels as 64 / kBK ring stages:
+// smaller stages mean more of the 192 KB ring is in flight while one stage is being multiplied -- the tensor pipe idles
+// whenever the operand feed (L2 -> shared memory, ~1 us under load) falls behind, and one 96 KB stage of lookahead does.
 constexpr int kRingBytes = 196608;
-static_assert(Ring<1>::kStages * Ring<1>::kStageBytes == kRingBytes && Ring<2>::kStages * Ring<2>::kStageBytes == kRingBytes, "ring size");
-constexpr int kMaxStages = 3;
+template <int CL> struct Ring {
+  static constexpr int kBK = CL == 2 ? NEFII_GEMM_BK2 : NEFII_GEMM_BK1;   // K columns per stage (64: SWIZZLE_128B rows, 32: SWIZZLE_64B)
+  static constexpr int kSub = BK / kBK;
+  static constexpr int kBRows = BN / CL;
+  static constexpr int kATileBytes = BM * kBK * 2;
+  static constexpr int kBTileBytes = kBRows * kBK * 2;
+  static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
+  static constexpr int kStages = kRingBytes / kStageBytes;
+  static_assert(kBK == 64 || kBK == 32, "stage width");
+  static_assert(kStages * kStageBytes == kRingBytes && kStages >= 2, "ring size");
+};
+constexpr int kMaxStages = 6;
+static_assert(Ring<1>::kStages <= kMaxStages && Ring<2>::kStages <= kMaxStages, "barrier slots");
 // mbarriers: [0..2] operand stage full, [3..5] stage empty, [6..7] TMEM partial full, [8..9] TMEM partial empty
 constexpr int kBarFull = 0, kBarEmpty = kMaxStages, kBarTFull = 2 * kMaxStages, kBarTEmpty = 2 * kMaxStages + 2;
 constexpr int kEpiWarps = 8;
@@ -171,13 +184,15 @@ __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row atoms of 1024 B).
+// ROW_BYTES = 128: SWIZZLE_128B rows of 64 bf16; 64: SWIZZLE_64B rows of 32 bf16.  8-row atoms either way.
+template <int ROW_BYTES>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address
   d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset between 8-row atoms
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;    // stride byte offset between 8-row atoms
   d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;   // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 
@@ -517,7 +532,9 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   using R = Ring<CL>;
   constexpr int kStages = R::kStages;
   constexpr int kStageBytes = R::kStageBytes;
+  constexpr int kATileBytes = R::kATileBytes;
   constexpr int kBTileBytes = R::kBTileBytes;
+  constexpr int kBK = R::kBK;
   const int cta_rank = (CL > 1) ? (int)cluster_ctarank() : 0;
   // every loop below runs while the PAIR's first tile is live, so both CTAs of a pair take the same trips
   if ((long long)(m_tile0 - cta_rank) * BM >= m_limit || k_blocks <= 0) return;
@@ -575,12 +592,12 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       uint32_t phase = 0;
       for (int m_tile = m_tile0; NEFII_TILE_LIVE(m_tile); m_tile += tile_stride)
       for (int nc = 0; nc < n_chunks; ++nc) {
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int ks = 0; ks < k_blocks * R::kSub; ++ks) {
           mbar_wait(smem_u32(&bars[kBarEmpty + stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars[kBarFull + stage]);
           if (dbg & 2) { if (cta_rank == 0) mbar_arrive(full); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
           unsigned char* st = tiles + (size_t)stage * kStageBytes;
-          const int kx = (kb_begin + kb) * BK;
+          const int kx = kb_begin * BK + ks * kBK;
           if (CL == 1) {
             mbar_expect_tx(full, kStageBytes);
             tma_load_2d(smem_u32(st), &map_a_hi, full, kx, m_tile * BM);
@@ -617,18 +634,18 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           mbar_wait(smem_u32(&bars[kBarTEmpty + buf]), ((pcount >> 1) & 1) ^ 1);   // the partial of two groups ago was read
           const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
           const int kb_first = sched.begin(pi), kb_end = sched.begin(pi + 1);
-          for (int kb = kb_first; kb < kb_end; ++kb) {
+          for (int ks = kb_first * R::kSub; ks < kb_end * R::kSub; ++ks) {
             mbar_wait(smem_u32(&bars[kBarFull + stage]), phase);
             tc_fence_after();
             const uint32_t st = smem_u32(tiles + (size_t)stage * kStageBytes);
-            const uint64_t a_hi = make_smem_desc(st);
-            const uint64_t a_lo = make_smem_desc(st + kATileBytes);
-            const uint64_t b_hi = make_smem_desc(st + 2 * kATileBytes);
-            const uint64_t b_lo = make_smem_desc(st + 2 * kATileBytes + kBTileBytes);
-            const uint32_t fresh = (kb == kb_first) ? 0u : 1u;
+            const uint64_t a_hi = make_smem_desc<2 * kBK>(st);
+            const uint64_t a_lo = make_smem_desc<2 * kBK>(st + kATileBytes);
+            const uint64_t b_hi = make_smem_desc<2 * kBK>(st + 2 * kATileBytes);
+            const uint64_t b_lo = make_smem_desc<2 * kBK>(st + 2 * kATileBytes + kBTileBytes);
+            const uint32_t fresh = (ks == kb_first * R::kSub) ? 0u : 1u;
             if (!(dbg & 4)) {
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {
+              for (int k = 0; k < kBK / UMMA_K; ++k) {
                 const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step inside the swizzle row
                 if (CL == 1) {
                   tc_mma_bf16(tmem_d, a_hi + koff, b_lo + koff, kIdesc, (k != 0) ? 1u : fresh);
@@ -639,7 +656,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
                 }
               }
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {
+              for (int k = 0; k < kBK / UMMA_K; ++k) {
                 const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
                 if (CL == 1) tc_mma_bf16(tmem_d, a_hi + koff, b_hi + koff, kIdesc, 1);
                 else tc_mma_bf16_pair(tmem_d, a_hi + koff, b_hi + koff, kIdescPair, 1);
@@ -809,15 +826,15 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_map(CUtensorMap* map, const void* base, int rows, int ld, int k_extent, int box_rows) {
+int make_map(CUtensorMap* map, const void* base, int rows, int ld, int k_extent, int box_rows, int bk) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(NEFII_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(NEFII_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d ld=%d", (int)r, rows, ld);
   return NEFII_OK;
@@ -942,10 +959,11 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   const int cl = (g_cluster_pref == 2 && m_tiles >= 2) ? 2 : 1;   // CTA pairs need two row tiles to work on
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map(&ma_hi, p.a_hi, p.rows_cap, p.a_ld, p.k_pad, BM))) return rc;
-  if ((rc = make_map(&ma_lo, p.a_lo, p.rows_cap, p.a_ld, p.k_pad, BM))) return rc;
-  if ((rc = make_map(&mb_hi, p.b_hi, p.n_pad, p.b_ld, p.k_pad, BN / cl))) return rc;
-  if ((rc = make_map(&mb_lo, p.b_lo, p.n_pad, p.b_ld, p.k_pad, BN / cl))) return rc;
+  const int bk = cl == 2 ? Ring<2>::kBK : Ring<1>::kBK;
+  if ((rc = make_map(&ma_hi, p.a_hi, p.rows_cap, p.a_ld, p.k_pad, BM, bk))) return rc;
+  if ((rc = make_map(&ma_lo, p.a_lo, p.rows_cap, p.a_ld, p.k_pad, BM, bk))) return rc;
+  if ((rc = make_map(&mb_hi, p.b_hi, p.n_pad, p.b_ld, p.k_pad, BN / cl, bk))) return rc;
+  if ((rc = make_map(&mb_lo, p.b_lo, p.n_pad, p.b_ld, p.k_pad, BN / cl, bk))) return rc;
   const int n_chunks = ceil_div(p.epi.dst_zero_to > p.epi.n_valid ? p.epi.dst_zero_to : p.epi.n_valid, BN);
   // plain hidden layers (the kernel's fast_layer): the output planes as tensors for the epilogue's bulk stores
   CUtensorMap md_hi = ma_hi, md_lo = ma_lo;

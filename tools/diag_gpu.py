@@ -192,9 +192,12 @@ def diag_gemmprof():
     a = ops.split_to_planes(x)
     b = ops.split_to_planes(w)
     dst = (torch.empty(rows, n, device=dev, dtype=torch.bfloat16), torch.empty(rows, n, device=dev, dtype=torch.bfloat16))
+    from nefii_b200 import _lib
+    _lib.check(_lib.raw().nefii_gemm_set_debug(int(os.environ.get("GEMM_DEBUG", "0"))))     # ablation mask for A/B captures
     for _ in range(8):
         ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n)
     torch.cuda.synchronize()
+    _lib.check(_lib.raw().nefii_gemm_set_debug(0))
 
 
 def diag_trunc():
