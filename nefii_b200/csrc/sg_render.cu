@@ -128,7 +128,7 @@ background_sg_fwd_kernel(int n_rays, int n_sg, const float* __restrict__ lgt,
 // differentiated with forward-mode duals over the forward math (sg_bwd_math.cuh).  Light gradients are accumulated in the
 // unit parametrisation (shared memory, then one atomicAdd per value per CTA); roughness / specular-reflectance gradients
 // (tiny [K,*] tensors) likewise; the albedo gradient is per ray.
-__global__ void __launch_bounds__(kSgThreads)
+__global__ void __launch_bounds__(kSgThreads, 4)
 sg_render_bwd_kernel(int n_rays, int n_sg, int n_mat, const float* __restrict__ lgt, const float* __restrict__ spec,
                      const float* __restrict__ rough, const float* __restrict__ albedo, const float* __restrict__ normal,
                      const float* __restrict__ view, const float* __restrict__ out_spec, const float* __restrict__ out_diff,

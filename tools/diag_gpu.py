@@ -47,6 +47,13 @@ def diag_sg():
         ms = ev_time(lambda: render_with_sg(lgt, spec, rough, albedo, normal, view))
         ms_ref = ev_time(lambda: sg.render_with_sg(lgt, spec, rough, albedo, normal, view), iters=3, warm=1) if n <= 131072 else float("nan")
         print("SG time n=%d ours %.4f ms (%.1f Mray/s)  torch-oracle-on-gpu %.3f ms" % (n, ms, n / ms / 1e3, ms_ref))
+        lg, rg, ag = lgt.clone().requires_grad_(True), rough.clone().requires_grad_(True), albedo.clone().requires_grad_(True)
+
+        def fb():
+            out = render_with_sg(lg, spec, rg, ag, normal, view)
+            out['sg_rgb'].sum().backward()
+        ms_fb = ev_time(fb, iters=5, warm=2)
+        print("SG fwd+bwd n=%d ours %.4f ms (bwd ~ %.4f ms, %.1f Mray/s)" % (n, ms_fb, ms_fb - ms, n / max(ms_fb - ms, 1e-9) / 1e3))
 
 
 def diag_gemm():
