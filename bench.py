@@ -277,6 +277,39 @@ def run_ours(args):
     torch.cuda.synchronize()
     step_ms = e_prof0.elapsed_time(e_prof1)
 
+    # ---- extra: the secondary-training pass the reference's trainer runs every `secondary_train_interval` = 10 steps
+    # (idr_train.py:804-852: <= secondary_batch_size 1024 secondary hit points x num_rays 64 directions through
+    # forward(with_point=True), L1 between the SG and the radiance-field colour, backward, both optimizers) ----
+    secondary_ms = None
+    try:
+        with torch.no_grad():
+            out = model({'uv': dev_batches[-1][0], 'object_mask': dev_batches[-1][1], 'pose': pose, 'intrinsics': K})
+        sp, sm, sd = out['secondary_points'].reshape(-1, 3), out['secondary_mask'].reshape(-1), out['secondary_dir'].reshape(-1, 3)
+        pts, dirs = sp[sm][:1024], sd[sm][:1024]
+        n_sec = pts.shape[0]
+        sec_in = {'points': pts.unsqueeze(1).expand(n_sec, NUM_RAYS, 3).contiguous(),
+                  'ray_dirs': dirs.unsqueeze(1).expand(n_sec, NUM_RAYS, 3).contiguous()}
+
+        def secondary_step():
+            flat.zero()
+            ret = model(sec_in, with_point=True)
+            loss = torch.nn.functional.l1_loss(ret['sg_rgb_values'], ret['idr_rgb_values'])
+            loss.backward()
+            flat.all_reduce(world)
+            opt_idr.step()
+            opt_sg.step()
+        if n_sec > 0:
+            secondary_step()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            secondary_step()
+            s1.record()
+            barrier()
+            secondary_ms = max_over_ranks(s0.elapsed_time(s1))
+    except Exception as exc:            # an extra: never let it take the headline line down
+        print("secondary-training pass failed: %r" % (exc,), file=sys.stderr)
+
     # ---- extra (BASELINE metric tail "ms/frame 800x800"): novel-view render, eval mode, 1 ray per pixel, this rank's share ----
     frame_ms = None
     try:
@@ -343,6 +376,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "ms_per_frame_800x800": frame_ms,
+            "ms_per_secondary_training_pass": secondary_ms,
             "clocks": clocks.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu,
