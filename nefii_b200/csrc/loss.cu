@@ -11,7 +11,7 @@ namespace nefii {
 
 namespace {
 
-constexpr int kLossThreads = 1024;
+constexpr int kLossThreads = 512;
 
 __device__ __forceinline__ float img_loss(float d, int kind) {
   if (kind == LOSS_L1) return fabsf(d);
