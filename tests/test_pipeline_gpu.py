@@ -204,3 +204,31 @@ def test_render_frame_chunked_matches_single_call(cuda_device):
         # geometry and material do not depend on the sampled secondary rays; bisection's batch-wide stop moves depths < 2e-5
         assert (whole[name] - parts[name])[m].abs().max().item() < 2e-3, name
     assert set(whole) == {k for k, _ in general.FRAME_PLANES}
+
+
+def test_render_frame_multi_ray_chunks(cuda_device):
+    """BASELINE configs[4]-style rendering (several jittered rays per pixel): chunks hold 2**level / num_rays pixels
+    (utils/general.py:29-30) and the per-pixel averages of the chunked frame equal the single-call frame."""
+    from nefii_b200.utils import general
+    dev = cuda_device
+    net, _ = _build(dev)
+    net.eval()
+    n, R = 32, 4
+    ii, jj = torch.meshgrid(torch.arange(n, device=dev).float(), torch.arange(n, device=dev).float(), indexing="xy")
+    g = torch.Generator().manual_seed(0)
+    jitter = (torch.rand(R, 2, generator=g) - 0.5).to(dev)
+    uv = (torch.stack([ii, jj], -1).reshape(-1, 1, 2) + 0.5 + jitter[None]).unsqueeze(0)        # [1, n*n, R, 2]
+    f = 2.0 * n
+    K = torch.tensor([[f, 0, n / 2, 0], [0, f, n / 2, 0], [0, 0, 1, 0], [0, 0, 0, 1]], device=dev)[None]
+    pose = torch.eye(4, device=dev)[None].clone()
+    pose[0, 2, 3] = -3.0
+    inp = {'uv': uv, 'object_mask': torch.ones(1, n * n, dtype=torch.bool, device=dev), 'pose': pose, 'intrinsics': K}
+    assert general.split_input(inp, n * n, num_rays=R, memory_capacity_level=10)[0]['uv'].shape == (1, 256, R, 2)
+    whole = general.render_frame(net, inp, n * n, num_rays=R, memory_capacity_level=20)
+    parts = general.render_frame(net, inp, n * n, num_rays=R, memory_capacity_level=10)
+    assert whole['points'].shape == (n * n, 3) and parts['sg_rgb_values'].shape == (n * n, 3)
+    assert torch.equal(whole['network_object_mask'], parts['network_object_mask'])
+    m = whole['network_object_mask']
+    assert int(m.sum()) > 50
+    for name in ('points', 'normal_values', 'idr_rgb_values', 'sg_diffuse_albedo_values', 'sg_roughness_values'):
+        assert (whole[name] - parts[name])[m].abs().max().item() < 2e-3, name
