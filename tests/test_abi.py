@@ -41,3 +41,31 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.NefiiError):
         render_with_sg(torch.zeros(4, 7), torch.zeros(1, 3), torch.ones(1, 1), torch.zeros(5, 3), torch.zeros(5, 3),
                        torch.zeros(5, 3))
+
+
+def test_argument_errors_return_codes_not_crashes():
+    """The ABI's error convention (include/nefii_b200.h: negative int + nefii_last_error text, nothing throws or exits):
+    malformed sizes are rejected before any CUDA call, so this runs without a GPU."""
+    from nefii_b200 import _lib
+    lib = _lib.raw()
+    null = None
+    one = ctypes.c_void_p(16)          # a non-null pointer that is never dereferenced (argument checks come first)
+    cases = [
+        lambda: lib.nefii_sg_render_fwd(null, 8, 0, 1, one, one, one, one, one, one, null, one, one, one),       # no light SGs
+        lambda: lib.nefii_sg_render_fwd(null, 8, 128, 99, one, one, one, one, one, one, null, one, one, one),    # too many materials
+        lambda: lib.nefii_sg_render_fwd(null, 8, 128, 1, null, one, one, one, one, one, null, one, one, one),    # null input
+        lambda: lib.nefii_background_sg_fwd(null, 8, 0, one, one, one),
+        lambda: lib.nefii_idr_loss_fwd(null, 10, 4, one, one, one, one, one, one, one, 0, 1, ctypes.c_float(50.0), one),   # 10 pixels, patches of 4
+        lambda: lib.nefii_idr_loss_fwd(null, 8, 4, one, one, one, one, one, one, one, 7, 1, ctypes.c_float(50.0), one),    # unknown loss kind
+        lambda: lib.nefii_idr_loss_fwd(null, 8, 4, one, one, one, one, one, one, one, 0, 1, ctypes.c_float(-1.0), one),    # alpha <= 0
+        lambda: lib.nefii_gemm_set_cluster(3),
+        lambda: lib.nefii_gemm_set_k_flush(0),
+    ]
+    for i, call in enumerate(cases):
+        rc = call()
+        assert rc < 0, (i, rc)
+        assert len(lib.nefii_last_error()) > 0
+    # empty problems are fine and touch nothing
+    assert lib.nefii_sg_render_fwd(null, 0, 128, 1, null, null, null, null, null, null, null, null, null, null) == 0
+    assert lib.nefii_idr_loss_bwd(null, 0, 4, null, null, null, null, null, null, null, 0, 1, ctypes.c_float(50.0), null, null,
+                                  null, null, null, null) == 0
