@@ -160,7 +160,8 @@ int64_t nefii_trace_workspace_bytes(int sdf_kind, const void* sdf, int n_rays, i
  * all rays (training only; the reference draws them on the CPU generator, ray_tracing.py:316).
  * Outputs: points [B*P,3], hit [B*P] uint8 (network_object_mask), dists [B*P].
  * stats: host int64[8] or NULL: {sampler rays, root-find rays, min-SDF rays, SDF point evaluations, ...}.
- * Synchronises `stream` once internally (twice when stats != NULL). */
+ * Synchronises `stream` once internally, a second time when rays went to the sampler (to read how many bracketed a root),
+ * and once more when stats != NULL. */
 int nefii_ray_trace(void* stream, const nefii_trace_config* cfg, int sdf_kind, const void* sdf, int n_prims,
                     int n_batch, int n_pix, const float* cam_loc, const float* ray_dirs, const uint8_t* object_mask,
                     int flags, const float* linspace, const float* uniforms, void* workspace, int64_t workspace_bytes,
