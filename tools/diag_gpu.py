@@ -1,4 +1,6 @@
-"""GPU diagnostics printed during development trips (not part of the product or the tests)."""
+"""GPU diagnostics printed during development trips.  TEST INFRASTRUCTURE, like tests/: it compares the CUDA path with the
+oracle (and therefore imports oracle/), times kernels with CUDA events and drives the ablation masks; nothing under
+nefii_b200/ imports it."""
 import sys
 import os
 import time
