@@ -89,13 +89,13 @@ int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* desc /* host */);
  * fp32 product counted once), number of launches}. */
 int nefii_gemm_profile_enable(int on);
 /* tuning knob: 1 = single-CTA layer GEMM, 2 = CTA pairs (tcgen05 cta_group::2: two SMs run one 256-row MMA and share the
- * weight tile through each other's shared memory).  The environment variable NEFII_GEMM_CLUSTER sets the default at load. */
+ * weight tile through each other's shared memory; default).  The environment variable NEFII_GEMM_CLUSTER sets the default at load. */
 int nefii_gemm_set_cluster(int cluster_size);
 /* development only: disables pieces of the GEMM pipeline (1 epilogue math, 2 TMA loads, 4 MMAs, 8 TMEM flush, 16 plane staging +
  * stores, 32 plane stores) for timing experiments; results are then garbage */
 int nefii_gemm_set_debug(int mask);
 /* accuracy / overlap knob of the layer GEMM: 64-wide K blocks accumulated inside TMEM before the partial sum moves to the fp32
- * register accumulators (1 = most accurate; default 2) */
+ * register accumulators (1 = most accurate; default 4, NEFII_GEMM_KFLUSH sets the default at load) */
 int nefii_gemm_set_k_flush(int k_blocks);
 /* ... for the first two partial sums of every 256-column chunk only (set_k_flush resets it to the same value) */
 int nefii_gemm_set_k_flush_head(int k_blocks);

@@ -98,3 +98,32 @@ def test_backward_layer(cuda_device):
     assert (got[:, 473:] == 0).all()
     # fp32 side output holds the raw product (no out_scale) for the PE columns
     assert (pe.double() - full[:, 473:]).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("k_flush", [1, 2, 4])
+def test_both_kernel_instantiations_and_partial_lengths(cuda_device, cluster, k_flush):
+    """The single-CTA kernel (cta_group::1) and the CTA-pair kernel (cta_group::2) are separate template instantiations, and
+    the partial-sum length is a runtime knob: every combination must reproduce the fp64 product (hidden layer with bulk
+    stores, ragged last tile, odd number of row tiles) -- whatever the library's defaults are."""
+    from nefii_b200 import _lib, ops
+    dev = cuda_device
+    lib = _lib.raw()
+    torch.manual_seed(11)
+    rows, k, n = 128 * 5 + 37, 512, 512
+    x = torch.randn(rows, k, device=dev) * 0.4
+    w = torch.randn(n, k, device=dev) / k ** 0.5
+    bias = torch.randn(n, device=dev) * 0.1
+    a, b = ops.split_to_planes(x), ops.split_to_planes(w)
+    dst = (torch.zeros(rows, n, device=dev, dtype=torch.bfloat16), torch.zeros(rows, n, device=dev, dtype=torch.bfloat16))
+    ref = torch.nn.functional.softplus(x.double() @ w.double().t() + bias.double(), beta=100)
+    try:
+        _lib.check(lib.nefii_gemm_set_cluster(cluster))
+        _lib.check(lib.nefii_gemm_set_k_flush(k_flush))
+        ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n)
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(lib.nefii_gemm_set_cluster(2))
+        _lib.check(lib.nefii_gemm_set_k_flush(4))
+    err = (_planes_to_f32(dst).double() - ref).abs().max().item()
+    assert err < 4e-5 * max(ref.abs().max().item(), 1.0), err

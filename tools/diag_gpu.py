@@ -125,7 +125,7 @@ def diag_cluster():
     b = ops.split_to_planes(w)
     dst = (torch.empty(rows, n, device=dev, dtype=torch.bfloat16), torch.empty(rows, n, device=dev, dtype=torch.bfloat16))
     ref = None
-    for cl in (1, 2, 4):
+    for cl in (1, 2):
         _lib.check(_lib.raw().nefii_gemm_set_cluster(cl))
         fn = lambda: ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n)
         ms = ev_time(fn)
@@ -133,7 +133,7 @@ def diag_cluster():
         if ref is None:
             ref = got
         print("CLUSTER %d: %.4f ms %.1f TFLOP/s alg ; identical to cluster 1: %s" % (cl, ms, 2.0 * rows * n * k / ms / 1e9, torch.equal(got, ref)))
-    _lib.check(_lib.raw().nefii_gemm_set_cluster(1))
+    _lib.check(_lib.raw().nefii_gemm_set_cluster(2))
 
 
 def diag_kflush():
@@ -165,7 +165,7 @@ def diag_kflush():
         e = sdf.double() - r64
         print("KFLUSH %d head %d: %.4f ms %.1f TFLOP/s alg | all-positive K=512 bias %.2f ulp | SDF err mean %.2e (signed %.2e) max %.2e" % (
             kf, head, ms, 2.0 * rows * n * k / ms / 1e9, err.mean().item() / 2 ** -24, e.abs().mean().item(), e.mean().item(), e.abs().max().item()))
-    _lib.check(_lib.raw().nefii_gemm_set_k_flush(2))
+    _lib.check(_lib.raw().nefii_gemm_set_k_flush(4))
 
 
 def diag_ablate():
@@ -188,7 +188,7 @@ def diag_ablate():
             ms = ev_time(lambda: ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n), iters=10)
             print("ABLATE cl=%d mask=%2d %-42s %.4f ms" % (cl, mask, names[mask], ms))
     _lib.check(_lib.raw().nefii_gemm_set_debug(0))
-    _lib.check(_lib.raw().nefii_gemm_set_cluster(1))
+    _lib.check(_lib.raw().nefii_gemm_set_cluster(2))
 
 
 def diag_gemmprof():
@@ -403,6 +403,24 @@ def diag_pipeline():
             print("   %-26s rel err median %.2e p95 %.2e p99 %.2e max %.2e" % ((k,) + tuple(rel.quantile(torch.tensor([0.5, 0.95, 0.99, 1.0], device=dev)).tolist())))
         if mine['secondary_mask'] is not None and mine['secondary_mask'].shape == ref['secondary_mask'].shape:
             print("   secondary mask agree %.5f" % (mine['secondary_mask'] == ref['secondary_mask']).float().mean().item())
+
+
+def diag_l2fit():
+    """Is the layer GEMM faster per row tile when its activations stay L2-resident (small row counts, same buffers reused)?"""
+    from nefii_b200 import ops
+    dev = torch.device("cuda:0")
+    k = n = 512
+    w = torch.randn(n, k, device=dev) / k ** 0.5
+    bias = torch.zeros(n, device=dev)
+    b = ops.split_to_planes(w)
+    for rows in (18944, 37888, 75776, 151552, 262144, 1 << 20):
+        x = torch.randn(rows, k, device=dev) * 0.3
+        a = ops.split_to_planes(x)
+        dst = (torch.empty(rows, n, device=dev, dtype=torch.bfloat16), torch.empty(rows, n, device=dev, dtype=torch.bfloat16))
+        ms = ev_time(lambda: ops.gemm_split_bf16(a, b, k, n, act=1, bias=bias, dst=dst, dst_ncols=n), iters=20)
+        waves = rows / 128 / 148
+        print("L2FIT rows %8d (%.1f MB in + out): %.4f ms  %.1f TFLOP/s alg  %.2f us per wave of 148 tiles" % (
+            rows, rows * 4096 / 1e6, ms, 2.0 * rows * n * k / ms / 1e9, ms * 1e3 / waves))
 
 
 if __name__ == "__main__":
