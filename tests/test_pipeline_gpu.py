@@ -232,3 +232,42 @@ def test_render_frame_multi_ray_chunks(cuda_device):
     assert int(m.sum()) > 50
     for name in ('points', 'normal_values', 'idr_rgb_values', 'sg_diffuse_albedo_values', 'sg_roughness_values'):
         assert (whole[name] - parts[name])[m].abs().max().item() < 2e-3, name
+
+
+def test_runner_toggles_roughness_warmup_and_load_light(cuda_device, tmp_path):
+    """What the reference trainer toggles on the material network during step 2 (idr_train.py:543-547,705-713: roughness
+    warm-up via set_roughness_fake, --light_sg_path via load_light): same semantics through the accelerated forward."""
+    import numpy as np
+    from tests.util import load_golden
+    dev = cuda_device
+    net, _ = _build(dev)
+    net.eval()
+    inp, U, vecs = _inputs(dev, 24, 0, seed=3)
+    with torch.no_grad():
+        base = net.forward_with_uv(inp, uniforms=U)
+        net.envmap_material_network.set_roughness_fake(True)
+        fake = net.forward_with_uv(inp, uniforms=U)
+        net.envmap_material_network.set_roughness_fake(False)
+    hit = base['network_object_mask']
+    assert int(hit.sum()) > 50
+    assert torch.equal(fake['network_object_mask'], hit)
+    assert (fake['sg_roughness_values'][hit] == 0.5).all()                       # sg_envmap_material.py:407-408
+    assert not torch.allclose(fake['sg_specular_rgb_values'][hit], base['sg_specular_rgb_values'][hit])
+    assert torch.equal(fake['sg_diffuse_albedo_values'], base['sg_diffuse_albedo_values'])
+    # load_light: a [M, 7] .npy replaces lgtSGs (here the reference's shipped sunrise environment from the golden file)
+    sunrise = load_golden("sg_render_cfg1.npz")["lgt_sunrise"]
+    path = str(tmp_path / "sg_128.npy")
+    np.save(path, sunrise)
+    net.envmap_material_network.load_light(path)
+    assert net.envmap_material_network.lgtSGs.shape == (128, 7) and net.envmap_material_network.lgtSGs.is_cuda
+    assert torch.equal(net.envmap_material_network.get_light().cpu(), torch.from_numpy(sunrise))
+    with torch.no_grad():
+        lit = net.forward_with_uv(inp, uniforms=U)
+    assert torch.isfinite(lit['sg_rgb_values']).all()
+    assert not torch.allclose(lit['sg_rgb_values'][hit], base['sg_rgb_values'][hit])
+    # the environment seen by miss rays is exactly the loaded light
+    from nefii_b200.utils import rend_util
+    from oracle import sg
+    dirs, _ = rend_util.get_camera_params(inp['uv'], inp['pose'], inp['intrinsics'])
+    bg = sg.background_sg(torch.from_numpy(sunrise).to(dev), dirs.reshape(-1, 3)[~hit])
+    assert torch.allclose(lit['sg_rgb_values'][~hit], bg, rtol=1e-4, atol=1e-6)
