@@ -380,7 +380,8 @@ def diag_pipeline():
     net = IDRNetwork(default_model_conf()).to(dev)
     rh.load_oracle_weights(net, om)
     om = om.to(dev)
-    for training, rays, n_side in ((False, 0, 64), (True, 4, 48)):
+    scale = int(os.environ.get("PIPE_SCALE", "1"))      # 2: 16 384 eval rays / 36 864 training rays
+    for training, rays, n_side in ((False, 0, 64 * scale), (True, 4, 48 * scale)):
         net.train(training)
         uv, pose, K = rh.camera_batch(n_side, rays, seed=3)
         S = uv.shape[1]
