@@ -375,7 +375,7 @@ def diag_pipeline():
     from nefii_b200.model.implicit_differentiable_renderer import IDRNetwork
     from nefii_b200.utils.conf import default_model_conf
     dev = torch.device("cuda:0")
-    om = rh.small_model(seed=0)
+    om = rh.small_model(seed=0, bumps=float(os.environ.get("PIPE_BUMPS", "0.03")))     # larger: rougher SDF, more sampler / bisection rays
     torch.manual_seed(0)
     net = IDRNetwork(default_model_conf()).to(dev)
     rh.load_oracle_weights(net, om)
