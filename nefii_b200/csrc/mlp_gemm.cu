@@ -192,8 +192,11 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   // plain hidden layers (the kernel's fast_layer): the output planes as tensors for the epilogue's bulk stores
   CUtensorMap md_hi = ma_hi, md_lo = ma_lo;
   int store_tma = 0;
-  if (g_store_tma && p.epi.mode == 0 && p.epi.w_last == nullptr && p.epi.bias != nullptr && p.epi.dst.hi != nullptr && p.epi.dst_f32 == nullptr &&
-      (p.epi.dst_col0 & 7) == 0 && (p.epi.dst.ld & 7) == 0 && n_chunks * BN <= kBiasSmemFloats && p.epi.dst_ncols >= 32) {
+  const bool planes_out = p.epi.dst.hi != nullptr && p.epi.dst_f32 == nullptr && (p.epi.dst_col0 & 7) == 0 && (p.epi.dst.ld & 7) == 0 &&
+                          p.epi.dst_ncols >= 32;
+  const bool fwd_fast = p.epi.mode == 0 && p.epi.w_last == nullptr && p.epi.bias != nullptr && n_chunks * BN <= kBiasSmemFloats;
+  const bool bwd_fast = p.epi.mode == 1 && p.epi.sav_hi != nullptr && (p.epi.sav_ld & 7) == 0;
+  if (g_store_tma && planes_out && (fwd_fast || bwd_fast)) {
     if ((rc = make_store_map(&md_hi, p.epi.dst.hi + p.epi.dst_col0, p.rows_cap, p.epi.dst.ld, p.epi.dst_ncols))) return rc;
     if ((rc = make_store_map(&md_lo, p.epi.dst.lo + p.epi.dst_col0, p.rows_cap, p.epi.dst.ld, p.epi.dst_ncols))) return rc;
     store_tma = 1;

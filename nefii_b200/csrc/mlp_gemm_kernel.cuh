@@ -376,6 +376,50 @@ __device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bia
   }
 }
 
+// Fast path of the data-gradient layers (MODE 1) on whole 32-row tiles whose column span is entirely real: the products are
+// scaled by the activation derivative recovered from the saved forward output (read as this lane's row, 16 bytes at a time) and
+// leave as bf16 planes through the same staged bulk tensor stores as the forward path; no per-element predicates.
+template <int ACT>
+__device__ __forceinline__ void finish_span_bwd_fast(float* acc, const __nv_bfloat16* sav_hi_row, const __nv_bfloat16* sav_lo_row,
+                                                     float sav_scale, int n_span0, float scale, const FastStore& fs) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < kColsPerWarp / 32; ++c) {
+    const float* v = acc + c * 32;
+    const uint4* sh = reinterpret_cast<const uint4*>(sav_hi_row + n_span0 + c * 32);
+    const uint4* sl = reinterpret_cast<const uint4*>(sav_lo_row + n_span0 + c * 32);
+    uint4 hq[4], lq[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 h4 = __ldg(sh + g), l4 = __ldg(sl + g);
+      const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+        const float2 lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[j]));
+        o[2 * j] = v[8 * g + 2 * j] * act_bwd_from_output<ACT>((hf.x + lf.x) * sav_scale) * scale;
+        o[2 * j + 1] = v[8 * g + 2 * j + 1] * act_bwd_from_output<ACT>((hf.y + lf.y) * sav_scale) * scale;
+      }
+      split8(o, hq[g], lq[g]);
+    }
+    if (lane == 0) bulk_wait_read_all();   // the previous bulk stores have read the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      fs.st_in[g ^ fs.sw_in] = hq[g];
+      fs.st_in[128 + (g ^ fs.sw_in)] = lq[g];
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(fs.map_hi, fs.st_u32, n_span0 + c * 32, fs.y0);
+      tma_store_2d(fs.map_lo, fs.st_u32 + 2048, n_span0 + c * 32, fs.y0);
+      bulk_commit();
+    }
+  }
+}
+
 // Fast path of the fused output layer when nothing but the n_last dot products leaves the tile (the SDF value of the
 // tracer's evaluations): activation and FMA only, bias and output weights read as broadcast 16-byte loads from the copies
 // staged in shared memory (s_w: [kMaxLast][kBiasSmemFloats]).
@@ -678,6 +722,9 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       for (int i = threadIdx.x; i < n_chunks * BN; i += kEpiWarps * 32) s_bias[i] = i < epi.n_valid ? __ldg(epi.bias + i) : 0.f;
       asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
     }
+    // data-gradient layer writing aligned planes with a saved forward output for every column it produces
+    const bool fast_bwd = MODE == 1 && store_tma && epi.dst.hi != nullptr && epi.dst_f32 == nullptr && epi.sav_hi != nullptr &&
+                          (epi.dst_col0 & 7) == 0 && (epi.dst.ld & 7) == 0 && (epi.sav_ld & 7) == 0;
     // fused output layer with only its dot products as output: bias and output weights staged behind the row partials
     float* s_fbias = reinterpret_cast<float*>(tail + 2 * BM * kMaxLast * sizeof(float));
     float* s_fw = s_fbias + kBiasSmemFloats;
@@ -709,7 +756,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     const long long row = (long long)m_tile * BM + row_in_tile;
     const bool row_ok = row < m_limit;
     float part[kMaxLast] = {0.f, 0.f, 0.f, 0.f};
-    if (fast_layer) {
+    if (fast_layer || fast_bwd) {
       const long long r0 = row - lane + (lane >> 2);
       fs.p_hi = epi.dst.hi + r0 * epi.dst.ld + epi.dst_col0 + 8 * (lane & 3);
       fs.p_lo = epi.dst.lo + r0 * epi.dst.ld + epi.dst_col0 + 8 * (lane & 3);
@@ -754,6 +801,12 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           finish_span_fast<ACT, true>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg);
         else
           finish_span_fast<ACT, false>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg);
+        continue;
+      }
+      if (fast_bwd && row - lane + 32 <= m_limit && n_span0 + kColsPerWarp <= epi.n_valid && n_span0 + kColsPerWarp <= epi.dst_ncols &&
+          n_span0 + kColsPerWarp <= epi.sav_ncols) {
+        finish_span_bwd_fast<ACT>(acc, epi.sav_hi + row * epi.sav_ld, epi.sav_lo + row * epi.sav_ld, epi.sav_scale, n_span0,
+                                  epi.out_scale, fs);
         continue;
       }
       if (fast_fused && n_span0 + kColsPerWarp <= epi.n_valid) {
