@@ -93,10 +93,12 @@ class ClockSampler:
     FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index):
-        self.samples, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index, enabled=True):
+        self.samples, self.proc, self.gpu, self.enabled = [], None, gpu_index, enabled
 
     def __enter__(self):
+        if not self.enabled:        # one poller per job (rank 0's GPU): eight NVML pollers contend with the ranks' launch threads
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -234,7 +236,7 @@ def run_ours(args):
     barrier()
     launches0 = int(_lib.raw().nefii_launch_count())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, enabled=(rank == 0)) as clocks:
         ev0.record()
         for i in range(args.warmup, n_steps):
             step(*dev_batches[i])
