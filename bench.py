@@ -11,6 +11,10 @@ Random-init weights of that architecture (the reference's own initialisers), syn
   python bench.py --impl reference ...                     # the reference's algorithm on the host CPU (oracle port)
 
 One JSON line on stdout (rank 0).  value = (primary + secondary rays of all ranks) / max-over-ranks device time.
+Beside the contract's keys the line carries `roofline` (the tcgen05 layer GEMM, timed live with CUDA events around every launch),
+`cpu_baseline` (oracle port on the host cores, bounded sample) and three extras: `ms_per_frame_800x800` (chunked, rank-sharded
+novel-view render with the gather onto rank 0), `ms_per_secondary_training_pass` (the trainer's every-10th-step pass through
+forward(with_point=True)) and `gpu_launches` (kernels of this library inside the timed region).
 """
 import argparse
 import json
