@@ -80,6 +80,8 @@ typedef struct nefii_gemm_desc {
   void* seed_hi; void* seed_lo; int32_t seed_ld;                                     /* input-gradient seed planes */
   const void* sav_hi; const void* sav_lo; int32_t sav_ld; int32_t sav_ncols; float sav_scale; /* backward: saved activations */
   int32_t k_splits; int64_t f32_split_stride; int32_t k_splits_used;   /* split-K: partial s -> dst_f32 + s*stride (floats); k_splits_used is an output */
+  int32_t k_flush;                /* K blocks per TMEM partial for this launch (1 = most accurate); 0 = library default */
+  int32_t dst_pad_ok;             /* 1: plane columns [dst_ncols, round_up(dst_ncols,128)) may be overwritten (caller refills them) */
 } nefii_gemm_desc;
 
 int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* desc /* host */);
@@ -129,9 +131,10 @@ int nefii_sdf_destroy(void* handle);
 int nefii_sdf_set_weights(void* handle, void* stream, const float* const* weights, const float* const* biases);
 int64_t nefii_sdf_workspace_bytes(void* handle, int rows_cap, int with_grad);
 /* x [rows_cap,3]; count: device int32 with the number of valid rows or NULL; sdf [rows_cap];
- * feat [rows_cap,width] or NULL; grad [rows_cap,3] or NULL (d sdf / d x). */
+ * feat [rows_cap,width] or NULL; grad [rows_cap,3] or NULL (d sdf / d x).
+ * k_flush: accuracy tier of the layer GEMMs (K blocks per TMEM partial, 1 = most accurate); 0 = library default. */
 int nefii_sdf_eval(void* handle, void* stream, int rows_cap, const int32_t* count, const float* x,
-                   void* workspace, int64_t workspace_bytes, float* sdf, float* feat, float* grad);
+                   void* workspace, int64_t workspace_bytes, float* sdf, float* feat, float* grad, int k_flush);
 
 /* ---------------------------------------------------------------------------------------------
  * Sphere tracing -- replaces RayTracing.forward, code/model/ray_tracing.py:29-101 (sphere_tracing
@@ -159,13 +162,24 @@ int64_t nefii_trace_workspace_bytes(int sdf_kind, const void* sdf, int n_rays, i
  * linspace: device [n_steps] = linspace(0,1,n_steps); uniforms: device [n_steps] U(0,1) draws shared by
  * all rays (training only; the reference draws them on the CPU generator, ray_tracing.py:316).
  * Outputs: points [B*P,3], hit [B*P] uint8 (network_object_mask), dists [B*P].
- * stats: host int64[8] or NULL: {sampler rays, root-find rays, min-SDF rays, SDF point evaluations, ...}.
- * Synchronises `stream` once internally, a second time when rays went to the sampler (to read how many bracketed a root),
- * and once more when stats != NULL. */
+ * stats: host int64[8] or NULL: {sampler rays, root-find rays, min-SDF rays, SDF point evaluations, march rounds, ...}.
+ * The trace never waits for the host: every loop of the reference (march iterations, sampler chunks, bisection steps,
+ * min-SDF chunks) is sized by a device-side control block.  Only stats != NULL synchronises `stream` (to read that block).
+ * In graph mode (default) the launch sequence is captured once per argument tuple into a CUDA graph whose loops are
+ * conditional WHILE nodes and replayed by later calls: keep the buffers at the same addresses to hit the cache. */
 int nefii_ray_trace(void* stream, const nefii_trace_config* cfg, int sdf_kind, const void* sdf, int n_prims,
                     int n_batch, int n_pix, const float* cam_loc, const float* ray_dirs, const uint8_t* object_mask,
                     int flags, const float* linspace, const float* uniforms, void* workspace, int64_t workspace_bytes,
                     float* points, uint8_t* hit, float* dists, int64_t* stats);
+/* accuracy tiers of the SDF evaluations inside a trace (K blocks per TMEM partial, 0 = library default): march_flush for the
+ * march and bisection rounds (they decide where a ray stops; default 1), bulk_flush for the n_steps-sample scans of the
+ * sampler and of min-SDF sampling (they only select brackets / arg-mins; default 0) */
+int nefii_trace_set_tiers(int march_flush, int bulk_flush);
+/* 0: fixed launch schedule (every loop unrolled to its worst case, empty rounds exit at once); 1: CUDA graph with
+ * conditional WHILE nodes (default; NEFII_TRACE_GRAPH=0 selects the fixed schedule at load) */
+int nefii_trace_set_graph_mode(int mode);
+/* drops the cached trace graphs (they hold raw pointers into workspaces and SDF handles) */
+int nefii_trace_graph_clear(void);
 /* the analytic test SDF alone: x [n,3] -> sdf [n] */
 int nefii_analytic_sdf_eval(void* stream, const float* prims, int n_prims, int n, const float* x, float* sdf);
 

@@ -40,12 +40,15 @@ SIGNATURES = {
     "nefii_trace_workspace_bytes": [c_int, c_void_p, c_int, c_int],
     "nefii_ray_trace": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                         c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p],
+    "nefii_trace_set_tiers": [c_int, c_int],
+    "nefii_trace_set_graph_mode": [c_int],
+    "nefii_trace_graph_clear": [],
     "nefii_analytic_sdf_eval": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "nefii_sdf_create": [c_void_p, c_void_p],
     "nefii_sdf_destroy": [c_void_p],
     "nefii_sdf_set_weights": [c_void_p, c_void_p, c_void_p, c_void_p],
     "nefii_sdf_workspace_bytes": [c_void_p, c_int, c_int],
-    "nefii_sdf_eval": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p],
+    "nefii_sdf_eval": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_int],
     "nefii_split_to_planes": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int],
     "nefii_idr_loss_fwd": [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_int, c_int, c_float, c_void_p],
     "nefii_idr_loss_bwd": [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_int, c_int, c_float] + [c_void_p] * 6,

@@ -19,6 +19,7 @@ char* error_buffer() {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
+void add_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -52,7 +53,7 @@ int reduce_splits(cudaStream_t, const float*, int, long long, int, int, int, flo
 extern "C" {
 
 const char* nefii_last_error(void) { return nefii::error_buffer(); }
-int nefii_abi_version(void) { return 1; }
+int nefii_abi_version(void) { return 2; }
 int64_t nefii_launch_count(void) { return (int64_t)nefii::launches(); }
 
 int nefii_sg_render_fwd(void* stream, int n_rays, int n_sg, int n_mat, const float* lgt_sgs, const float* specular,
@@ -83,6 +84,7 @@ int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* d) {
   e.sav_hi = (const __nv_bfloat16*)d->sav_hi; e.sav_lo = (const __nv_bfloat16*)d->sav_lo; e.sav_ld = d->sav_ld;
   e.sav_ncols = d->sav_ncols; e.sav_scale = d->sav_scale;
   p.k_splits = d->k_splits; p.f32_split_stride = d->f32_split_stride;
+  p.k_flush = d->k_flush; e.dst_pad_ok = d->dst_pad_ok;
   int used = 1;
   p.k_splits_used = &used;
   int rc = nefii::gemm_split_bf16((cudaStream_t)stream, p);
@@ -108,6 +110,7 @@ int nefii_sdf_create(void** handle, const nefii_sdf_config* cfg) {
   return NEFII_OK;
 }
 int nefii_sdf_destroy(void* handle) {
+  nefii::trace_graph_clear();     // cached trace graphs point into the handle's packed weights
   delete static_cast<nefii::SdfNet*>(handle);
   return NEFII_OK;
 }
@@ -120,10 +123,10 @@ int64_t nefii_sdf_workspace_bytes(void* handle, int rows_cap, int with_grad) {
   return (int64_t)static_cast<nefii::SdfNet*>(handle)->workspace_bytes(rows_cap, with_grad != 0);
 }
 int nefii_sdf_eval(void* handle, void* stream, int rows_cap, const int32_t* count, const float* x, void* workspace,
-                   int64_t workspace_bytes, float* sdf, float* feat, float* grad) {
+                   int64_t workspace_bytes, float* sdf, float* feat, float* grad, int k_flush) {
   if (!handle) return nefii::set_error(NEFII_ERR_ARG, "nefii_sdf_eval: null handle");
   return static_cast<nefii::SdfNet*>(handle)->eval((cudaStream_t)stream, rows_cap, count, x, workspace,
-                                                   (size_t)workspace_bytes, sdf, feat, grad);
+                                                   (size_t)workspace_bytes, sdf, feat, grad, k_flush);
 }
 
 static nefii::SdfSource make_source(int sdf_kind, const void* sdf, int n_prims) {
@@ -148,6 +151,9 @@ int nefii_ray_trace(void* stream, const nefii_trace_config* cfg, int sdf_kind, c
                           object_mask, flags, linspace, uniforms, workspace, (size_t)workspace_bytes, points, hit, dists,
                           (long long*)stats);
 }
+int nefii_trace_set_tiers(int march_flush, int bulk_flush) { return nefii::trace_set_tiers(march_flush, bulk_flush); }
+int nefii_trace_set_graph_mode(int mode) { return nefii::trace_set_graph_mode(mode); }
+int nefii_trace_graph_clear(void) { return nefii::trace_graph_clear(); }
 int nefii_analytic_sdf_eval(void* stream, const float* prims, int n_prims, int n, const float* x, float* sdf) {
   return nefii::analytic_sdf_eval((cudaStream_t)stream, prims, n_prims, n, nullptr, x, sdf);
 }

@@ -38,11 +38,14 @@ int set_error(int code, const char* fmt, ...);
                                 cudaGetErrorString(e__), __FILE__, __LINE__);              \
   } while (0)
 
-// number of kernels this library has launched (nefii_launch_count); bumped by NEFII_LAUNCH_CHECK
+// number of kernels this library has launched (nefii_launch_count); bumped by NEFII_LAUNCH_CHECK.  Replays of a captured
+// trace graph add the kernels of one trip through each of its loops (tracer_graph.cu).
 void count_launch();
+long long launches();
+void add_launches(long long n);
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (grid sizing default; launchers that depend on it read the device attribute)
 
 }  // namespace nefii

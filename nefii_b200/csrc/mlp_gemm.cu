@@ -13,6 +13,9 @@
 //   warp 8      : TMA producer (A/B hi+lo tiles, 128B swizzle, mbarrier ring)
 //   warp 9      : TMEM allocator + single-thread tcgen05.mma issuer (2 x 256-column partial-sum buffers)
 // Two instantiations: single CTA (cta_group::1, M = 128) and CTA pairs (cta_group::2, M = 256 over two SMs).
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 #include "mlp_gemm_kernel.cuh"
 
@@ -37,7 +40,29 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_map(CUtensorMap* map, const void* base, int rows, int ld, int k_extent, int box_rows, int bk) {
+// Encoded tensor maps are pure functions of their arguments: a per-thread cache takes cuTensorMapEncodeTiled (six calls per
+// launch otherwise) off the host path of the launch-bound phases.
+struct MapKey {
+  const void* base; int rows, ld, ext, box_rows, bk;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && ld == o.ld && ext == o.ext && box_rows == o.box_rows && bk == o.bk;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)(uintptr_t)k.base * 0x9E3779B97F4A7C15ull;
+    h ^= ((size_t)k.rows << 32) ^ ((size_t)k.ld << 8) ^ ((size_t)k.ext << 20) ^ ((size_t)k.box_rows << 44) ^ (size_t)k.bk;
+    return h ^ (h >> 29);
+  }
+};
+typedef std::unordered_map<MapKey, CUtensorMap, MapKeyHash> MapCache;
+MapCache& map_cache() {
+  static thread_local MapCache cache;
+  if (cache.size() > 8192) cache.clear();
+  return cache;
+}
+
+int make_map_uncached(CUtensorMap* map, const void* base, int rows, int ld, int k_extent, int box_rows, int bk) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(NEFII_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
@@ -51,8 +76,28 @@ int make_map(CUtensorMap* map, const void* base, int rows, int ld, int k_extent,
   return NEFII_OK;
 }
 
+int make_map(CUtensorMap* map, const void* base, int rows, int ld, int k_extent, int box_rows, int bk) {
+  MapCache& c = map_cache();
+  const MapKey key{base, rows, ld, k_extent, box_rows, bk};
+  auto it = c.find(key);
+  if (it != c.end()) { *map = it->second; return NEFII_OK; }
+  const int rc = make_map_uncached(map, base, rows, ld, k_extent, box_rows, bk);
+  if (!rc) c.emplace(key, *map);
+  return rc;
+}
+
+int make_store_map_uncached(CUtensorMap* map, const void* base, int rows, int ld, int cols);
 // [rows, cols] bf16 plane view (row stride ld) for the epilogue's 32 x 32 bulk stores out of 64 B-swizzled staging tiles
 int make_store_map(CUtensorMap* map, const void* base, int rows, int ld, int cols) {
+  MapCache& c = map_cache();
+  const MapKey key{base, rows, ld, cols, 32, -1};
+  auto it = c.find(key);
+  if (it != c.end()) { *map = it->second; return NEFII_OK; }
+  const int rc = make_store_map_uncached(map, base, rows, ld, cols);
+  if (!rc) c.emplace(key, *map);
+  return rc;
+}
+int make_store_map_uncached(CUtensorMap* map, const void* base, int rows, int ld, int cols) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(NEFII_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -120,24 +165,62 @@ struct ProfRec {
 };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
+std::atomic<long long> g_epoch{0};
+std::mutex g_dev_mu;
+bool g_dev_ready[64] = {};
+int g_dev_sms[64] = {};
+}  // namespace
+
+long long gemm_config_epoch() { return g_epoch.load(std::memory_order_relaxed); }
+bool gemm_profile_active() { return g_prof_on; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: every device this process launches on
+// gets its own opt-in (and its own SM count for the persistent grids).
+int gemm_prepare_device() {
+  int dev = 0;
+  NEFII_CUDA(cudaGetDevice(&dev));
+  NEFII_CHECK_ARG(dev >= 0 && dev < 64, "gemm: device index out of range");
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  if (g_dev_ready[dev]) return NEFII_OK;
+  for (int key = 0; key < 12; ++key) {
+    GemmKernelFn f1 = select_gemm_kernel<1>(key);
+    GemmKernelFn f2 = reinterpret_cast<GemmKernelFn>(gemm_pair_kernel(key));
+    if (f1) NEFII_CUDA(cudaFuncSetAttribute(f1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    if (f2) NEFII_CUDA(cudaFuncSetAttribute(f2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  }
+  int sms = 0;
+  NEFII_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  g_dev_sms[dev] = sms > 0 ? sms : kNumSMs;
+  g_dev_ready[dev] = true;
+  return NEFII_OK;
+}
+namespace {
+int device_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_dev_ready[dev]) return kNumSMs;
+  return g_dev_sms[dev];
+}
 }  // namespace
 
 int gemm_set_cluster(int cl) {
   NEFII_CHECK_ARG(cl == 1 || cl == 2, "gemm_set_cluster: 1 (single CTA) or 2 (cta_group::2 pair)");
   g_cluster_pref = cl;
+  ++g_epoch;
   return NEFII_OK;
 }
 
-int gemm_set_debug(int mask) { g_debug = mask; return NEFII_OK; }
+int gemm_set_debug(int mask) { g_debug = mask; ++g_epoch; return NEFII_OK; }
 int gemm_set_k_flush(int k) {
   NEFII_CHECK_ARG(k >= 1 && k <= 64, "gemm_set_k_flush: out of range");
   g_k_flush = k;
   g_k_flush_head = k;
+  ++g_epoch;
   return NEFII_OK;
 }
 int gemm_set_k_flush_head(int k) {
   NEFII_CHECK_ARG(k >= 1 && k <= 64, "gemm_set_k_flush_head: out of range");
   g_k_flush_head = k;
+  ++g_epoch;
   return NEFII_OK;
 }
 
@@ -178,11 +261,14 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   NEFII_CHECK_ARG(p.a_ld % 8 == 0 && p.b_ld % 8 == 0, "gemm_split_bf16: leading dimensions must be multiples of 8");
   NEFII_CHECK_ARG(p.epi.n_valid > 0 && p.epi.n_valid <= p.n_pad, "gemm_split_bf16: n_valid out of range");
   NEFII_CHECK_ARG(p.epi.n_last <= kMaxLast, "gemm_split_bf16: fused output layer supports at most %d outputs", kMaxLast);
+  NEFII_CHECK_ARG(p.k_flush >= 0 && p.k_flush <= 64, "gemm_split_bf16: k_flush out of range");
   if (p.rows_cap <= 0) return NEFII_OK;
+  int rc;
+  if ((rc = gemm_prepare_device())) return rc;
+  const int n_sms = device_sms();
   const int m_tiles = ceil_div(p.rows_cap, BM);
   const int cl = (g_cluster_pref == 2 && m_tiles >= 2) ? 2 : 1;   // CTA pairs need two row tiles to work on
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  int rc;
   const int bk = cl == 2 ? Ring<2>::kBK : Ring<1>::kBK;
   if ((rc = make_map(&ma_hi, p.a_hi, p.rows_cap, p.a_ld, p.k_pad, BM, bk))) return rc;
   if ((rc = make_map(&ma_lo, p.a_lo, p.rows_cap, p.a_ld, p.k_pad, BM, bk))) return rc;
@@ -205,7 +291,7 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   NEFII_CHECK_ARG(p.epi.mode == 0 || p.epi.sav_hi == nullptr || p.epi.sav_ld >= n_chunks * BN || p.epi.sav_ncols % 32 == 0,
                   "gemm_split_bf16: saved-activation rows must cover whole 32-column groups");
   int grid = ceil_div(m_tiles, cl) * cl;
-  if (grid > kNumSMs) grid = kNumSMs / cl * cl;   // persistent CTAs: one per SM, looping over row tiles
+  if (grid > n_sms) grid = n_sms / cl * cl;   // persistent CTAs: one per SM, looping over row tiles
   GemmKernelFn fn = nullptr;
   const bool fuse = p.epi.mode == 0 && p.epi.w_last != nullptr;
   NEFII_CHECK_ARG(!fuse || (p.epi.dst_last != nullptr && p.epi.n_last >= 1), "gemm_split_bf16: fused output layer needs dst_last");
@@ -213,11 +299,6 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   const int key = ((cl == 2) ? 12 : 0) + (fuse ? 8 : 0) + p.epi.mode * 4 + p.epi.act;
   fn = cl == 2 ? reinterpret_cast<GemmKernelFn>(gemm_pair_kernel(key % 12)) : select_gemm_kernel<1>(key % 12);
   if (fn == nullptr) return set_error(NEFII_ERR_ARG, "gemm_split_bf16: bad mode/act (%d/%d)", p.epi.mode, p.epi.act);
-  static bool attr_set[36] = {};
-  if (!attr_set[key]) {
-    NEFII_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_set[key] = true;
-  }
   const int k_blocks = p.k_pad / BK;
   int splits = p.k_splits > 1 ? p.k_splits : 1;
   if (splits > k_blocks) splits = k_blocks;
@@ -252,7 +333,8 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     NEFII_CUDA(cudaLaunchKernelEx(&cfg, fn, ma_hi, ma_lo, mb_hi, mb_lo, md_hi, md_lo, store_tma, p.count, p.rows_cap, k_blocks, n_chunks, kb_per,
-                                  (long long)p.f32_split_stride, g_debug, g_k_flush | (g_k_flush_head << 8), p.epi));
+                                  (long long)p.f32_split_stride, g_debug,
+                                  p.k_flush > 0 ? (p.k_flush | (p.k_flush << 8)) : (g_k_flush | (g_k_flush_head << 8)), p.epi));
   }
   if (rec) NEFII_CUDA(cudaEventRecord(rec->b, stream));
   NEFII_LAUNCH_CHECK();

@@ -25,6 +25,8 @@ struct GemmEpilogue {
   int dst_col0 = 0;
   int dst_ncols = 0;
   int dst_zero_to = 0;      // plane columns [dst_ncols, dst_zero_to) are written as zeros
+  int dst_pad_ok = 0;       // 1: plane columns [dst_ncols, round_up(dst_ncols, 128)) may be overwritten with finite garbage
+                            // (the caller fills them afterwards): a ragged last column span then stays on the fast epilogue
   // optional fp32 copy of columns [f32_begin, f32_end): dst_f32[m * f32_ld + n - f32_begin]
   float* dst_f32 = nullptr;
   int f32_ld = 0, f32_begin = 0, f32_end = 0;
@@ -52,6 +54,7 @@ struct GemmProblem {
   int k_splits = 1;         // >1: split-K over gridDim.y, partial s is written to dst_f32 + s * f32_split_stride
   long long f32_split_stride = 0;
   int* k_splits_used = nullptr;   // host out: number of partials actually produced
+  int k_flush = 0;          // K blocks per TMEM partial for this launch (accuracy tier); 0: the library default
   GemmEpilogue epi;
 };
 
@@ -68,6 +71,11 @@ int gemm_set_k_flush(int k);
 int gemm_set_k_flush_head(int k);
 int gemm_profile_enable(int on);
 int gemm_profile_fetch(double* out3);
+bool gemm_profile_active();
+// per-device one-time set-up (dynamic shared memory opt-in of every kernel variant, SM count); cheap when already done
+int gemm_prepare_device();
+// bumped by every setter above: anything that caches launches (trace graphs) keys on it
+long long gemm_config_epoch();
 
 // fp32 [rows, cols] (row stride ld_src) -> zero-padded bf16 planes [rows_pad, cols_pad];
 // transpose=1 writes src^T.

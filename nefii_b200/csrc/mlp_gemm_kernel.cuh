@@ -747,6 +747,8 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     fs.map_lo = &map_d_lo;
     fs.st_u32 = smem_u32(stage_out);
     const int n_loop = epi.dst_zero_to > epi.n_valid ? epi.dst_zero_to : epi.n_valid;
+    const int n_real = epi.n_valid < epi.dst_ncols ? epi.n_valid : epi.dst_ncols;
+    const int n_fast = epi.dst_pad_ok ? (n_real + kColsPerWarp - 1) / kColsPerWarp * kColsPerWarp : n_real;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kColsPerWarp);
     float acc[kColsPerWarp];
     const PartSched sched{(k_flush >> 8) ? (k_flush >> 8) : (k_flush & 255), k_flush & 255, k_blocks};
@@ -795,7 +797,9 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       }
       const int n_span0 = nc * BN + half * kColsPerWarp;
       if (dbg & 1) continue;
-      if (fast_layer && n_span0 + kColsPerWarp <= epi.n_valid && n_span0 + kColsPerWarp <= epi.dst_ncols) {
+      // dst_pad_ok: the plane columns up to the next multiple of 128 belong to this layer too (zero weights, zero bias; the
+      // bulk store clips at the tensor map's extent dst_ncols, the predicated path may overwrite them: the caller refills them)
+      if (fast_layer && n_span0 + kColsPerWarp <= n_fast) {
         // whole 32-row tiles leave by bulk tensor store; the ragged last tile keeps per-row predicates
         if (store_tma && row - lane + 32 <= m_limit)
           finish_span_fast<ACT, true>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg);

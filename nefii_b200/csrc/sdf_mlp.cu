@@ -239,7 +239,7 @@ size_t SdfNet::workspace_bytes(int rows_cap, bool with_grad) const {
 }
 
 int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const float* x, void* workspace, size_t ws_bytes,
-                 float* sdf, float* feat, float* grad) const {
+                 float* sdf, float* feat, float* grad, int k_flush) const {
   const Impl& s = *impl_;
   NEFII_CHECK_ARG(s.has_weights, "sdf: eval before set_weights");
   if (rows_cap <= 0) return NEFII_OK;
@@ -279,12 +279,8 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
   Planes seed;  // gradient seed G_{H-1}
   if (with_grad) seed = act[H - 1];
   for (int l = 0; l < H; ++l) {
-    if (l + 1 == skip) {
-      // the skip layer's input = [h / sqrt2 | PE / sqrt2]; its PE columns are free from now on
-      encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, kInvSqrt2, in_of(skip), W - s.d_pe, 0);
-      NEFII_LAUNCH_CHECK();
-    }
     GemmProblem g{};
+    g.k_flush = k_flush;
     const Planes& a = (l == 0) ? in0 : in_of(l);
     g.a_hi = a.hi; g.a_lo = a.lo; g.a_ld = a.ld; g.rows_cap = rows_cap;
     g.b_hi = s.w_fwd[l].hi; g.b_lo = s.w_fwd[l].lo; g.b_ld = s.w_fwd[l].ld; g.n_pad = s.n_pad[l];
@@ -298,6 +294,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
       g.epi.dst = in_of(l + 1);
       g.epi.dst_ncols = s.out_dim[l];
       g.epi.out_scale = (l + 1 == skip) ? kInvSqrt2 : 1.f;
+      g.epi.dst_pad_ok = (l + 1 == skip) ? 1 : 0;   // the PE columns next to h are written right after this layer
     } else {
       g.epi.w_last = s.w_last; g.epi.b_last = s.b_last; g.epi.n_last = s.cfg.d_out; g.epi.w_last_ld = W;
       g.epi.dst_last = sdf;
@@ -305,6 +302,11 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
       if (with_grad) g.epi.seed = seed;
     }
     if ((rc = gemm_split_bf16(stream, g))) return rc;
+    if (l + 1 == skip) {
+      // the skip layer's input = [h / sqrt2 | PE / sqrt2]: the encoding goes next to the h columns the GEMM just wrote
+      encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, kInvSqrt2, in_of(skip), W - s.d_pe, 0);
+      NEFII_LAUNCH_CHECK();
+    }
   }
   if (!with_grad) return NEFII_OK;
 
@@ -314,6 +316,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
   Planes spare = act[H];
   for (int l = H - 1; l >= 1; --l) {
     GemmProblem g{};
+    g.k_flush = k_flush;
     g.a_hi = cur.hi; g.a_lo = cur.lo; g.a_ld = cur.ld; g.rows_cap = rows_cap;
     g.b_hi = s.w_bwd[l].hi; g.b_lo = s.w_bwd[l].lo; g.b_ld = s.w_bwd[l].ld; g.n_pad = round_up(s.in_dim[l], 256);
     g.k_pad = round_up(s.out_dim[l], 64);
@@ -339,6 +342,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
   }
   {
     GemmProblem g{};   // layer 0: gradient w.r.t. the encoding, fp32 out
+    g.k_flush = k_flush;
     g.a_hi = cur.hi; g.a_lo = cur.lo; g.a_ld = cur.ld; g.rows_cap = rows_cap;
     g.b_hi = s.w_bwd[0].hi; g.b_lo = s.w_bwd[0].lo; g.b_ld = s.w_bwd[0].ld; g.n_pad = round_up(s.in_dim[0], 256);
     g.k_pad = round_up(s.out_dim[0], 64);

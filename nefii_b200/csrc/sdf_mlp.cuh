@@ -21,9 +21,10 @@ class SdfNet {
   // weights[l]: device fp32 [out_l, in_l] (weight-norm already folded), biases[l]: [out_l]; l = 0..n_hidden
   int set_weights(cudaStream_t stream, const float* const* weights, const float* const* biases);
   size_t workspace_bytes(int rows_cap, bool with_grad) const;
-  // x [rows,3] -> sdf [rows], feat [rows,width] (optional), grad [rows,3] (optional)
+  // x [rows,3] -> sdf [rows], feat [rows,width] (optional), grad [rows,3] (optional).  k_flush: K blocks per TMEM partial of
+  // the layer GEMMs (accuracy tier, see gemm_set_k_flush); 0 = the library default.
   int eval(cudaStream_t stream, int rows_cap, const int* count, const float* x, void* workspace, size_t ws_bytes,
-           float* sdf, float* feat, float* grad) const;
+           float* sdf, float* feat, float* grad, int k_flush = 0) const;
   const SdfConfig& config() const;
 
  private:

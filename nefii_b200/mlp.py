@@ -19,7 +19,14 @@ import torch
 from . import _lib, ops
 
 c_void_p = ctypes.c_void_p
-_NUM_SMS = 148
+# accuracy tier of the forward layer GEMMs of the trainable stacks (K blocks per TMEM partial; 1 = most accurate, 0 = library
+# default): their outputs are the radiance / albedo / roughness the parity tolerances are stated on, and they run on surface
+# points only (a few percent of a step), so they take the accurate tier; the backward GEMMs keep the default.
+FWD_FLUSH = 1
+
+
+def _num_sms(device):
+    return torch.cuda.get_device_properties(device).multi_processor_count
 
 
 def _planes(rows, cols, device):
@@ -74,7 +81,7 @@ class _DenseMlp(torch.autograd.Function):
     layer s-1 then has width - d_in outputs."""
 
     @staticmethod
-    def forward(ctx, act, seg_freqs, n_hidden, skip, skip_scale, want_hidden, *tensors):
+    def forward(ctx, act, seg_freqs, n_hidden, skip, skip_scale, want_hidden, need_grad, *tensors):
         n_seg = len(seg_freqs)
         seg_src = tensors[:n_seg]
         params = tensors[n_seg:]
@@ -87,7 +94,6 @@ class _DenseMlp(torch.autograd.Function):
         assert d_in == Ws[0].shape[1], (d_in, Ws[0].shape)
         n_out = Ws[-1].shape[0]
         assert n_out <= 4
-        need_grad = any(p.requires_grad for p in params)
         y = torch.empty(n, n_out, device=dev, dtype=torch.float32)
         ctx.n_seg = n_seg
         hidden = torch.empty(n if want_hidden else 0, Ws[-1].shape[1], device=dev, dtype=torch.float32)
@@ -119,16 +125,17 @@ class _DenseMlp(torch.autograd.Function):
                 enc_hi = enc.to(torch.bfloat16)
                 dst[0][:, out_dim:out_dim + d_in] = enc_hi
                 dst[1][:, out_dim:out_dim + d_in] = (enc - enc_hi.float()).to(torch.bfloat16)
-                ops.gemm_split_bf16(a, wp, k_pad, out_dim, act=act, bias=bias, out_scale=skip_scale, dst=dst, dst_ncols=out_dim)
+                ops.gemm_split_bf16(a, wp, k_pad, out_dim, act=act, bias=bias, out_scale=skip_scale, dst=dst, dst_ncols=out_dim,
+                                    k_flush=FWD_FLUSH)
             elif l < n_hidden - 1:
                 dst = _planes(n, ops.round_up(out_dim, 64), dev)
                 ops.gemm_split_bf16(a, wp, k_pad, out_dim, act=act, bias=bias, dst=dst, dst_ncols=out_dim,
-                                    dst_zero_to=ops.round_up(out_dim, 64))
+                                    dst_zero_to=ops.round_up(out_dim, 64), k_flush=FWD_FLUSH)
             else:
                 dst = _planes(n, ops.round_up(out_dim, 64), dev) if (need_grad or want_hidden) else None
                 ops.gemm_split_bf16(a, wp, k_pad, out_dim, act=act, bias=bias, dst=dst, dst_ncols=out_dim if dst else 0,
                                     dst_zero_to=ops.round_up(out_dim, 64) if dst else 0,
-                                    w_last=w_last, b_last=b_last, dst_last=y)
+                                    w_last=w_last, b_last=b_last, dst_last=y, k_flush=FWD_FLUSH)
             if need_grad or l < n_hidden - 1:
                 if not need_grad:
                     acts = [dst]          # ping-pong: drop what is no longer needed
@@ -141,7 +148,7 @@ class _DenseMlp(torch.autograd.Function):
             ctx.acts = acts                # in0, h_1 .. h_L (planes)
             ctx.weights = packed           # effective fp32 hidden weights
             ctx.w_last = w_last
-            ctx.needs = [p.requires_grad for p in params]
+            ctx.needs = [ctx.needs_input_grad[7 + n_seg + i] for i in range(len(params))]
         if want_hidden:
             # the last hidden activation (ImplicitNetwork's feature vector), rebuilt from its two bf16 planes; no gradient
             torch.add(dst[0][:, :hidden.shape[1]].float(), dst[1][:, :hidden.shape[1]].float(), out=hidden)
@@ -149,9 +156,12 @@ class _DenseMlp(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy, _g_hidden=None):
-        n_lead = 6
+        n_lead = 7
         if ctx.empty:
             return (None,) * (n_lead + ctx.n_seg) + tuple(torch.zeros(s, device=gy.device) for s in ctx.shapes)
+        if ctx.acts is None:
+            raise _lib.NefiiError("dense_mlp: backward called a second time; the activation planes are released after the first "
+                                  "pass (retain_graph is not supported on this path)")
         act, L, n = ctx.act, ctx.n_hidden, ctx.n
         dev = gy.device
         gy = _lib.f32c(gy)
@@ -177,7 +187,8 @@ class _DenseMlp(torch.autograd.Function):
             GT = transpose_planes(G, n, out_dim, n_pad, ops.round_up(out_dim, 128), col_sum=gb)
             h_prev = acts[l]
             HT = transpose_planes(h_prev, n, in_dim, n_pad, ops.round_up(in_dim, 256))
-            splits = max(1, min(n_pad // 128, (_NUM_SMS + (GT[0].shape[0] // 128) - 1) // (GT[0].shape[0] // 128)))
+            n_sms = _num_sms(dev)
+            splits = max(1, min(n_pad // 128, (n_sms + (GT[0].shape[0] // 128) - 1) // (GT[0].shape[0] // 128)))
             partial = torch.empty(splits, out_dim, in_dim, device=dev, dtype=torch.float32)
             used = ops.gemm_split_bf16(GT, HT, n_pad, in_dim, dst_f32=partial, f32_begin=0, f32_end=in_dim,
                                        f32_ld=in_dim, k_splits=splits, f32_split_stride=out_dim * in_dim,
@@ -221,5 +232,8 @@ def dense_mlp(segments, weights, biases, act, skip=0, skip_scale=1.0, want_hidde
     params = []
     for w, b in zip(weights, biases):
         params += [w, b]
-    y, hidden = _DenseMlp.apply(act, seg_freqs, len(weights) - 1, int(skip), float(skip_scale), bool(want_hidden), *seg_src, *params)
+    # bias Parameters keep requires_grad under torch.no_grad(): the activation planes are only kept when a backward can follow
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    y, hidden = _DenseMlp.apply(act, seg_freqs, len(weights) - 1, int(skip), float(skip_scale), bool(want_hidden), need_grad,
+                                *seg_src, *params)
     return (y, hidden) if want_hidden else y

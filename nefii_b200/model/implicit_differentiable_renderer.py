@@ -118,11 +118,30 @@ class ImplicitNetwork(nn.Module):
             raise _lib.NefiiError("nefii_b200: the SDF network runs inference-only on the accelerated path; call "
                                   "model.freeze_geometry() (step 2 / rendering) or wrap the call in torch.no_grad()")
 
+    # accuracy tier of the stand-alone evaluations (sdf_output, features, normals: direct outputs of the renderer):
+    # one K block per TMEM partial, the most accurate setting of the layer GEMM (csrc/mlp_gemm.cu)
+    EVAL_FLUSH = 1
+
     def evaluate(self, x, want_feat=False, want_grad=False):
         """Fused pass: (sdf [N], feature [N,W] | None, d sdf/dx [N,3] | None)."""
         self._check_frozen()
         net = self._sync(x.device)
-        return net.eval(x.detach(), want_feat=want_feat, want_grad=want_grad)
+        return net.eval(x.detach(), want_feat=want_feat, want_grad=want_grad, k_flush=self.EVAL_FLUSH)
+
+    def invalidate(self):
+        """Drop the packed copy of the weights.  The cache is keyed on the parameters' (data_ptr, _version): in-place edits
+        through `.data` (checkpoint surgery, converters) do not bump the version -- call this after such edits."""
+        self._packed_versions = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
 
     def _trainable(self):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
@@ -322,6 +341,9 @@ class IDRNetwork(nn.Module):
         ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics)
         batch_size, num_pixels, _ = ray_dirs.shape
 
+        if pose.requires_grad or intrinsics.requires_grad:
+            raise _lib.NefiiError("nefii_b200: camera parameters that require grad (--train_cameras) are outside the "
+                                  "accelerated path: surface points are computed without a graph")
         with torch.no_grad():
             points, network_object_mask, dists = self.ray_tracer(sdf=self.implicit_network, cam_loc=cam_loc,
                                                                  object_mask=object_mask, ray_directions=ray_dirs,
@@ -331,34 +353,42 @@ class IDRNetwork(nn.Module):
             sdf_output = sdf_all.unsqueeze(-1)
         ray_dirs = ray_dirs.reshape(-1, 3)
         surface_mask = network_object_mask
-        differentiable_surface_points = points[surface_mask]
+        n_rays = points.shape[0]
+        # host sync 1 of 2 per forward: the number of surface hits sizes everything downstream.  All gathers / scatters below
+        # use the index list (index_select / index_copy): no further boolean-mask round trips.
+        surface_idx = torch.nonzero(surface_mask).squeeze(1)
+        n_hit = surface_idx.shape[0]
+        differentiable_surface_points = points.index_select(0, surface_idx)
         grad_theta = None
 
         ones = torch.ones_like(points)
-        idr_rgb_values, sg_rgb_values, normal_values = ones.clone(), ones.clone(), ones.clone()
-        sg_diffuse_rgb_values, sg_diffuse_albedo_values = ones.clone(), ones.clone()
+        idr_rgb_values, sg_rgb_values, normal_values = ones, ones, ones
+        sg_diffuse_rgb_values, sg_diffuse_albedo_values = ones, ones
         sg_specular_rgb_values = torch.zeros_like(points)
         sg_roughness_values = torch.zeros_like(points[..., 0:1])
-        sg_specular_reflection_values = torch.zeros_like(points)
+        sg_specular_reflection_values = sg_specular_rgb_values
         ret = {}
-        if differentiable_surface_points.shape[0] > 0:
-            view_dirs = -ray_dirs[surface_mask]
+        if n_hit > 0:
+            view_dirs = -ray_dirs.index_select(0, surface_idx)
             ret = self.get_rbg_value(differentiable_surface_points, view_dirs, uniforms=uniforms)
-            idr_rgb_values = idr_rgb_values.index_put((surface_mask,), ret['idr_rgb'])
-            sg_rgb_values = sg_rgb_values.index_put((surface_mask,), ret['sg_rgb'])
-            normal_values = normal_values.index_put((surface_mask,), ret['normals'])
-            sg_diffuse_rgb_values = sg_diffuse_rgb_values.index_put((surface_mask,), ret['sg_diffuse_rgb'])
-            sg_diffuse_albedo_values = sg_diffuse_albedo_values.index_put((surface_mask,), ret['sg_diffuse_albedo'])
-            sg_specular_rgb_values = sg_specular_rgb_values.index_put((surface_mask,), ret['sg_specular_rgb'])
-            sg_roughness_values = sg_roughness_values.index_put((surface_mask,), ret['sg_roughness'])
+            idr_rgb_values = ones.index_copy(0, surface_idx, ret['idr_rgb'])
+            sg_rgb_values = ones.index_copy(0, surface_idx, ret['sg_rgb'])
+            normal_values = ones.index_copy(0, surface_idx, ret['normals'])
+            sg_diffuse_rgb_values = ones.index_copy(0, surface_idx, ret['sg_diffuse_rgb'])
+            sg_diffuse_albedo_values = ones.index_copy(0, surface_idx, ret['sg_diffuse_albedo'])
+            sg_specular_rgb_values = sg_specular_rgb_values.index_copy(0, surface_idx, ret['sg_specular_rgb'])
+            sg_roughness_values = sg_roughness_values.index_copy(0, surface_idx, ret['sg_roughness'])
             spec = ret['sg_specular_reflectance']
-            sg_specular_reflection_values = sg_specular_reflection_values.index_put(
-                (surface_mask,), spec.expand(differentiable_surface_points.shape[0], 3))
+            sg_specular_reflection_values = torch.zeros_like(points).index_copy(0, surface_idx, spec.expand(n_hit, 3))
+        else:   # distinct tensors per output key, as the reference returns
+            idr_rgb_values, sg_rgb_values, normal_values = ones.clone(), ones.clone(), ones.clone()
+            sg_diffuse_rgb_values, sg_diffuse_albedo_values = ones.clone(), ones.clone()
+            sg_specular_reflection_values = torch.zeros_like(points)
 
-        background_mask = ~surface_mask
-        if self.render_background and bool(background_mask.any()):
-            background_rgb = self.get_background_rgb(ray_dirs[background_mask])
-            sg_rgb_values = sg_rgb_values.index_put((background_mask,), background_rgb)
+        if self.render_background and n_hit < n_rays:
+            background_idx = torch.nonzero_static(~surface_mask, size=n_rays - n_hit).squeeze(1)     # size known: no sync
+            background_rgb = self.get_background_rgb(ray_dirs.index_select(0, background_idx))
+            sg_rgb_values = sg_rgb_values.index_copy(0, background_idx, background_rgb)
 
         output = {
             'points': points,

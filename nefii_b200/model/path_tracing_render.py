@@ -30,15 +30,17 @@ def get_visibility_and_indirect_light(light_points, hit_mask, wi, model):
     """All three sample types at once.  light_points [3,N,3], hit_mask [3,N,1] bool, wi [3,N,3]
     -> incoming radiance [3,N,3] (zero where the secondary ray escaped); visibility is 1 - hit_mask."""
     m = hit_mask.reshape(-1)
-    xs = light_points.reshape(-1, 3)[m]
+    # host sync 2 of 2 per forward: the number of secondary hits sizes the radiance query
+    idx = torch.nonzero(m).squeeze(1)
     indirect = torch.zeros(light_points.shape, device=light_points.device, dtype=torch.float32).reshape(-1, 3)
-    if xs.shape[0] > 0:
+    if idx.shape[0] > 0:
+        xs = light_points.reshape(-1, 3).index_select(0, idx)
         _, feats, grads = model.implicit_network.evaluate(xs, want_feat=True, want_grad=True)
         normals = grads / (torch.norm(grads, dim=-1, keepdim=True) + 1e-6)
-        view = -wi.reshape(-1, 3)[m]
+        view = -wi.reshape(-1, 3).index_select(0, idx)
         view = view / (torch.norm(view, dim=-1, keepdim=True) + 1e-6)
         rgb = model.rendering_network(xs, normals, view, feats)
-        indirect = indirect.index_put((m,), rgb)
+        indirect = indirect.index_copy(0, idx, rgb)
     return indirect.reshape(light_points.shape)
 
 

@@ -85,7 +85,27 @@ def resolve_sdf_source(sdf):
     return src
 
 
+class _TraceBuffers:
+    """Persistent device buffers of one trace shape: the C side keys its CUDA-graph cache on the raw pointers, so inputs are
+    copied into (and outputs out of) tensors that stay where they are from call to call."""
+
+    def __init__(self, dev, n_batch, n_pix, n_steps):
+        n = n_batch * n_pix
+        self.cam = torch.empty(n_batch, 3, device=dev, dtype=torch.float32)
+        self.dirs = torch.empty(n_batch, n_pix, 3, device=dev, dtype=torch.float32)
+        self.obj = torch.empty(n, device=dev, dtype=torch.uint8)
+        self.uniforms = torch.empty(n_steps, device=dev, dtype=torch.float32)
+        self.points = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        self.hit = torch.empty(n, device=dev, dtype=torch.uint8)
+        self.dists = torch.empty(n, device=dev, dtype=torch.float32)
+
+
 class RayTracing(nn.Module):
+    # rays with their own origin (the integrator's secondary rays: n_pix == 1) are padded to a multiple of this many rays
+    # with rays that miss the bounding sphere, so that a slowly varying ray count replays the same CUDA graph
+    RAY_BUCKET = 8192
+    MAX_SHAPES = 8
+
     def __init__(
             self,
             object_bounding_sphere=1.0,
@@ -111,26 +131,49 @@ class RayTracing(nn.Module):
         self.collect_stats = False
         self._ws = None
         self._linspace = {}
+        self._bufs = {}
 
     def _config(self):
         return TraceConfig(self.object_bounding_sphere, self.sdf_threshold, self.line_search_step, self.line_step_iters,
                            self.sphere_tracing_iters, self.n_steps, self.n_rootfind_steps)
 
+    def _buffers(self, dev, n_batch, n_pix):
+        key = (dev, n_batch, n_pix)
+        b = self._bufs.pop(key, None)
+        if b is None:
+            while len(self._bufs) >= self.MAX_SHAPES:
+                self._bufs.pop(next(iter(self._bufs)))          # oldest shape
+            b = _TraceBuffers(dev, n_batch, n_pix, self.n_steps)
+        self._bufs[key] = b                                      # most recently used last
+        return b
+
     def forward(self, sdf, cam_loc, object_mask, ray_directions, uniforms=None, skip_min_sdf=None):
         kind, ptr, n_prims, keep = resolve_sdf_source(sdf)
         dev = ray_directions.device
+        if not ray_directions.is_cuda:
+            raise _lib.NefiiError("nefii_b200: expected CUDA tensors (no CPU path exists)")
         batch_size, num_pixels, _ = ray_directions.shape
         n_rays = batch_size * num_pixels
-        dirs = _lib.f32c(ray_directions)
-        cam = _lib.f32c(cam_loc).reshape(batch_size, 3)
-        obj = object_mask.reshape(-1).to(torch.uint8).contiguous() if object_mask is not None else None
-        points = torch.empty(n_rays, 3, device=dev, dtype=torch.float32)
-        hit = torch.empty(n_rays, device=dev, dtype=torch.uint8)
-        dists = torch.empty(n_rays, device=dev, dtype=torch.float32)
         if n_rays == 0:
-            return points, hit.bool(), dists
+            return (torch.empty(0, 3, device=dev), torch.empty(0, dtype=torch.bool, device=dev), torch.empty(0, device=dev))
+        # secondary-style rays: pad the batch to a bucket with rays that miss the bounding sphere
+        cap_batch = batch_size
+        if num_pixels == 1 and batch_size > 1:
+            cap_batch = (batch_size + self.RAY_BUCKET - 1) // self.RAY_BUCKET * self.RAY_BUCKET
+        bufs = self._buffers(dev, cap_batch, num_pixels)
+        bufs.cam[:batch_size].copy_(cam_loc.detach().reshape(batch_size, 3))
+        bufs.dirs[:batch_size].copy_(ray_directions.detach())
+        if cap_batch > batch_size:
+            far = 4.0 * float(self.object_bounding_sphere) + 1.0
+            bufs.cam[batch_size:] = torch.tensor([0.0, 0.0, far], device=dev)
+            bufs.dirs[batch_size:] = torch.tensor([0.0, 1.0, 0.0], device=dev)
+            bufs.obj[n_rays:].zero_()
+        have_mask = object_mask is not None
+        if have_mask:
+            bufs.obj[:n_rays].copy_(object_mask.reshape(-1))
         flags = 0
         skip = self.skip_min_sdf if skip_min_sdf is None else skip_min_sdf
+        have_uniforms = False
         if self.training:
             flags |= TRACE_TRAINING
             if skip:
@@ -139,25 +182,27 @@ class RayTracing(nn.Module):
                 # same draw as the reference (CPU generator, ray_tracing.py:316)
                 uniforms = torch.empty(self.n_steps).uniform_(0.0, 1.0)
         if uniforms is not None:
-            uniforms = uniforms.to(device=dev, dtype=torch.float32).contiguous()
+            bufs.uniforms.copy_(uniforms.detach().reshape(-1), non_blocking=True)
+            have_uniforms = True
         key = (self.n_steps, dev)
         if key not in self._linspace:
             self._linspace[key] = torch.linspace(0, 1, steps=self.n_steps).to(dev)   # CPU linspace, as the reference
         lin = self._linspace[key]
         cfg = self._config()
         lib = _lib.raw()
-        need = int(lib.nefii_trace_workspace_bytes(kind, c_void_p(ptr), n_rays, self.n_steps))
+        n_cap = cap_batch * num_pixels
+        need = int(lib.nefii_trace_workspace_bytes(kind, c_void_p(ptr), n_cap, self.n_steps))
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         stats = (ctypes.c_int64 * 8)() if self.collect_stats else None
         with torch.cuda.device(dev):
             _lib.check(lib.nefii_ray_trace(
-                _lib.stream_ptr(dev), ctypes.byref(cfg), kind, c_void_p(ptr), n_prims, batch_size, num_pixels,
-                cam.data_ptr(), dirs.data_ptr(), obj.data_ptr() if obj is not None else None, flags,
-                lin.data_ptr(), uniforms.data_ptr() if uniforms is not None else None,
-                self._ws.data_ptr(), self._ws.numel(), points.data_ptr(), hit.data_ptr(), dists.data_ptr(), stats))
+                _lib.stream_ptr(dev), ctypes.byref(cfg), kind, c_void_p(ptr), n_prims, cap_batch, num_pixels,
+                bufs.cam.data_ptr(), bufs.dirs.data_ptr(), bufs.obj.data_ptr() if have_mask else None, flags,
+                lin.data_ptr(), bufs.uniforms.data_ptr() if have_uniforms else None,
+                self._ws.data_ptr(), self._ws.numel(), bufs.points.data_ptr(), bufs.hit.data_ptr(), bufs.dists.data_ptr(), stats))
         if stats is not None:
             self.last_stats = dict(n_sampler=stats[0], n_rootfind=stats[1], n_min_sdf=stats[2], n_evals=stats[3],
-                                   n_sphere_hits=stats[4] // 2)
-        return points, hit.bool(), dists
+                                   n_rounds=stats[4])
+        return bufs.points[:n_rays].clone(), bufs.hit[:n_rays].bool(), bufs.dists[:n_rays].clone()

@@ -26,6 +26,7 @@ class GemmDesc(ctypes.Structure):
         ("seed_hi", c_void_p), ("seed_lo", c_void_p), ("seed_ld", c_int),
         ("sav_hi", c_void_p), ("sav_lo", c_void_p), ("sav_ld", c_int), ("sav_ncols", c_int), ("sav_scale", c_float),
         ("k_splits", c_int), ("f32_split_stride", ctypes.c_int64), ("k_splits_used", c_int),
+        ("k_flush", c_int), ("dst_pad_ok", c_int),
     ]
 
 
@@ -56,7 +57,7 @@ def split_to_planes(src, rows_pad=None, cols_pad=None, transpose=False, scale=1.
 def gemm_split_bf16(a, b, k_pad, n_valid, *, mode=0, act=ACT_NONE, bias=None, out_scale=1.0, count=None,
                     dst=None, dst_col0=0, dst_ncols=0, dst_zero_to=0, dst_f32=None, f32_begin=0, f32_end=0, f32_ld=None,
                     w_last=None, b_last=None, dst_last=None, seed=None, sav=None, sav_ncols=0, sav_scale=1.0,
-                    k_splits=1, f32_split_stride=0, rows_cap=None):
+                    k_splits=1, f32_split_stride=0, rows_cap=None, k_flush=0):
     """a=(hi,lo) activations planes [rows_cap, a_ld], b=(hi,lo) weight planes [n_pad, b_ld]."""
     d = GemmDesc()
     d.a_hi, d.a_lo, d.a_ld, d.rows_cap = _p(a[0]), _p(a[1]), a[0].stride(0), (a[0].shape[0] if rows_cap is None else rows_cap)
@@ -81,6 +82,7 @@ def gemm_split_bf16(a, b, k_pad, n_valid, *, mode=0, act=ACT_NONE, bias=None, ou
         d.sav_hi, d.sav_lo, d.sav_ld = _p(sav[0]), _p(sav[1]), sav[0].stride(0)
         d.sav_ncols, d.sav_scale = sav_ncols, sav_scale
     d.k_splits, d.f32_split_stride = k_splits, f32_split_stride
+    d.k_flush = k_flush
     _lib.check(_lib.raw().nefii_gemm_split_bf16(_lib.stream_ptr(a[0].device), ctypes.byref(d)))
     return d.k_splits_used
 
@@ -133,8 +135,9 @@ class SdfMlp:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def eval(self, x, want_feat=False, want_grad=False, count=None):
-        """x [N,3] -> (sdf [N], feat [N,width] | None, grad [N,3] | None)."""
+    def eval(self, x, want_feat=False, want_grad=False, count=None, k_flush=0):
+        """x [N,3] -> (sdf [N], feat [N,width] | None, grad [N,3] | None).  k_flush: accuracy tier (1 = most accurate,
+        0 = library default)."""
         x = _lib.f32c(x).reshape(-1, 3)
         n = x.shape[0]
         sdf = torch.empty(n, device=x.device, dtype=torch.float32)
@@ -146,5 +149,5 @@ class SdfMlp:
         with torch.cuda.device(self.device):
             _lib.check(_lib.raw().nefii_sdf_eval(
                 self._h, _lib.stream_ptr(self.device), n, _p(count), x.data_ptr(), ws.data_ptr(), ws.numel(),
-                sdf.data_ptr(), _p(feat), _p(grad)))
+                sdf.data_ptr(), _p(feat), _p(grad), int(k_flush)))
         return sdf, feat, grad
