@@ -131,20 +131,20 @@ class RayTracing(nn.Module):
         self.collect_stats = False
         self._ws = None
         self._linspace = {}
-        self._bufs = {}
+        self._shape_bufs = {}
 
     def _config(self):
         return TraceConfig(self.object_bounding_sphere, self.sdf_threshold, self.line_search_step, self.line_step_iters,
                            self.sphere_tracing_iters, self.n_steps, self.n_rootfind_steps)
 
-    def _buffers(self, dev, n_batch, n_pix):
+    def _shape_buffers(self, dev, n_batch, n_pix):
         key = (dev, n_batch, n_pix)
-        b = self._bufs.pop(key, None)
+        b = self._shape_bufs.pop(key, None)
         if b is None:
-            while len(self._bufs) >= self.MAX_SHAPES:
-                self._bufs.pop(next(iter(self._bufs)))          # oldest shape
+            while len(self._shape_bufs) >= self.MAX_SHAPES:
+                self._shape_bufs.pop(next(iter(self._shape_bufs)))          # oldest shape
             b = _TraceBuffers(dev, n_batch, n_pix, self.n_steps)
-        self._bufs[key] = b                                      # most recently used last
+        self._shape_bufs[key] = b                                      # most recently used last
         return b
 
     def forward(self, sdf, cam_loc, object_mask, ray_directions, uniforms=None, skip_min_sdf=None):
@@ -160,7 +160,7 @@ class RayTracing(nn.Module):
         cap_batch = batch_size
         if num_pixels == 1 and batch_size > 1:
             cap_batch = (batch_size + self.RAY_BUCKET - 1) // self.RAY_BUCKET * self.RAY_BUCKET
-        bufs = self._buffers(dev, cap_batch, num_pixels)
+        bufs = self._shape_buffers(dev, cap_batch, num_pixels)
         bufs.cam[:batch_size].copy_(cam_loc.detach().reshape(batch_size, 3))
         bufs.dirs[:batch_size].copy_(ray_directions.detach())
         if cap_batch > batch_size:
