@@ -86,6 +86,10 @@ typedef struct nefii_gemm_desc {
 
 int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* desc /* host */);
 
+/* Measurement aid (bench.py): `blocks` x 256 threads run `iters` rounds of 8 independent FP32 FMAs each
+ * (flops = blocks * 256 * iters * 16); timed by the caller with CUDA events -> the FP32 peak `fp32_fraction` is quoted against */
+int nefii_probe_fp32(void* stream, int blocks, int iters, float* sink);
+
 /* Measurement aid (bench.py roofline): while enabled, every nefii layer-GEMM launch is bracketed by CUDA events on its
  * own stream.  fetch() synchronises those events and returns {total ms, total algorithmic flops (2*rows*n*k, each
  * fp32 product counted once), number of launches}. */
@@ -101,6 +105,9 @@ int nefii_gemm_set_debug(int mask);
 int nefii_gemm_set_k_flush(int k_blocks);
 /* ... for the first two partial sums of every 256-column chunk only (set_k_flush resets it to the same value) */
 int nefii_gemm_set_k_flush_head(int k_blocks);
+/* first-order compensation of the tensor core's round-toward-zero accumulation: TMEM partial sums of `k_blocks` K blocks are
+ * scaled by (1 + rho) when they are added to the fp32 register accumulators; rho = 0 (default): plain sum */
+int nefii_gemm_set_trunc_comp(int k_blocks, float rho);
 int nefii_gemm_profile_fetch(double* out3 /* host */);
 
 /* fp32 [rows, cols] (row stride ld_src) -> zero-padded bf16 hi/lo planes [rows_pad, cols_pad];

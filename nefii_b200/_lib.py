@@ -21,11 +21,13 @@ SIGNATURES = {
     "nefii_sg_render_bwd": [c_void_p, c_int, c_int, c_int] + [c_void_p] * 15,
     "nefii_background_sg_fwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "nefii_gemm_split_bf16": [c_void_p, c_void_p],
+    "nefii_probe_fp32": [c_void_p, c_int, c_int, c_void_p],
     "nefii_gemm_profile_enable": [c_int],
     "nefii_gemm_set_cluster": [c_int],
     "nefii_gemm_set_debug": [c_int],
     "nefii_gemm_set_k_flush": [c_int],
     "nefii_gemm_set_k_flush_head": [c_int],
+    "nefii_gemm_set_trunc_comp": [c_int, c_float],
     "nefii_gemm_profile_fetch": [c_void_p],
     "nefii_assemble_input": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int],
     "nefii_transpose_planes": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

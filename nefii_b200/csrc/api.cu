@@ -47,6 +47,7 @@ int transpose_planes(cudaStream_t, const __nv_bfloat16*, const __nv_bfloat16*, i
 int last_layer_bwd(cudaStream_t, int, int, int, int, const float*, const float*, const __nv_bfloat16*, const __nv_bfloat16*, int,
                    __nv_bfloat16*, __nv_bfloat16*, int, float*, float*);
 int reduce_splits(cudaStream_t, const float*, int, long long, int, int, int, float*);
+int probe_fp32(cudaStream_t, int, int, float*);
 
 }  // namespace nefii
 
@@ -208,11 +209,13 @@ int nefii_reduce_splits(void* stream, const float* partial, int n_splits, int64_
   return nefii::reduce_splits((cudaStream_t)stream, partial, n_splits, (long long)stride, rows, ld_src, cols, out);
 }
 
+int nefii_probe_fp32(void* stream, int blocks, int iters, float* sink) { return nefii::probe_fp32((cudaStream_t)stream, blocks, iters, sink); }
 int nefii_gemm_profile_enable(int on) { return nefii::gemm_profile_enable(on); }
 int nefii_gemm_set_cluster(int cl) { return nefii::gemm_set_cluster(cl); }
 int nefii_gemm_set_debug(int mask) { return nefii::gemm_set_debug(mask); }
 int nefii_gemm_set_k_flush(int k) { return nefii::gemm_set_k_flush(k); }
 int nefii_gemm_set_k_flush_head(int k) { return nefii::gemm_set_k_flush_head(k); }
+int nefii_gemm_set_trunc_comp(int k_blocks, float rho) { return nefii::gemm_set_trunc_comp(k_blocks, rho); }
 int nefii_gemm_profile_fetch(double* out3) { return nefii::gemm_profile_fetch(out3); }
 
 int nefii_sg_render_bwd(void* stream, int n_rays, int n_sg, int n_mat, const float* lgt_sgs, const float* specular,

@@ -141,10 +141,12 @@ int env_int(const char* name, int dflt, int lo, int hi) {
   return (v >= lo && v <= hi) ? v : dflt;
 }
 // K blocks (of 64) accumulated inside TMEM before the sum moves to registers; see gemm_set_k_flush (NEFII_GEMM_KFLUSH
-// overrides the default at load, for A/B runs of whole programs).  Default 4: SDF-MLP error mean 6e-6 (2: 3e-6, 1: 2e-6; the
-// reference's own TF32-era matmuls are ~1e-4), hit masks identical to the oracle's in the parity scenes, and 10 % less time
-// per layer than 2 because only two partial sums per 256-column chunk have to be handed to the epilogue.
-constexpr int kDefaultKFlush = 4;
+// overrides the default at load, for A/B runs of whole programs).  Default 8 = a whole 512-wide layer per partial, the fastest
+// schedule (one hand-off per 256-column chunk).  Its truncation shortfall (22 ulp of 2^-24, systematic) is removed by the
+// first-order compensation below: measured SDF-MLP error vs f64 (tools/diag_gpu.py trunccomp, mean |err|) 1.9e-6 at 8 blocks
+// with compensation against 1.22e-5 without, 2.0e-6 at ONE block without and 1.6e-6 with -- what is left (1.9e-6 rms about
+// the mean at every setting) is the 16-bit operand representation of the bf16 hi/lo split, not the accumulation.
+constexpr int kDefaultKFlush = 8;
 int g_k_flush = env_int("NEFII_GEMM_KFLUSH", kDefaultKFlush, 1, 64);
 int g_store_tma = getenv("NEFII_GEMM_NO_TMA_STORE") ? 0 : 1;   // development switch for A/B timing
 int g_k_flush_head = env_int("NEFII_GEMM_KFLUSH", kDefaultKFlush, 1, 64);   // ... for the first two partials of a column chunk (gemm_set_k_flush_head)
@@ -166,6 +168,30 @@ struct ProfRec {
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 std::atomic<long long> g_epoch{0};
+// Relative shortfall of a TMEM partial sum of L K blocks (64 columns each).  tcgen05 aligns every addend to the accumulator and
+// truncates it towards zero, so a partial sum comes out short by a factor that depends on its length only.  Measured on B200
+// with `tools/diag_gpu.py trunccomp` (slope of the accumulation error against the exact sum of the three bf16 products, 16384 x
+// 512 x 512, Gaussian and all-positive activations agree to 3 %): 1.02 / 3.9 / 9.9 / 22.1 ulp of 2^-24 at 1 / 2 / 4 / 8 blocks.
+// Other lengths: log-log interpolation.  gemm_set_trunc_comp overrides an entry; NEFII_GEMM_TRUNC_COMP=0 switches it off.
+float default_rho(int L) {
+  static const float kL[4] = {1.f, 2.f, 4.f, 8.f};
+  static const float kRho[4] = {6.10e-8f, 2.34e-7f, 5.92e-7f, 1.32e-6f};
+  if (L <= 1) return kRho[0];
+  int i = 0;
+  while (i < 2 && (float)L > kL[i + 1]) ++i;
+  const float t = (logf((float)L) - logf(kL[i])) / (logf(kL[i + 1]) - logf(kL[i]));
+  return expf(logf(kRho[i]) + t * (logf(kRho[i + 1]) - logf(kRho[i])));
+}
+struct RhoTable {
+  float v[65];
+  RhoTable() {
+    const char* e = getenv("NEFII_GEMM_TRUNC_COMP");
+    const bool on = !(e && e[0] == '0');
+    v[0] = 0.f;
+    for (int L = 1; L <= 64; ++L) v[L] = on ? default_rho(L) : 0.f;
+  }
+};
+RhoTable g_trunc;
 std::mutex g_dev_mu;
 bool g_dev_ready[64] = {};
 int g_dev_sms[64] = {};
@@ -220,6 +246,14 @@ int gemm_set_k_flush(int k) {
 int gemm_set_k_flush_head(int k) {
   NEFII_CHECK_ARG(k >= 1 && k <= 64, "gemm_set_k_flush_head: out of range");
   g_k_flush_head = k;
+  ++g_epoch;
+  return NEFII_OK;
+}
+
+int gemm_set_trunc_comp(int k_blocks, float rho) {
+  NEFII_CHECK_ARG(k_blocks >= 1 && k_blocks <= 64, "gemm_set_trunc_comp: partial length out of range");
+  NEFII_CHECK_ARG(rho > -1e-3f && rho < 1e-3f, "gemm_set_trunc_comp: |rho| must be below 1e-3");
+  g_trunc.v[k_blocks] = rho;
   ++g_epoch;
   return NEFII_OK;
 }
@@ -332,9 +366,21 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
     attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    const int kf_tail = p.k_flush > 0 ? p.k_flush : g_k_flush;
+    const int kf_head = p.k_flush > 0 ? p.k_flush : g_k_flush_head;
+    // Partial schedule of a column chunk (PartSched): partials of kf K blocks, the last one takes what is left.  Split-K
+    // launches (kb_per blocks per split; the last split may be shorter) and head != tail schedules are compensated with the
+    // full-length factor only where the lengths are known to be uniform.
+    float scale_full = 1.0f, scale_last = 1.0f;
+    if (kf_head == kf_tail) {
+      const int len_full = kf_tail < kb_per ? kf_tail : kb_per;
+      const int n_parts = ceil_div(kb_per, len_full);
+      const int len_last = kb_per - (n_parts - 1) * len_full;
+      scale_full = 1.0f + g_trunc.v[len_full < 64 ? len_full : 64];
+      scale_last = (splits == 1) ? 1.0f + g_trunc.v[len_last < 64 ? len_last : 64] : scale_full;
+    }
     NEFII_CUDA(cudaLaunchKernelEx(&cfg, fn, ma_hi, ma_lo, mb_hi, mb_lo, md_hi, md_lo, store_tma, p.count, p.rows_cap, k_blocks, n_chunks, kb_per,
-                                  (long long)p.f32_split_stride, g_debug,
-                                  p.k_flush > 0 ? (p.k_flush | (p.k_flush << 8)) : (g_k_flush | (g_k_flush_head << 8)), p.epi));
+                                  (long long)p.f32_split_stride, g_debug, kf_tail | (kf_head << 8), scale_full, scale_last, p.epi));
   }
   if (rec) NEFII_CUDA(cudaEventRecord(rec->b, stream));
   NEFII_LAUNCH_CHECK();

@@ -69,6 +69,9 @@ int gemm_set_debug(int mask);
 // added to the fp32 register accumulators (round to nearest).  1 = most accurate, 2 = default, >= K/64 = everything in TMEM.
 int gemm_set_k_flush(int k);
 int gemm_set_k_flush_head(int k);
+// First-order compensation of the truncating accumulator: a TMEM partial sum of `k_blocks` K blocks is multiplied by
+// (1 + rho) when it is added to the register accumulators.  rho = 0 (default) leaves the sum untouched.
+int gemm_set_trunc_comp(int k_blocks, float rho);
 int gemm_profile_enable(int on);
 int gemm_profile_fetch(double* out3);
 bool gemm_profile_active();

@@ -544,7 +544,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const __grid_constant__ CUtensorMap map_d_hi, const __grid_constant__ CUtensorMap map_d_lo, int store_tma,
                        const int* __restrict__ count_ptr, int rows_cap, int k_blocks_total, int n_chunks, int kb_per_split,
-                       long long f32_split_stride, int dbg, int k_flush, const __grid_constant__ GemmEpilogue epi_in) {
+                       long long f32_split_stride, int dbg, int k_flush, float part_scale_full, float part_scale_last, const __grid_constant__ GemmEpilogue epi_in) {
   // Persistent over row tiles: CTA x handles tiles x, x + gridDim.x, ... so that the final epilogue math of one tile
   // overlaps the MMAs of the next (the pipelines and barrier phases simply keep running across tiles).
   const int m_tile0 = blockIdx.x;
@@ -780,12 +780,16 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
 #pragma unroll
           for (int q = 0; q < 4; ++q) tc_ld16_nowait(t_lane + (uint32_t)(buf * BN + hc * 64 + q * 16), r + q * 16);
           tc_wait_ld();
+          const float part_scale = (pi == parts_per_chunk - 1) ? part_scale_last : part_scale_full;
+          // part_scale = 1 + rho: first-order compensation of the tensor core's round-toward-zero accumulation (every addend
+          // is truncated towards zero when it is aligned to the accumulator: a partial sum comes out short by a factor that
+          // depends on its length only; gemm_set_trunc_comp).  1.0f reproduces the plain sum bit for bit.
           if (pi == 0) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) acc[hc * 64 + j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 64; ++j) acc[hc * 64 + j] = __uint_as_float(r[j]) * part_scale;
           } else {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) acc[hc * 64 + j] += __uint_as_float(r[j]);
+            for (int j = 0; j < 64; ++j) acc[hc * 64 + j] = fmaf(__uint_as_float(r[j]), part_scale, acc[hc * 64 + j]);
           }
         }
         tc_fence_before();
@@ -855,7 +859,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
 }
 
 using GemmKernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, int, const int*, int, int, int,
-                              int, long long, int, int, GemmEpilogue);
+                              int, long long, int, int, float, float, GemmEpilogue);
 
 // kernel of one (mode, act, fused-output-layer) combination for cluster size CL; key = fuse * 8 + mode * 4 + act
 template <int CL>

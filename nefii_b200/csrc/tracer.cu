@@ -21,6 +21,8 @@
 // followed by a rounded add, as torch evaluates it.
 #include <cuda_bf16.h>
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include "tracer.cuh"
 #include "tracer_math.cuh"
 
@@ -460,7 +462,15 @@ Layout make_layout(const SdfSource& src, int n_rays, int n_steps) {
   return L;
 }
 
-TraceTiers g_tiers;
+// NEFII_TRACE_TIERS="march,bulk" overrides the defaults at load (A/B runs of whole programs)
+TraceTiers env_tiers() {
+  TraceTiers t;
+  const char* e = getenv("NEFII_TRACE_TIERS");
+  int a = 0, b = 0;
+  if (e && sscanf(e, "%d,%d", &a, &b) == 2 && a >= 0 && a <= 64 && b >= 0 && b <= 64) { t.march_flush = a; t.bulk_flush = b; }
+  return t;
+}
+TraceTiers g_tiers = env_tiers();
 
 }  // namespace
 

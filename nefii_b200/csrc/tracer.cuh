@@ -32,8 +32,10 @@ enum TraceFlags : int {
 // to the fp32 register accumulators (see gemm_set_k_flush).  0 = the library default.
 //   march_flush: march and bisection rounds -- their values decide where a ray stops;
 //   bulk_flush : the n_steps-sample scans of the sampler and of min-SDF sampling -- they only select brackets / arg-mins.
+// Both default to 0 since the truncation compensation of the layer GEMM (gemm_set_trunc_comp) made the longest partials as
+// accurate as the shortest; the knobs remain for A/B measurements (NEFII_TRACE_TIERS="march,bulk").
 struct TraceTiers {
-  int march_flush = 1;
+  int march_flush = 0;
   int bulk_flush = 0;
 };
 int trace_set_tiers(int march_flush, int bulk_flush);

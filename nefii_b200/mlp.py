@@ -19,10 +19,9 @@ import torch
 from . import _lib, ops
 
 c_void_p = ctypes.c_void_p
-# accuracy tier of the forward layer GEMMs of the trainable stacks (K blocks per TMEM partial; 1 = most accurate, 0 = library
-# default): their outputs are the radiance / albedo / roughness the parity tolerances are stated on, and they run on surface
-# points only (a few percent of a step), so they take the accurate tier; the backward GEMMs keep the default.
-FWD_FLUSH = 1
+# accuracy tier of the forward layer GEMMs of the trainable stacks (K blocks per TMEM partial; 1 = shortest partial sums,
+# 0 = library default).  With the truncation compensation of the layer GEMM (csrc/mlp_gemm.cu) the default is as accurate as 1.
+FWD_FLUSH = 0
 
 
 def _num_sms(device):

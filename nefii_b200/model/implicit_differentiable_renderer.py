@@ -118,9 +118,9 @@ class ImplicitNetwork(nn.Module):
             raise _lib.NefiiError("nefii_b200: the SDF network runs inference-only on the accelerated path; call "
                                   "model.freeze_geometry() (step 2 / rendering) or wrap the call in torch.no_grad()")
 
-    # accuracy tier of the stand-alone evaluations (sdf_output, features, normals: direct outputs of the renderer):
-    # one K block per TMEM partial, the most accurate setting of the layer GEMM (csrc/mlp_gemm.cu)
-    EVAL_FLUSH = 1
+    # accuracy tier of the stand-alone evaluations (sdf_output, features, normals): K blocks per TMEM partial of the layer GEMM,
+    # 0 = library default (as accurate as 1 since the truncation compensation, csrc/mlp_gemm.cu)
+    EVAL_FLUSH = 0
 
     def evaluate(self, x, want_feat=False, want_grad=False):
         """Fused pass: (sdf [N], feature [N,W] | None, d sdf/dx [N,3] | None)."""

@@ -1,11 +1,12 @@
-"""Chunked full-frame rendering around the hot path: the reference's split_input / merge_output helpers
+"""Full-frame rendering around the hot path: the reference's split_input / merge_output helpers
 (code/utils/general.py:24-37,68-82, same names and argument meaning) and the multi-GPU frame loop of
 scripts/render.py:283-360 with its pickle-through-CPU `gather_object` replaced by ONE fixed-shape NCCL gather.
 
-Work split (render.py:288-295): the frame is cut into chunks of 2**memory_capacity_level rays; chunk c belongs to rank
-c % world (round robin, balances hit density over the image).  Every rank renders its chunks, packs the 11 output
-planes the renderer keeps (render.py:311-323) into one [n_chunks_local, chunk_pixels, 27] float tensor, and rank 0
-receives all of them with a single `dist.gather`, un-interleaves the chunks and returns the merged dict.
+Work split: pixel p belongs to rank p % world (the reference deals whole 2**level-ray chunks round robin, render.py:288-295;
+dealing single pixels gives every rank the same pixel count and the same hit density, so no rank waits for another).  A rank
+renders its pixels in forwards of at most 2**memory_capacity_level rays (one forward when they fit), packs the 11 output
+planes the renderer keeps (render.py:311-323) into one [pixels_per_rank, 27] float tensor; rank 0 receives all of them with a
+single `dist.gather` and un-interleaves them on the device (a transpose).
 """
 import torch
 
@@ -61,44 +62,39 @@ def unpack_planes(buf, n_pixels):
     out, c0 = {}, 0
     for name, c in FRAME_PLANES:
         v = buf[:n_pixels, c0:c0 + c]
-        out[name] = (v[:, 0] > 0.5) if name in _BOOL_PLANES else (v if c > 1 or name == 'sg_roughness_values' else v[:, 0])
+        out[name] = (v[:, 0] > 0.5) if name in _BOOL_PLANES else (v.contiguous() if c > 1 or name == 'sg_roughness_values' else v[:, 0])
         c0 += c
     return out
 
 
 def render_frame(model, model_input, total_pixels, num_rays=1, memory_capacity_level=18, group=None):
-    """Renders every pixel of model_input['uv'] ([1, total_pixels, (R,) 2]) through `model` in chunks, sharded over the
-    ranks of `group` (None / uninitialised torch.distributed = single process).  Returns the merged dict of FRAME_PLANES
-    on rank 0 ([total_pixels, c] tensors, masks bool [total_pixels]) and None on the other ranks."""
+    """Renders every pixel of model_input['uv'] ([1, total_pixels, (R,) 2]) through `model`, sharded over the ranks of `group`
+    (None / uninitialised torch.distributed = single process).  Returns the merged dict of FRAME_PLANES on rank 0
+    ([total_pixels, c] tensors, masks bool [total_pixels]) and None on the other ranks."""
     import torch.distributed as dist
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     rank = dist.get_rank(group) if multi else 0
     world = dist.get_world_size(group) if multi else 1
-    level = memory_capacity_level
-    if multi:
-        w, shift = world, 0
-        while w > 1:                      # render.py:287: level - floor(log2(world))
-            w >>= 1
-            shift += 1
-        level -= shift
-    split = split_input(model_input, total_pixels, num_rays, level)
-    chunk_pixels = split[0]['uv'].shape[1]
-    mine = split[rank::world]
-    per_rank = (len(split) + world - 1) // world
+    per_rank = (total_pixels + world - 1) // world
     dev = model_input['uv'].device
-    local = torch.zeros(per_rank, chunk_pixels, FRAME_CHANNELS, device=dev)
+    mine = dict(model_input)
+    mine['uv'] = model_input['uv'][:, rank::world]
+    mine['object_mask'] = model_input['object_mask'][:, rank::world]
+    n_mine = mine['uv'].shape[1]
+    local = torch.zeros(per_rank, FRAME_CHANNELS, device=dev)
     with torch.no_grad():
-        for i, s in enumerate(mine):
+        done = 0
+        for s in (split_input(mine, n_mine, num_rays, memory_capacity_level) if n_mine > 0 else []):
+            n = s['uv'].shape[1]
             out = model(s)
-            local[i] = pack_planes(out, s['uv'].shape[1], chunk_pixels)
+            local[done:done + n] = pack_planes(out, n, n)
+            done += n
     if multi:
-        gathered = [torch.empty_like(local) for _ in range(world)] if rank == 0 else None
-        dist.gather(local, gathered, dst=0, group=group)
+        gathered = torch.empty(world, per_rank, FRAME_CHANNELS, device=dev) if rank == 0 else None
+        dist.gather(local, list(gathered.unbind(0)) if rank == 0 else None, dst=0, group=group)
         if rank != 0:
             return None
+        frame = gathered.permute(1, 0, 2).reshape(world * per_rank, FRAME_CHANNELS)      # pixel p = rank + world * i
     else:
-        gathered = [local]
-    res = []
-    for c, s in enumerate(split):                     # chunk c was rendered by rank c % world as its (c // world)-th chunk
-        res.append(unpack_planes(gathered[c % world][c // world], s['uv'].shape[1]))
-    return merge_output(res, total_pixels, 1)
+        frame = local
+    return unpack_planes(frame, total_pixels)

@@ -1,5 +1,6 @@
-"""CPU, world_size 2 over gloo: the host-side multi-GPU logic of bench.py (per-rank pixel batches, the single flat
-gradient all-reduce that replaces DDP's buckets)."""
+"""CPU, world_size 2 over gloo: the host-side multi-GPU logic of bench.py -- ONE global pixel batch whose 2x2 patches are
+dealt to the ranks (reference datasets/scene_dataset.py:268-279, training/idr_train.py:653-662) and the single flat gradient
+all-reduce that replaces DDP's buckets."""
 import os
 import socket
 
@@ -25,7 +26,7 @@ def _worker(rank, world, port, out):
     net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
     net[0].bias.requires_grad_(False)         # frozen parameters stay out of the flat buffer
     flat = bench.FlatGrads(net.parameters())
-    uv, obj, rgb = bench.make_batch(1000 * rank, num_pixels=64, num_rays=2)      # rank-specific pixels
+    uv, obj, rgb = bench.shard_batch(bench.make_batch(1000, num_pixels=64, num_rays=2), rank, world)      # this rank's patches of the global batch
     x = torch.cat([uv[0, :, 0], uv[0, :, 1], uv[0, :, 0] * 1e-3], dim=-1)
     flat.zero()
     loss = (net(x / 800.0) - rgb).abs().mean()
@@ -50,6 +51,21 @@ def test_flat_gradient_allreduce_world2():
     assert out[0][0] and out[1][0]
     assert out[0][1] == 6 * 16 + 16 * 3 + 3          # trainable parameters only (frozen bias excluded)
     assert out[0][2] != out[1][2]                    # each rank rendered different pixels
+    whole = bench.make_batch(1000, num_pixels=64, num_rays=2)[0]
+    assert abs(out[0][2] + out[1][2] - float(whole.sum())) < 1e-2 * abs(float(whole.sum())) * 1e-3 + 1.0      # together: the global batch
+
+
+def test_shard_batch_deals_whole_patches():
+    batch = bench.make_batch(5, num_pixels=96, num_rays=4)
+    world = 4
+    parts = [bench.shard_batch(batch, r, world) for r in range(world)]
+    assert all(p[0].shape == (1, 24, 4, 2) and p[1].shape == (1, 24) and p[2].shape == (24, 3) for p in parts)
+    # patch p of the global batch is patch p // world of rank p % world, pixels in order
+    for p in range(24):
+        r, j = p % world, p // world
+        assert torch.equal(parts[r][0][0, 4 * j:4 * j + 4], batch[0][0, 4 * p:4 * p + 4])
+        assert torch.equal(parts[r][2][4 * j:4 * j + 4], batch[2][4 * p:4 * p + 4])
+    assert bench.shard_batch(batch, 0, 1) is batch
 
 
 def test_batch_layout_matches_reference_dataset_contract():

@@ -406,149 +406,7 @@ def diag_pipeline():
             print("   secondary mask agree %.5f" % (mine['secondary_mask'] == ref['secondary_mask']).float().mean().item())
 
 
-def _chunked(fn, chunk=1 << 21):
-    """evaluate an oracle callable in row chunks (bounds the torch-eager activation memory at full size)"""
-    def g(x):
-        if x.shape[0] <= chunk:
-            return fn(x)
-        return torch.cat([fn(x[i:i + chunk]) for i in range(0, x.shape[0], chunk)], 0)
-    return g
-
-
-def _quant(x, qs=(0.5, 0.95, 0.99, 1.0)):
-    x = x.flatten().float()
-    if x.numel() == 0:
-        return tuple(float("nan") for _ in qs)
-    srt = x.sort()[0]
-    return tuple(srt[min(srt.numel() - 1, int(q * (srt.numel() - 1) + 0.5))].item() for q in qs)
-
-
-def fullsize_compare(dev, bumps, n_px, n_rays, training, tiers=None, grads=True, seed=0, verbose=True):
-    """BASELINE configs[2]-sized parity run: IDRNetwork.forward_with_uv against oracle/pipeline.py on the same device, same
-    weights, same uniforms.  Returns a dict of statistics (used by tests/test_parity_fullsize_gpu.py and printed here)."""
-    import bench
-    from oracle import pipeline, ref_harness as rh
-    from nefii_b200 import _lib
-    from nefii_b200.model.implicit_differentiable_renderer import IDRNetwork
-    from nefii_b200.utils.conf import default_model_conf
-    if tiers is not None:
-        _lib.check(_lib.raw().nefii_trace_set_tiers(int(tiers[0]), int(tiers[1])))
-    om = rh.small_model(seed=seed, bumps=bumps)
-    torch.manual_seed(0)
-    net = IDRNetwork(default_model_conf()).to(dev)
-    rh.load_oracle_weights(net, om)
-    om = om.to(dev)
-    om.sdf_fn = _chunked(om.sdf_fn)
-    net.train(training)
-    uv, obj, rgb = bench.make_batch(seed + 11, num_pixels=n_px, num_rays=max(n_rays, 1))
-    if n_rays == 0:
-        uv = uv[:, :, 0]
-    pose, K = bench.make_camera()
-    obj = obj.clone()
-    obj[0, ::9] = False
-    g = torch.Generator().manual_seed(seed + 100)
-    U = torch.rand(n_px * max(n_rays, 1), 7, generator=g).to(dev)
-    vecs = [torch.rand(100, generator=g) for _ in range(2)]
-    inp = dict(uv=uv.to(dev), pose=pose.to(dev), intrinsics=K.to(dev), object_mask=obj.to(dev))
-    gt = rgb.to(dev)
-    res = {}
-
-    def loss_of(out):
-        m = out['network_object_mask'] & out['object_mask']
-        bg = (~out['network_object_mask']) & (~out['object_mask'])
-        l = (out['sg_rgb_values'][m] - gt[m]).abs().mean() + (out['idr_rgb_values'][m] - gt[m]).abs().mean()
-        if bool(bg.any()):
-            l = l + ((out['sg_rgb_values'][bg] - gt[bg]) ** 2).mean()
-        return l
-
-    for p in net.parameters():
-        p.grad = None
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    with torch.set_grad_enabled(grads):
-        mine = net.forward_with_uv(inp, uniforms=U, trace_uniforms=vecs[0])
-        if grads:
-            loss_of(mine).backward()
-    torch.cuda.synchronize()
-    res['ours_s'] = time.perf_counter() - t0
-    if grads:
-        om.lgtSGs.requires_grad_(True)
-        om.material.requires_grad_(True)
-        om.radiance.requires_grad_(True)
-    t0 = time.perf_counter()
-    with torch.set_grad_enabled(grads):
-        ref = pipeline.forward_with_uv(om, inp['uv'], inp['pose'], inp['intrinsics'], inp['object_mask'], lambda n: U[:n], training,
-                                       vecs[0], vecs[1])
-        if grads:
-            loss_of(ref).backward()
-    torch.cuda.synchronize()
-    res['oracle_s'] = time.perf_counter() - t0
-
-    a, b = mine['network_object_mask'], ref['network_object_mask']
-    agree = a == b
-    hit = agree & a
-    res['pixels'] = int(a.numel())
-    res['mask_mismatch'] = int((~agree).sum())
-    res['hits'] = int(hit.sum())
-    dp = (mine['points'] - ref['points'])[hit].abs().amax(-1)
-    res['depth'] = _quant(dp)
-    miss = agree & ~a
-    res['sdf_output_hit'] = _quant((mine['sdf_output'] - ref['sdf_output'])[hit].abs())
-    res['sdf_output_miss'] = _quant((mine['sdf_output'] - ref['sdf_output'])[miss].abs()) if bool(miss.any()) else None
-    res['keys'] = {}
-    for k in ('normal_values', 'idr_rgb_values', 'sg_rgb_values', 'sg_diffuse_rgb_values', 'sg_specular_rgb_values',
-              'sg_roughness_values', 'sg_diffuse_albedo_values'):
-        x, y = mine[k][hit].float(), ref[k][hit].float()
-        rel = ((x - y).abs() / (y.abs() + 1e-6)).flatten()
-        res['keys'][k] = dict(q=_quant(rel), frac_1e4=(rel <= 1e-4).float().mean().item(), absq=_quant((x - y).abs()))
-    bgm = agree & ~a & ~mine['object_mask']
-    if bool(bgm.any()):
-        x, y = mine['sg_rgb_values'][bgm], ref['sg_rgb_values'][bgm]
-        res['background_rel'] = _quant(((x - y).abs() / (y.abs() + 1e-6)))
-    if mine['secondary_mask'] is not None and ref['secondary_mask'] is not None and mine['secondary_mask'].shape == ref['secondary_mask'].shape:
-        sm, sr = mine['secondary_mask'], ref['secondary_mask']
-        res['secondary_rays'] = int(sm.numel())
-        res['secondary_mismatch'] = int((sm != sr).sum())
-        both = (sm & sr).reshape(3, -1)
-        d2 = (mine['secondary_points'] - ref['secondary_points']).abs().amax(-1)[both]
-        res['secondary_depth'] = _quant(d2)
-    else:
-        res['secondary_mismatch'] = None
-    if grads:
-        def rel(x, y):
-            return (x - y).norm().item() / (y.norm().item() + 1e-20)
-        res['g_lgt'] = rel(net.envmap_material_network.lgtSGs.grad, om.lgtSGs.grad)
-        g_mat = [l.weight.grad for l in net.envmap_material_network.diffuse_albedo_layers if hasattr(l, "weight")]
-        res['g_mat'] = [rel(x, w.grad) for x, w in zip(g_mat, om.material.W)]
-        g_rad = []
-        for i, w in enumerate(om.radiance.W):
-            gv_mine = getattr(net.rendering_network, "lin%d" % i).weight_v.grad
-            gW, v = w.grad, w.detach()
-            nrm = v.norm(dim=1, keepdim=True)
-            gv = gW - (gW * v).sum(1, keepdim=True) * v / (nrm * nrm)
-            g_rad.append(rel(gv_mine, gv))
-        res['g_rad'] = g_rad
-    if verbose:
-        print("FULL bumps=%.2f px=%d rays/px=%d train=%d tiers=%s: ours %.3fs oracle %.3fs | mask mismatches %d of %d (hits %d)" % (
-            bumps, n_px, max(n_rays, 1), training, tiers, res['ours_s'], res['oracle_s'], res['mask_mismatch'], res['pixels'], res['hits']))
-        print("   depth |dp| on hits   median %.2e p95 %.2e p99 %.2e max %.2e" % res['depth'])
-        print("   |d sdf_output| hits  median %.2e p95 %.2e p99 %.2e max %.2e" % res['sdf_output_hit'])
-        if res['sdf_output_miss']:
-            print("   |d sdf_output| miss  median %.2e p95 %.2e p99 %.2e max %.2e" % res['sdf_output_miss'])
-        for k, v in res['keys'].items():
-            print("   %-26s rel median %.2e p95 %.2e p99 %.2e max %.2e | lanes<=1e-4: %.4f | abs p99 %.2e max %.2e" % (
-                (k,) + v['q'] + (v['frac_1e4'], v['absq'][2], v['absq'][3])))
-        if 'background_rel' in res:
-            print("   background sg_rgb rel  median %.2e p95 %.2e p99 %.2e max %.2e" % res['background_rel'])
-        if res['secondary_mismatch'] is not None:
-            print("   secondary mask mismatches %d of %d; depth on common hits median %.2e p95 %.2e p99 %.2e max %.2e" % (
-                (res['secondary_mismatch'], res['secondary_rays']) + res['secondary_depth']))
-        if grads:
-            print("   grad rel (Frobenius): lgtSGs %.2e | material %s | radiance %s" % (
-                res['g_lgt'], " ".join("%.1e" % x for x in res['g_mat']), " ".join("%.1e" % x for x in res['g_rad'])))
-    if tiers is not None:
-        _lib.check(_lib.raw().nefii_trace_set_tiers(1, 0))
-    return res
+from tests.parity_util import fullsize_compare  # noqa: E402
 
 
 def diag_fullsize():
@@ -557,12 +415,70 @@ def diag_fullsize():
     bumps = float(os.environ.get("FULL_BUMPS", "0.08"))
     n_px = int(os.environ.get("FULL_PX", "2048"))
     n_rays = int(os.environ.get("FULL_RAYS", "64"))
-    tiers = [tuple(int(v) for v in t.split(",")) for t in os.environ.get("FULL_TIERS", "1,0").split(";")]
+    tiers = [tuple(int(v) for v in t.split(",")) for t in os.environ.get("FULL_TIERS", "0,0").split(";")]
     for t in tiers:
         fullsize_compare(dev, bumps, n_px, n_rays, True, tiers=t, grads=True)
     fullsize_compare(dev, bumps, n_px * 4, 0, False, tiers=tiers[0], grads=False)
     # per-ray lanes (no averaging over the rays of a pixel): the same rays as single-ray pixels
     fullsize_compare(dev, bumps, min(n_px * max(n_rays, 1), 32768), 0, True, tiers=tiers[0], grads=False)
+
+
+def diag_trunccomp():
+    """Calibrates and checks the first-order compensation of tcgen05's round-toward-zero accumulation
+    (nefii_gemm_set_trunc_comp): slope of the accumulation error against the exact product sum, per partial length."""
+    from nefii_b200 import ops, _lib
+    from oracle import mlp
+    dev = torch.device("cuda:0")
+    lib = _lib.raw()
+    rows, k, n = 16384, 512, 512
+    g = torch.Generator(device="cpu").manual_seed(0)
+    slopes = {}
+    for data in ("positive", "gauss"):
+        x = torch.randn(rows, k, generator=g) * 0.3
+        if data == "positive":
+            x = x.abs()
+        w = torch.randn(n, k, generator=g) / k ** 0.5
+        x, w = x.to(dev), w.to(dev)
+        a = ops.split_to_planes(x); b = ops.split_to_planes(w)
+        ah, al, bh, bl = [t.double() for t in (a[0], a[1], b[0], b[1])]
+        ref3 = ah @ bh.t() + ah @ bl.t() + al @ bh.t()        # what the three MMAs sum, exactly
+        for L in (1, 2, 4, 8):
+            _lib.check(lib.nefii_gemm_set_trunc_comp(L, 0.0))
+            out = torch.zeros(rows, n, device=dev)
+            ops.gemm_split_bf16(a, b, k, n, dst_f32=out, f32_begin=0, f32_end=n, k_flush=L)
+            err = out.double() - ref3
+            slope = ((err * ref3).sum() / (ref3 * ref3).sum()).item()
+            resid = (err - slope * ref3)
+            slopes[(data, L)] = slope
+            print("TRUNCCOMP %-8s L=%d: slope %.3e (%.2f ulp of 2^-24) | err rms %.3e -> after removing the slope %.3e | mean|ref| %.3f" % (
+                data, L, slope, slope / 2 ** -24, err.pow(2).mean().sqrt().item(), resid.pow(2).mean().sqrt().item(), ref3.abs().mean().item()))
+    params = mlp.sdf_init(seed=1, bumps=0.3)
+    net = ops.SdfMlp(device=dev)
+    net.set_weights([t.to(dev) for t in params.W], [t.to(dev) for t in params.b])
+    pts = torch.rand(131072, 3, device=dev) * 1.8 - 0.9
+    p64 = params.to(dev, torch.float64)
+    r64 = mlp.sdf_forward(p64, pts.double())[:, 0]
+    g64 = mlp.sdf_gradient(p64, pts[:16384].double())
+
+    def report(tag):
+        for L in (1, 2, 4, 8):
+            sdf, _, grad = net.eval(pts[:16384], want_grad=True, k_flush=L)
+            sdf_all, _, _ = net.eval(pts, k_flush=L)
+            e = sdf_all.double() - r64
+            ge = ((grad.double() - g64).norm(dim=-1) / g64.norm(dim=-1))
+            print("   %s SDF k_flush=%d: err mean|.| %.2e signed %.2e rms-about-mean %.2e max %.2e | grad rel median %.2e p99 %.2e" % (
+                tag, L, e.abs().mean().item(), e.mean().item(), (e - e.mean()).pow(2).mean().sqrt().item(), e.abs().max().item(),
+                ge.median().item(), ge.kthvalue(int(0.99 * ge.numel()))[0].item()))
+    report("comp off")
+    for src in ("positive", "gauss"):
+        for L in (1, 2, 4, 8):
+            _lib.check(lib.nefii_gemm_set_trunc_comp(L, -slopes[(src, L)]))
+        report("comp from %-8s" % src)
+    for L in (1, 2, 4, 8):
+        _lib.check(lib.nefii_gemm_set_trunc_comp(L, 0.0))
+    r32 = mlp.sdf_forward(params.to(dev), pts)[:, 0]
+    e = r32.double() - r64
+    print("   torch fp32 for scale: err mean|.| %.2e signed %.2e max %.2e" % (e.abs().mean().item(), e.mean().item(), e.abs().max().item()))
 
 
 def diag_l2fit():
