@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "shaded rays/sec (primary+indirect, fwd+bwd)"
-NUM_PIXELS, NUM_RAYS, NUM_SGS, IMG = 2048, 64, 128, 800
+NUM_PIXELS, NUM_RAYS, NUM_SGS, IMG = int(os.environ.get("NEFII_BENCH_PIXELS", 2048)), 64, 128, 800      # env: diagnostics only
 SDF_FLOPS_PER_POINT = 3.671e6      # 1,835,520 MAC forward
 SCENE_BUMPS = 0.08                 # perturbation of the geometric-init sphere (the parity tests' rough scene)
 SG_FLOPS_PER_RAY, SG_BYTES_PER_RAY = 35.0e3, 72.0      # render_with_sg at M = 128, K = 1 (algorithmic)

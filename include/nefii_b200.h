@@ -191,6 +191,29 @@ int nefii_trace_graph_clear(void);
 int nefii_analytic_sdf_eval(void* stream, const float* prims, int n_prims, int n, const float* x, float* sdf);
 
 /* ---------------------------------------------------------------------------------------------
+ * Ray set-up -- replaces rend_util.get_camera_params + lift, code/utils/rend_util.py:90-142 (pose-matrix form; the [B,7]
+ * quaternion form is converted to a matrix by the caller, :91-96).  uv [B,P,2], pose [B,4,4] camera-to-world, intrinsics
+ * [B,4,4] -> dirs [B,P,3] (unit), cam_loc [B,3] (may be NULL).  order: summation order of the 4-term products of
+ * torch.bmm(pose, cam_points) to reproduce (0: FMA chain, 1: separate multiply / add).
+ * ------------------------------------------------------------------------------------------- */
+int nefii_camera_rays(void* stream, int n_batch, int n_pix, const float* uv, const float* pose, const float* intrinsics,
+                      int order, float* dirs, float* cam_loc);
+
+/* ---------------------------------------------------------------------------------------------
+ * Differentiable intersection -- replaces SampleNetwork.forward, code/model/sample_network.py:10-24 (IDR eq. 3):
+ *   x = c + (t0 - (s - s0) / (grad . v0)) v,   |grad . v0| < 1e-8 -> 1e-8.
+ * surface_output / surface_sdf_values / surface_dists [n] (the reference's [n,1]), the others [n,3].
+ * bwd: g_points [n,3] -> gradients w.r.t. every input (any output pointer may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+int nefii_sample_network_fwd(void* stream, int n, const float* surface_output, const float* surface_sdf_values,
+                             const float* surface_points_grad, const float* surface_dists, const float* surface_cam_loc,
+                             const float* surface_ray_dirs, float* out_points);
+int nefii_sample_network_bwd(void* stream, int n, const float* surface_output, const float* surface_sdf_values,
+                             const float* surface_points_grad, const float* surface_dists, const float* surface_ray_dirs,
+                             const float* g_points, float* g_output, float* g_sdf_values, float* g_dists, float* g_cam_loc,
+                             float* g_ray_dirs, float* g_points_grad);
+
+/* ---------------------------------------------------------------------------------------------
  * Near-field indirect-illumination integrator -- replaces the sampling and shading halves of
  * pt_render_indirect_mlp, code/model/path_tracing_render.py:1255-1487 (cos_sampling :128-156,
  * brdf_sampling :61-125, mix_sg_sampling :168-271, power_heuristic_list :390-401, shading :1406-1476).

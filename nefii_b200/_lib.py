@@ -22,6 +22,9 @@ SIGNATURES = {
     "nefii_background_sg_fwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "nefii_gemm_split_bf16": [c_void_p, c_void_p],
     "nefii_probe_fp32": [c_void_p, c_int, c_int, c_void_p],
+    "nefii_camera_rays": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "nefii_sample_network_fwd": [c_void_p, c_int] + [c_void_p] * 7,
+    "nefii_sample_network_bwd": [c_void_p, c_int] + [c_void_p] * 12,
     "nefii_gemm_profile_enable": [c_int],
     "nefii_gemm_set_cluster": [c_int],
     "nefii_gemm_set_debug": [c_int],

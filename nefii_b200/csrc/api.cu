@@ -48,6 +48,10 @@ int last_layer_bwd(cudaStream_t, int, int, int, int, const float*, const float*,
                    __nv_bfloat16*, __nv_bfloat16*, int, float*, float*);
 int reduce_splits(cudaStream_t, const float*, int, long long, int, int, int, float*);
 int probe_fp32(cudaStream_t, int, int, float*);
+int camera_rays(cudaStream_t, int, int, const float*, const float*, const float*, int, float*, float*);
+int sample_network_fwd(cudaStream_t, int, const float*, const float*, const float*, const float*, const float*, const float*, float*);
+int sample_network_bwd(cudaStream_t, int, const float*, const float*, const float*, const float*, const float*, const float*, float*,
+                       float*, float*, float*, float*, float*);
 
 }  // namespace nefii
 
@@ -209,6 +213,23 @@ int nefii_reduce_splits(void* stream, const float* partial, int n_splits, int64_
   return nefii::reduce_splits((cudaStream_t)stream, partial, n_splits, (long long)stride, rows, ld_src, cols, out);
 }
 
+int nefii_camera_rays(void* stream, int n_batch, int n_pix, const float* uv, const float* pose, const float* intrinsics, int order,
+                      float* dirs, float* cam_loc) {
+  return nefii::camera_rays((cudaStream_t)stream, n_batch, n_pix, uv, pose, intrinsics, order, dirs, cam_loc);
+}
+int nefii_sample_network_fwd(void* stream, int n, const float* surface_output, const float* surface_sdf_values,
+                             const float* surface_points_grad, const float* surface_dists, const float* surface_cam_loc,
+                             const float* surface_ray_dirs, float* out_points) {
+  return nefii::sample_network_fwd((cudaStream_t)stream, n, surface_output, surface_sdf_values, surface_points_grad, surface_dists,
+                                   surface_cam_loc, surface_ray_dirs, out_points);
+}
+int nefii_sample_network_bwd(void* stream, int n, const float* surface_output, const float* surface_sdf_values,
+                             const float* surface_points_grad, const float* surface_dists, const float* surface_ray_dirs,
+                             const float* g_points, float* g_output, float* g_sdf_values, float* g_dists, float* g_cam_loc,
+                             float* g_ray_dirs, float* g_points_grad) {
+  return nefii::sample_network_bwd((cudaStream_t)stream, n, surface_output, surface_sdf_values, surface_points_grad, surface_dists,
+                                   surface_ray_dirs, g_points, g_output, g_sdf_values, g_dists, g_cam_loc, g_ray_dirs, g_points_grad);
+}
 int nefii_probe_fp32(void* stream, int blocks, int iters, float* sink) { return nefii::probe_fp32((cudaStream_t)stream, blocks, iters, sink); }
 int nefii_gemm_profile_enable(int on) { return nefii::gemm_profile_enable(on); }
 int nefii_gemm_set_cluster(int cl) { return nefii::gemm_set_cluster(cl); }

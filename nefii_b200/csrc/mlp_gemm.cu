@@ -325,6 +325,8 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   NEFII_CHECK_ARG(p.epi.mode == 0 || p.epi.sav_hi == nullptr || p.epi.sav_ld >= n_chunks * BN || p.epi.sav_ncols % 32 == 0,
                   "gemm_split_bf16: saved-activation rows must cover whole 32-column groups");
   int grid = ceil_div(m_tiles, cl) * cl;
+  // few row tiles: room for the kernel's device-side split of the column chunks over clusters (see the kernel)
+  if (n_chunks > 1 && !(p.epi.mode == 0 && p.epi.w_last != nullptr) && p.k_splits <= 1) grid *= n_chunks;
   if (grid > n_sms) grid = n_sms / cl * cl;   // persistent CTAs: one per SM, looping over row tiles
   GemmKernelFn fn = nullptr;
   const bool fuse = p.epi.mode == 0 && p.epi.w_last != nullptr;

@@ -547,8 +547,9 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
                        long long f32_split_stride, int dbg, int k_flush, float part_scale_full, float part_scale_last, const __grid_constant__ GemmEpilogue epi_in) {
   // Persistent over row tiles: CTA x handles tiles x, x + gridDim.x, ... so that the final epilogue math of one tile
   // overlaps the MMAs of the next (the pipelines and barrier phases simply keep running across tiles).
-  const int m_tile0 = blockIdx.x;
-  const int tile_stride = gridDim.x;
+  int m_tile0 = blockIdx.x;
+  int tile_stride = gridDim.x;
+  int nc_begin = 0, nc_end = n_chunks;
   // split-K (weight gradients): CTA (x, y) reduces K blocks [y * kb_per_split, ...) into its own fp32 partial
   const int kb_begin = blockIdx.y * kb_per_split;
   const int k_blocks = min(k_blocks_total, kb_begin + kb_per_split) - kb_begin;
@@ -568,6 +569,23 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   constexpr int kBTileBytes = R::kBTileBytes;
   constexpr int kBK = R::kBK;
   const int cta_rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  // Few live row tiles (the march / bisection rounds of a trace; decided from the DEVICE-side row count): the column chunks of
+  // a tile go to different clusters instead of running one after the other in the same one, which halves the latency of a
+  // layer when less than half of the grid has work.  Cluster c takes (tile group c % G, chunk c / G), G = live tile groups.
+  // Not for the fused output layer (its dot product needs the whole row) and not together with split-K.
+  if (!FUSE && n_chunks > 1 && gridDim.y == 1) {
+    const int live_tiles = (m_limit + BM - 1) / BM;
+    const int groups = (live_tiles + CL - 1) / CL;
+    const int clusters = (int)gridDim.x / CL;
+    if (groups > 0 && groups * n_chunks <= clusters) {
+      const int c = (int)blockIdx.x / CL;
+      if (c >= groups * n_chunks) return;              // uniform over the cluster
+      m_tile0 = (c % groups) * CL + cta_rank;
+      nc_begin = c / groups;
+      nc_end = nc_begin + 1;
+      tile_stride = 1 << 28;                            // one tile per CTA
+    }
+  }
   // every loop below runs while the PAIR's first tile is live, so both CTAs of a pair take the same trips
   if ((long long)(m_tile0 - cta_rank) * BM >= m_limit || k_blocks <= 0) return;
 #define NEFII_TILE_LIVE(t) ((long long)((t) - cta_rank) * BM < m_limit)
@@ -623,7 +641,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       int stage = 0;
       uint32_t phase = 0;
       for (int m_tile = m_tile0; NEFII_TILE_LIVE(m_tile); m_tile += tile_stride)
-      for (int nc = 0; nc < n_chunks; ++nc) {
+      for (int nc = nc_begin; nc < nc_end; ++nc) {
         for (int ks = 0; ks < k_blocks * R::kSub; ++ks) {
           mbar_wait(smem_u32(&bars[kBarEmpty + stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars[kBarFull + stage]);
@@ -660,7 +678,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       const int parts_per_chunk = sched.count();
       uint32_t pcount = 0;
       for (int m_tile = m_tile0; NEFII_TILE_LIVE(m_tile); m_tile += tile_stride)
-      for (int nc = 0; nc < n_chunks; ++nc) {
+      for (int nc = nc_begin; nc < nc_end; ++nc) {
         for (int pi = 0; pi < parts_per_chunk; ++pi, ++pcount) {
           const int buf = pcount & 1;
           mbar_wait(smem_u32(&bars[kBarTEmpty + buf]), ((pcount >> 1) & 1) ^ 1);   // the partial of two groups ago was read
@@ -767,7 +785,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       for (int i = 0; i < 4; ++i) fs.ok_mask |= (r0 + 8 * i < m_limit) ? (1u << i) : 0u;
       fs.y0 = (int)(row - lane);
     }
-    for (int nc = 0; nc < n_chunks; ++nc) {
+    for (int nc = nc_begin; nc < nc_end; ++nc) {
       for (int pi = 0; pi < parts_per_chunk; ++pi, ++pcount) {
         const int buf = pcount & 1;
         mbar_wait(smem_u32(&bars[kBarTFull + buf]), (pcount >> 1) & 1);

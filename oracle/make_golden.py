@@ -49,6 +49,12 @@ def main():
     ref_shim.install()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    only = sys.argv[1:]                      # e.g. `python -m oracle.make_golden small_ops`: regenerate one fixture
+    if only:
+        for name in only:
+            globals()["golden_" + name]()
+        print("wrote", sorted(os.listdir(OUT)))
+        return
     golden_sg_render()
     for extra in EXTRA:
         extra()
@@ -186,7 +192,50 @@ def golden_mis_and_pipeline():
     np.savez_compressed(os.path.join(OUT, "pipeline_small.npz"), **out)
 
 
-EXTRA = [golden_tracer, golden_mis_and_pipeline, golden_loss]
+def golden_small_ops():
+    """SampleNetwork.forward + backward (model/sample_network.py:10-24) and get_camera_params in both pose forms
+    (utils/rend_util.py:90-142) from the REAL reference."""
+    from model.sample_network import SampleNetwork
+    from utils import rend_util as ref_rend
+    g = torch.Generator().manual_seed(11)
+    n = 777
+    s = (torch.randn(n, 1, generator=g) * 1e-3).requires_grad_(True)
+    s0 = (s.detach() + torch.randn(n, 1, generator=g) * 1e-4).requires_grad_(True)
+    grad = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    grad[:5] = 0.0                                   # exercises the |grad . v| < 1e-8 guard
+    grad = grad.requires_grad_(True)
+    dirs = dirs.requires_grad_(True)
+    t0 = (torch.rand(n, 1, generator=g) * 3 + 0.5).requires_grad_(True)
+    cam = torch.randn(n, 3, generator=g).requires_grad_(True)
+    x = SampleNetwork()(s, s0, grad, t0, cam, dirs)
+    g_out = torch.randn(n, 3, generator=g)
+    grads = torch.autograd.grad(x, [s, s0, grad, t0, cam, dirs], g_out)
+    out = dict(sn_s=s.detach().numpy(), sn_s0=s0.detach().numpy(), sn_grad=grad.detach().numpy(), sn_t0=t0.detach().numpy(),
+               sn_cam=cam.detach().numpy(), sn_dirs=dirs.detach().numpy(), sn_x=x.detach().numpy(), sn_g_out=g_out.numpy())
+    for name, t in zip(("s", "s0", "grad", "t0", "cam", "dirs"), grads):
+        out["sn_g_" + name] = t.numpy()
+    # camera rays: a rotated pose with skewed intrinsics, as a matrix and as quaternion + translation
+    B, S = 2, 500
+    uv = torch.rand(B, S, 2, generator=g) * 800
+    q = torch.nn.functional.normalize(torch.randn(B, 4, generator=g), dim=-1)
+    tr = torch.randn(B, 3, generator=g)
+    pose7 = torch.cat([q, tr], -1)
+    R = ref_rend.quat_to_rot(q)
+    pose44 = torch.eye(4).repeat(B, 1, 1)
+    pose44[:, :3, :3] = R
+    pose44[:, :3, 3] = tr
+    K = torch.eye(4).repeat(B, 1, 1)
+    K[:, 0, 0] = torch.tensor([1900.0, 2100.0]); K[:, 1, 1] = torch.tensor([1950.0, 2050.0])
+    K[:, 0, 1] = torch.tensor([0.7, -1.3]); K[:, 0, 2] = 400.5; K[:, 1, 2] = 399.25
+    d44, c44 = ref_rend.get_camera_params(uv, pose44, K)
+    d7, c7 = ref_rend.get_camera_params(uv, pose7, K)
+    out.update(cr_uv=uv.numpy(), cr_pose44=pose44.numpy(), cr_pose7=pose7.numpy(), cr_K=K.numpy(), cr_dirs44=d44.numpy(),
+               cr_cam44=c44.numpy(), cr_dirs7=d7.numpy(), cr_cam7=c7.numpy())
+    np.savez_compressed(os.path.join(OUT, "small_ops.npz"), **out)
+
+
+EXTRA = [golden_tracer, golden_mis_and_pipeline, golden_loss, golden_small_ops]
 
 if __name__ == "__main__":
     main()

@@ -92,6 +92,7 @@ def fullsize_compare(dev, bumps, n_px, n_rays, training, tiers=None, grads=True,
     res['hits'] = int(hit.sum())
     dp = (mine['points'] - ref['points'])[hit].abs().amax(-1)
     res['depth'] = _quant(dp)
+    res['depth_frac_1e4'] = (dp < 1e-4).float().mean().item() if dp.numel() else 1.0
     miss = agree & ~a
     res['sdf_output_hit'] = _quant((mine['sdf_output'] - ref['sdf_output'])[hit].abs())
     res['sdf_output_miss'] = _quant((mine['sdf_output'] - ref['sdf_output'])[miss].abs()) if bool(miss.any()) else None
@@ -131,7 +132,7 @@ def fullsize_compare(dev, bumps, n_px, n_rays, training, tiers=None, grads=True,
     if verbose:
         print("FULL bumps=%.2f px=%d rays/px=%d train=%d tiers=%s: ours %.3fs oracle %.3fs | mask mismatches %d of %d (hits %d)" % (
             bumps, n_px, max(n_rays, 1), training, tiers, res['ours_s'], res['oracle_s'], res['mask_mismatch'], res['pixels'], res['hits']))
-        print("   depth |dp| on hits   median %.2e p95 %.2e p99 %.2e max %.2e" % res['depth'])
+        print("   depth |dp| on hits   median %.2e p95 %.2e p99 %.2e max %.2e | within 1e-4: %.5f" % (res['depth'] + (res['depth_frac_1e4'],)))
         print("   |d sdf_output| hits  median %.2e p95 %.2e p99 %.2e max %.2e" % res['sdf_output_hit'])
         if res['sdf_output_miss']:
             print("   |d sdf_output| miss  median %.2e p95 %.2e p99 %.2e max %.2e" % res['sdf_output_miss'])

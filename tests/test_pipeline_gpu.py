@@ -45,7 +45,7 @@ def test_forward_matches_oracle_pipeline(cuda_device, training, rays):
                                        training, vecs[0], vecs[1])
     a, b = mine['network_object_mask'], ref['network_object_mask']
     agree = a == b
-    assert agree.float().mean().item() > 0.998, agree.float().mean().item()      # measured: 0 mismatches (tools/diag_gpu.py pipeline)
+    assert int((~agree).sum()) <= 1, int((~agree).sum())      # measured: 0 mismatches (tools/diag_gpu.py pipeline / fullsize)
     assert int((a & b).sum()) > 100
     assert torch.equal(mine['object_mask'], ref['object_mask'])
     sel = agree
@@ -53,7 +53,7 @@ def test_forward_matches_oracle_pipeline(cuda_device, training, rays):
     # the arg-min over 100 random depths (minimal_sdf_points): the arg-min may jump between two near-equal samples, so
     # there the minimum VALUE (sdf_output) is compared instead of its position.
     hit = sel & a
-    assert ((mine['points'] - ref['points'])[hit].abs().max(-1)[0] < 1e-4).float().mean().item() > 0.98      # measured 0.994 / 1.0
+    assert ((mine['points'] - ref['points'])[hit].abs().max(-1)[0] < 1e-4).float().mean().item() > 0.99      # measured 0.9995 / 1.0
     miss = sel & ~a
     if bool(miss.any()):
         assert (mine['sdf_output'] - ref['sdf_output'])[miss].abs().max().item() < 1e-4
@@ -67,7 +67,8 @@ def test_forward_matches_oracle_pipeline(cuda_device, training, rays):
         err = (x - y).abs() / (y.abs() + 1e-3)
         p95 = err.flatten().kthvalue(max(1, int(0.95 * err.numel())))[0].item()
         # idr_rgb = (raw MLP output)^2 of a random-init net: tiny values, the relative error of the square is amplified
-        assert p95 < (8e-3 if k == 'idr_rgb_values' else 5e-4), (k, p95)
+        print('pipeline train=%d %-28s p95 rel err %.2e' % (training, k, p95))
+        assert p95 < (6e-3 if k == 'idr_rgb_values' else 3e-4), (k, p95)
     # secondary rays: same directions (bit-exact sampler) wherever the primary hit point agrees
     if mine['secondary_dir'] is not None and mine['secondary_dir'].shape == ref['secondary_dir'].shape:
         d = (mine['secondary_dir'] - ref['secondary_dir']).abs().amax(-1)
@@ -107,9 +108,12 @@ def test_gradients_match_oracle_pipeline(cuda_device):
     def rel(a, b):
         return (a - b).norm().item() / (b.norm().item() + 1e-20)
 
-    assert rel(g_lgt, om.lgtSGs.grad) < 2e-2, rel(g_lgt, om.lgtSGs.grad)
+    # north_star: gradients rel 1e-3 -- met at BASELINE size (tests/test_parity_fullsize_gpu.py); this 1024-pixel x 2-ray batch
+    # has so few samples per weight that single ReLU / ELU sign flips of near-zero pre-activations show: 5e-3 here
+    print('grad rel: lgtSGs %.2e material %s' % (rel(g_lgt, om.lgtSGs.grad), ' '.join('%.1e' % rel(a, w.grad) for a, w in zip(g_mat, om.material.W))))
+    assert rel(g_lgt, om.lgtSGs.grad) < 5e-3, rel(g_lgt, om.lgtSGs.grad)
     for a, b in zip(g_mat, [w.grad for w in om.material.W]):
-        assert rel(a, b) < 2e-2, rel(a, b)
+        assert rel(a, b) < 5e-3, rel(a, b)
     # radiance net: the oracle holds effective weights W = g v/|v| with |v| = g at init, so dL/dW == dL/dv + radial part;
     # compare the tangential gradient (what weight_v receives) after projecting the oracle's gradient the same way
     for a, w in zip(g_rad_v, om.radiance.W):
@@ -117,7 +121,8 @@ def test_gradients_match_oracle_pipeline(cuda_device):
         v = w.detach()
         nrm = v.norm(dim=1, keepdim=True)
         gv = gW - (gW * v).sum(1, keepdim=True) * v / (nrm * nrm)      # d/dv of g * v/|v| at g == |v|
-        assert rel(a, gv) < 2e-2, rel(a, gv)
+        print('grad rel radiance %.2e' % rel(a, gv))
+        assert rel(a, gv) < 5e-3, rel(a, gv)
 
 
 def test_forward_with_point_entry(cuda_device):
@@ -150,6 +155,22 @@ def test_forward_with_point_entry(cuda_device):
         nrm = pipeline.unit(omlp.sdf_gradient(om.sdf, points.reshape(-1, 3)))
         ref = omlp.radiance_forward(om.radiance, points.reshape(-1, 3), nrm, pipeline.unit(-dirs.reshape(-1, 3)), feats)
     assert torch.allclose(res['idr_rgb_values'], ref.reshape(n, R, 3).mean(1), rtol=2e-3, atol=2e-4)
+    # the SG branch of the same entry: get_rbg_value with injected uniforms against the oracle's get_rgb_value (the entry
+    # itself draws its random numbers like the reference, so it is compared through the function it wraps)
+    U2 = torch.rand(n * R, 7, generator=g).to(dev)
+    with torch.no_grad():
+        mine = net.get_rbg_value(points.reshape(-1, 3), -dirs.reshape(-1, 3), uniforms=U2)
+        oref = pipeline.get_rgb_value(om, points.reshape(-1, 3), -dirs.reshape(-1, 3), U2, True, vecs[1])
+    assert torch.equal(mine['secondary_dir'].reshape(3, -1, 3), oref['secondary_dir'].reshape(3, -1, 3)) or \
+        (mine['secondary_dir'].reshape(3, -1, 3) - oref['secondary_dir'].reshape(3, -1, 3)).abs().max().item() < 1e-4
+    same = (mine['secondary_mask'].reshape(3, -1) == oref['secondary_mask'].reshape(3, -1)).all(0)
+    assert same.float().mean().item() > 0.995
+    err = ((mine['sg_rgb'] - oref['sg_rgb']).abs() / (oref['sg_rgb'].abs() + 1e-6))[same]
+    frac = (err <= 1e-4).float().mean().item()
+    print('forward_with_point sg_rgb: lanes within rel 1e-4: %.4f, p95 %.2e' % (frac, err.flatten().kthvalue(int(0.95 * err.numel()))[0].item()))
+    assert frac > 0.85 and err.flatten().kthvalue(int(0.95 * err.numel()))[0].item() < 1e-3
+    for k in ('sg_diffuse_rgb', 'sg_specular_rgb'):
+        assert torch.allclose(mine[k][same], oref[k][same], rtol=5e-3, atol=5e-5), k
 
 
 def test_degenerate_batches(cuda_device):
@@ -204,6 +225,17 @@ def test_render_frame_chunked_matches_single_call(cuda_device):
         # geometry and material do not depend on the sampled secondary rays; bisection's batch-wide stop moves depths < 2e-5
         assert (whole[name] - parts[name])[m].abs().max().item() < 2e-3, name
     assert set(whole) == {k for k, _ in general.FRAME_PLANES}
+    # ... and the ORACLE's frame (eval mode, one call): geometry and material planes do not depend on the sampled directions
+    om = rh.small_model(seed=0).to(dev)
+    Uo = torch.rand(n * n, 7, generator=torch.Generator().manual_seed(1)).to(dev)
+    with torch.no_grad():
+        ref = pipeline.forward_with_uv(om, inp['uv'], inp['pose'], inp['intrinsics'], inp['object_mask'], lambda k: Uo[:k], False)
+    assert int((parts['network_object_mask'] != ref['network_object_mask']).sum()) <= 1
+    both = parts['network_object_mask'] & ref['network_object_mask']
+    assert ((parts['points'] - ref['points'])[both].abs().amax(-1) < 1e-4).float().mean().item() > 0.99
+    assert (parts['normal_values'] - ref['normal_values'])[both].abs().flatten().kthvalue(int(0.99 * int(both.sum()) * 3))[0].item() < 5e-4
+    assert torch.allclose(parts['sg_diffuse_albedo_values'][both], ref['sg_diffuse_albedo_values'][both], rtol=1e-3, atol=1e-4)
+    assert torch.allclose(parts['sg_roughness_values'][both], ref['sg_roughness_values'][both], rtol=1e-3, atol=1e-4)
 
 
 def test_render_frame_multi_ray_chunks(cuda_device):

@@ -1,6 +1,7 @@
 """CPU: the chunked / sharded frame loop (nefii_b200/utils/general.py, reference utils/general.py:24-82 and
 scripts/render.py:283-360) with a stand-in model: split/merge round trip, ragged last chunk, and the world_size-2 gloo
-gather giving rank 0 exactly the single-process frame."""
+gather (pixels dealt to the ranks p % world, an odd pixel count so that the ranks' shares differ) giving rank 0 exactly the
+single-process frame."""
 import os
 
 import pytest
@@ -53,8 +54,8 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        inp = _frame(1000)
-        out = general.render_frame(FakeModel(), inp, 1000, memory_capacity_level=8)     # -> 128-pixel chunks at world 2
+        inp = _frame(1001)
+        out = general.render_frame(FakeModel(), inp, 1001, memory_capacity_level=8)     # 501 / 500 pixels per rank, 256-pixel forwards
         if rank == 0:
             q.put({k: v.clone() for k, v in out.items()})
         else:
@@ -76,9 +77,10 @@ def test_world2_gather_matches_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     got = next(r for r in res if r is not None)
-    whole = FakeModel()(_frame(1000))
+    whole = FakeModel()(_frame(1001))
     for name, c in general.FRAME_PLANES:
         ref = whole[name]
+        assert got[name].shape[0] == 1001
         if ref.dtype == torch.bool:
             assert torch.equal(got[name].reshape(ref.shape), ref), name
         else:
