@@ -128,17 +128,19 @@ typedef struct nefii_sdf_config {
   int32_t n_hidden;    /* len(dims) (8) */
   int32_t skip_layer;  /* skip_in[0] (4); <= 0: none */
   int32_t d_out;       /* 1 */
+  int32_t d_feat;      /* 0: feature vector = input of the last layer (use_last_as_f, conf.conf); > 0: the last Linear has
+                          1 + d_feat outputs, rows 1.. are the feature vector (use_last_as_f = False, conf_neus.conf) */
 } nefii_sdf_config;
 
 int nefii_sdf_create(void** handle, const nefii_sdf_config* cfg /* host */);
 int nefii_sdf_destroy(void* handle);
 /* weights / biases: host arrays of n_hidden+1 device pointers; weights[l] is the EFFECTIVE fp32 matrix
- * [out_l, in_l] (weight_norm folded: g * v / |v|), row-major contiguous.  Call again whenever the
- * parameters change. */
+ * [out_l, in_l] (weight_norm folded: g * v / |v|), row-major contiguous; the last one is [1 + d_feat, width].
+ * Call again whenever the parameters change. */
 int nefii_sdf_set_weights(void* handle, void* stream, const float* const* weights, const float* const* biases);
 int64_t nefii_sdf_workspace_bytes(void* handle, int rows_cap, int with_grad);
 /* x [rows_cap,3]; count: device int32 with the number of valid rows or NULL; sdf [rows_cap];
- * feat [rows_cap,width] or NULL; grad [rows_cap,3] or NULL (d sdf / d x).
+ * feat [rows_cap, d_feat > 0 ? d_feat : width] or NULL; grad [rows_cap,3] or NULL (d sdf / d x).
  * k_flush: accuracy tier of the layer GEMMs (K blocks per TMEM partial, 1 = most accurate); 0 = library default. */
 int nefii_sdf_eval(void* handle, void* stream, int rows_cap, const int32_t* count, const float* x,
                    void* workspace, int64_t workspace_bytes, float* sdf, float* feat, float* grad, int k_flush);

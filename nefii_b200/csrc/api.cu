@@ -107,7 +107,7 @@ int nefii_sdf_create(void** handle, const nefii_sdf_config* cfg) {
   if (!handle || !cfg) return nefii::set_error(NEFII_ERR_ARG, "nefii_sdf_create: null argument");
   nefii::SdfConfig c;
   c.d_in = cfg->d_in; c.n_freqs = cfg->n_freqs; c.width = cfg->width; c.n_hidden = cfg->n_hidden;
-  c.skip_layer = cfg->skip_layer; c.d_out = cfg->d_out;
+  c.skip_layer = cfg->skip_layer; c.d_out = cfg->d_out; c.d_feat = cfg->d_feat;
   nefii::SdfNet* net = new nefii::SdfNet();
   int rc = net->init(c);
   if (rc) { delete net; return rc; }

@@ -137,6 +137,8 @@ struct SdfNet::Impl {
   std::vector<float*> bias;
   float* w_last = nullptr;            // [d_out, width] fp32
   float* b_last = nullptr;
+  Planes w_feat;                      // d_feat > 0: rows 1.. of the last Linear as planes [round_up(d_feat,256), width]
+  float* b_feat = nullptr;
   void* blob = nullptr;
   bool has_weights = false;
 };
@@ -155,7 +157,8 @@ int SdfNet::init(const SdfConfig& cfg) {
   NEFII_CHECK_ARG(cfg.width >= 64 && cfg.width % 64 == 0 && cfg.width <= 1024, "sdf: width must be a multiple of 64 in [64,1024]");
   NEFII_CHECK_ARG(cfg.n_hidden >= 2 && cfg.n_hidden <= 16, "sdf: n_hidden out of range");
   NEFII_CHECK_ARG(cfg.skip_layer < cfg.n_hidden, "sdf: skip_layer out of range");
-  NEFII_CHECK_ARG(cfg.d_out == 1, "sdf: d_out must be 1 (use_last_as_f layout)");
+  NEFII_CHECK_ARG(cfg.d_out == 1, "sdf: d_out must be 1");
+  NEFII_CHECK_ARG(cfg.d_feat >= 0 && cfg.d_feat <= 1024, "sdf: d_feat out of range");
   Impl& s = *impl_;
   s.cfg = cfg;
   s.d_pe = 3 + 6 * cfg.n_freqs;
@@ -182,6 +185,9 @@ int SdfNet::init(const SdfConfig& cfg) {
   }
   const size_t off_wl = take((size_t)cfg.d_out * cfg.width * 4);
   const size_t off_bl_last = take((size_t)cfg.d_out * 4);
+  const size_t n_wf = (size_t)round_up(cfg.d_feat > 0 ? cfg.d_feat : 1, 256) * cfg.width * 2;
+  const size_t off_wfh = take(cfg.d_feat > 0 ? n_wf : 0), off_wfl = take(cfg.d_feat > 0 ? n_wf : 0);
+  const size_t off_bf = take((size_t)(cfg.d_feat > 0 ? cfg.d_feat : 0) * 4);
   if (s.blob) cudaFree(s.blob);
   NEFII_CUDA(cudaMalloc(&s.blob, bytes));
   NEFII_CUDA(cudaMemset(s.blob, 0, bytes));
@@ -200,6 +206,8 @@ int SdfNet::init(const SdfConfig& cfg) {
   }
   s.w_last = (float*)(base + off_wl);
   s.b_last = (float*)(base + off_bl_last);
+  s.w_feat.hi = (__nv_bfloat16*)(base + off_wfh); s.w_feat.lo = (__nv_bfloat16*)(base + off_wfl); s.w_feat.ld = cfg.width;
+  s.b_feat = (float*)(base + off_bf);
   s.has_weights = false;
   return NEFII_OK;
 }
@@ -218,8 +226,16 @@ int SdfNet::set_weights(cudaStream_t stream, const float* const* weights, const 
       return rc;
     NEFII_CUDA(cudaMemcpyAsync(s.bias[l], biases[l], (size_t)s.out_dim[l] * 4, cudaMemcpyDeviceToDevice, stream));
   }
+  // the last Linear: row 0 (the SDF) is applied in fp32 inside the last hidden layer's epilogue; with d_feat > 0 its
+  // remaining rows (the feature vector of the use_last_as_f = False layout) become one more plain layer
   NEFII_CUDA(cudaMemcpyAsync(s.w_last, weights[s.n_lin - 1], (size_t)s.cfg.d_out * s.cfg.width * 4, cudaMemcpyDeviceToDevice, stream));
   NEFII_CUDA(cudaMemcpyAsync(s.b_last, biases[s.n_lin - 1], (size_t)s.cfg.d_out * 4, cudaMemcpyDeviceToDevice, stream));
+  if (s.cfg.d_feat > 0) {
+    if ((rc = split_to_planes(stream, weights[s.n_lin - 1] + (size_t)s.cfg.d_out * s.cfg.width, s.cfg.d_feat, s.cfg.width, s.cfg.width, 0,
+                              1.f, s.w_feat.hi, s.w_feat.lo, round_up(s.cfg.d_feat, 256), s.cfg.width)))
+      return rc;
+    NEFII_CUDA(cudaMemcpyAsync(s.b_feat, biases[s.n_lin - 1] + s.cfg.d_out, (size_t)s.cfg.d_feat * 4, cudaMemcpyDeviceToDevice, stream));
+  }
   s.has_weights = true;
   return NEFII_OK;
 }
@@ -278,6 +294,9 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
   // ---------------------------------------------------------------- forward
   Planes seed;  // gradient seed G_{H-1}
   if (with_grad) seed = act[H - 1];
+  // d_feat > 0: planes of the last hidden activation, input of the feature rows of the last Linear.  Buffer: the one
+  // the last hidden layer does not read (ping-pong) / the spare buffer of the gradient chain (with_grad).
+  Planes feat_in = with_grad ? act[H] : act[(H - 1) & 1];
   for (int l = 0; l < H; ++l) {
     GemmProblem g{};
     g.k_flush = k_flush;
@@ -298,10 +317,22 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
     } else {
       g.epi.w_last = s.w_last; g.epi.b_last = s.b_last; g.epi.n_last = s.cfg.d_out; g.epi.w_last_ld = W;
       g.epi.dst_last = sdf;
-      if (feat) { g.epi.dst_f32 = feat; g.epi.f32_ld = W; g.epi.f32_begin = 0; g.epi.f32_end = W; }
+      if (feat && s.cfg.d_feat == 0) { g.epi.dst_f32 = feat; g.epi.f32_ld = W; g.epi.f32_begin = 0; g.epi.f32_end = W; }
+      if (feat && s.cfg.d_feat > 0) { g.epi.dst = feat_in; g.epi.dst_ncols = W; }   // planes of the last hidden activation
       if (with_grad) g.epi.seed = seed;
     }
     if ((rc = gemm_split_bf16(stream, g))) return rc;
+    if (l == H - 1 && feat && s.cfg.d_feat > 0) {
+      GemmProblem f{};     // feature = W_last[1:] h + b_last[1:]  (no activation), fp32 out
+      f.k_flush = k_flush;
+      f.a_hi = feat_in.hi; f.a_lo = feat_in.lo; f.a_ld = feat_in.ld; f.rows_cap = rows_cap;
+      f.b_hi = s.w_feat.hi; f.b_lo = s.w_feat.lo; f.b_ld = s.w_feat.ld; f.n_pad = round_up(s.cfg.d_feat, 256);
+      f.k_pad = W;
+      f.count = count;
+      f.epi.mode = 0; f.epi.act = ACT_NONE; f.epi.n_valid = s.cfg.d_feat; f.epi.bias = s.b_feat;
+      f.epi.dst_f32 = feat; f.epi.f32_ld = s.cfg.d_feat; f.epi.f32_begin = 0; f.epi.f32_end = s.cfg.d_feat;
+      if ((rc = gemm_split_bf16(stream, f))) return rc;
+    }
     if (l + 1 == skip) {
       // the skip layer's input = [h / sqrt2 | PE / sqrt2]: the encoding goes next to the h columns the GEMM just wrote
       encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, kInvSqrt2, in_of(skip), W - s.d_pe, 0);

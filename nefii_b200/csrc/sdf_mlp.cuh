@@ -11,6 +11,9 @@ struct SdfConfig {
   int n_hidden = 8;     // Linear+Softplus layers before the 1-wide output layer
   int skip_layer = 4;   // layer whose input is cat([h, PE]) / sqrt(2); <= 0: none
   int d_out = 1;
+  // 0: feature vector = input of the last layer (`use_last_as_f`, conf.conf); > 0: the last Linear has 1 + d_feat outputs,
+  // row 0 the SDF and rows 1.. the feature vector (use_last_as_f = False, conf_neus.conf)
+  int d_feat = 0;
 };
 
 class SdfNet {

@@ -46,13 +46,15 @@ class ImplicitNetwork(nn.Module):
             use_last_as_f=False
     ):
         super().__init__()
-        if not use_last_as_f or feature_vector_size != dims[-1] or d_in != 3 or d_out != 1 or len(skip_in) > 1:
-            raise NotImplementedError("nefii_b200: ImplicitNetwork is built for the use_last_as_f layout of conf.conf "
-                                      "(feature vector = input of the last layer, d_in 3, d_out 1, one skip)")
+        if d_in != 3 or d_out != 1 or len(skip_in) > 1:
+            raise NotImplementedError("nefii_b200: ImplicitNetwork is built for d_in 3, d_out 1 and at most one skip connection "
+                                      "(conf.conf, conf_neus.conf)")
+        if use_last_as_f and feature_vector_size != dims[-1]:
+            raise ValueError("use_last_as_f needs feature_vector_size == dims[-1]")       # the reference asserts the same
         if len(set(dims)) != 1:
             raise NotImplementedError("nefii_b200: hidden layers must share one width")
         self.feature_vector_size = feature_vector_size
-        dims = [d_in] + list(dims) + [d_out]
+        dims = [d_in] + list(dims) + [d_out if use_last_as_f else d_out + feature_vector_size]
         self.embed_fn = None
         self.multires = multires
         if multires > 0:
@@ -98,7 +100,8 @@ class ImplicitNetwork(nn.Module):
         if self._sdf_mlp is None or self._sdf_mlp.device != torch.device(device):
             skip = self.skip_in[0] if len(self.skip_in) else 0
             self._sdf_mlp = ops.SdfMlp(n_freqs=self.multires, width=self._width, n_hidden=self._n_hidden,
-                                       skip_layer=skip, device=device)
+                                       skip_layer=skip, device=device,
+                                       d_feat=0 if self.use_last_as_f else self.feature_vector_size)
             self._packed_versions = None
         if versions != self._packed_versions:
             with torch.no_grad():
@@ -153,6 +156,9 @@ class ImplicitNetwork(nn.Module):
         weight_v / bias through torch's weight-norm fold.  The feature columns are returned detached (nothing in step 1
         reads them); d sdf/dx with create_graph (the eikonal term) is not built -- gradient() raises for it."""
         from ..mlp import dense_mlp
+        if not self.use_last_as_f:
+            raise _lib.NefiiError("nefii_b200: the trainable SDF stack (step-1 geometry fitting) is built for the use_last_as_f "
+                                  "layout of conf.conf")
         layers = self._layers()
         ws = [_effective_weight(l) for l in layers]
         bs = [l.bias for l in layers]

@@ -55,8 +55,8 @@ def pt_render_indirect_mlp(lgtSGs, specular_reflectance, roughness, diffuse_albe
     :param model: the IDRNetwork (ray_tracer, implicit_network, rendering_network)
     :param uniforms: optional [N,7] uniforms (parity tests); default: drawn like the reference
     """
-    if blending_weights is not None or diffuse_rgb is not None:
-        raise NotImplementedError("nefii_b200: blending_weights / diffuse_rgb are not used by the shipped confs")
+    # blending_weights / diffuse_rgb: accepted and ignored, exactly as the reference's pt_render_diff_shadow_indirect_mlp does
+    # (path_tracing_render.py:1265-1487 never reads them)
     dots_shape = list(normal.shape[:-1])
     n = normal.reshape(-1, 3).shape[0]
     dev = normal.device

@@ -90,16 +90,18 @@ def gemm_split_bf16(a, b, k_pad, n_valid, *, mode=0, act=ACT_NONE, bias=None, ou
 class SdfConfig(ctypes.Structure):
     """Mirror of ``nefii_sdf_config``."""
     _fields_ = [("d_in", c_int), ("n_freqs", c_int), ("width", c_int), ("n_hidden", c_int),
-                ("skip_layer", c_int), ("d_out", c_int)]
+                ("skip_layer", c_int), ("d_out", c_int), ("d_feat", c_int)]
 
 
 class SdfMlp:
     """Owner of a ``nefii_sdf_*`` handle: packed weights live in the library, workspaces are torch tensors."""
 
-    def __init__(self, n_freqs=6, width=512, n_hidden=8, skip_layer=4, device=None):
+    def __init__(self, n_freqs=6, width=512, n_hidden=8, skip_layer=4, device=None, d_feat=0):
+        """d_feat = 0: feature vector = input of the last layer (use_last_as_f); > 0: rows 1.. of the last Linear."""
         self.device = torch.device(device if device is not None else "cuda")
-        self.cfg = SdfConfig(3, n_freqs, width, n_hidden, skip_layer, 1)
+        self.cfg = SdfConfig(3, n_freqs, width, n_hidden, skip_layer, 1, d_feat)
         self.width, self.n_hidden = width, n_hidden
+        self.feat_width = d_feat if d_feat > 0 else width
         h = c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(_lib.raw().nefii_sdf_create(ctypes.byref(h), ctypes.byref(self.cfg)))
@@ -141,7 +143,7 @@ class SdfMlp:
         x = _lib.f32c(x).reshape(-1, 3)
         n = x.shape[0]
         sdf = torch.empty(n, device=x.device, dtype=torch.float32)
-        feat = torch.empty(n, self.width, device=x.device, dtype=torch.float32) if want_feat else None
+        feat = torch.empty(n, self.feat_width, device=x.device, dtype=torch.float32) if want_feat else None
         grad = torch.empty(n, 3, device=x.device, dtype=torch.float32) if want_grad else None
         if n == 0:
             return sdf, feat, grad

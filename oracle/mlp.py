@@ -46,18 +46,22 @@ def fold_weight_norm(weight_g, weight_v):
 class SdfParams:
     """Effective weights of ImplicitNetwork: W[l] [out_l, in_l], b[l] [out_l], l = 0..n_hidden."""
 
-    def __init__(self, weights, biases, n_freqs=6, skip_layer=4):
+    def __init__(self, weights, biases, n_freqs=6, skip_layer=4, last_as_f=True):
         self.W = list(weights)
         self.b = list(biases)
         self.n_freqs = n_freqs
         self.skip_layer = skip_layer
+        # True: feature vector = input of the last layer (conf.conf); False: the last Linear has 1 + F outputs and the
+        # feature vector is its rows 1.. (conf_neus.conf; implicit_differentiable_renderer.py:39-42,105-106)
+        self.last_as_f = last_as_f
 
     @property
     def n_layers(self):
         return len(self.W)
 
     def to(self, *a, **k):
-        return SdfParams([w.to(*a, **k) for w in self.W], [b.to(*a, **k) for b in self.b], self.n_freqs, self.skip_layer)
+        return SdfParams([w.to(*a, **k) for w in self.W], [b.to(*a, **k) for b in self.b], self.n_freqs, self.skip_layer,
+                         self.last_as_f)
 
     def state_dict(self, prefix=""):
         """weight_g / weight_v / bias entries as the reference's checkpoints name them."""
@@ -69,13 +73,13 @@ class SdfParams:
         return sd
 
 
-def sdf_init(seed=0, width=512, n_hidden=8, n_freqs=6, skip_layer=4, bias=0.6, bumps=0.0):
+def sdf_init(seed=0, width=512, n_hidden=8, n_freqs=6, skip_layer=4, bias=0.6, bumps=0.0, d_feat=0):
     """Geometric initialisation as in ImplicitNetwork.__init__ (implicit_differentiable_renderer.py:60-74).
     `bumps` > 0 additionally gives the PE columns of layer 0 small random weights, which turns the
     sphere of radius `bias` into a bumpy blob (used by the synthetic 'robot-scale' scene)."""
     g = torch.Generator().manual_seed(seed)
     d_pe = 3 + 6 * n_freqs
-    dims = [d_pe] + [width] * n_hidden + [1]
+    dims = [d_pe] + [width] * n_hidden + [1 + d_feat]      # d_feat > 0: use_last_as_f = False layout
     W, B = [], []
     n_lin = len(dims) - 1
     for l in range(n_lin):
@@ -98,7 +102,7 @@ def sdf_init(seed=0, width=512, n_hidden=8, n_freqs=6, skip_layer=4, bias=0.6, b
             w.normal_(0.0, math.sqrt(2) / math.sqrt(out_dim), generator=g)
         W.append(w)
         B.append(b)
-    return SdfParams(W, B, n_freqs, skip_layer)
+    return SdfParams(W, B, n_freqs, skip_layer, last_as_f=(d_feat == 0))
 
 
 def sdf_forward(p, x, return_hidden=False):
@@ -116,7 +120,7 @@ def sdf_forward(p, x, return_hidden=False):
         h = F.linear(h, p.W[l], p.b[l])
         if l < n_lin - 1:
             h = F.softplus(h, beta=100)
-    out = torch.cat([h, feat], dim=-1)
+    out = torch.cat([h, feat], dim=-1) if p.last_as_f else h
     return (out, hidden) if return_hidden else out
 
 

@@ -117,3 +117,28 @@ def test_tracer_oracle_vs_reference_mlp_sdf_train_mode():
     assert torch.equal(m, m2)
     assert torch.equal(t, t2)
     assert torch.equal(p[st["sphere_hits"]], p2[st["sphere_hits"]])
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present")
+def test_neus_layout_sdf_network_matches_reference():
+    """use_last_as_f = False (confs_sg/conf_neus.conf: width 256, the last Linear has 1 + 256 outputs, the feature vector is
+    its rows 1..; implicit_differentiable_renderer.py:39-42,85-108): oracle forward + closed-form gradient against the REAL
+    ImplicitNetwork with the same weights."""
+    import contextlib
+    import io
+    ref_shim.install()
+    with contextlib.redirect_stdout(io.StringIO()):
+        from model.implicit_differentiable_renderer import ImplicitNetwork
+        net = ImplicitNetwork(256, d_in=3, d_out=1, dims=[256] * 8, geometric_init=True, bias=0.5, skip_in=[4], weight_norm=True,
+                              multires=6, use_last_as_f=False)
+    params = mlp.sdf_init(seed=5, width=256, bias=0.5, bumps=0.05, d_feat=256)
+    assert params.W[-1].shape == (257, 256) and not params.last_as_f
+    net.load_state_dict(params.state_dict(""))
+    x = torch.rand(500, 3, generator=torch.Generator().manual_seed(0)) * 1.6 - 0.8
+    with torch.no_grad():
+        ref = net(x)
+        mine = mlp.sdf_forward(params, x)
+    assert mine.shape == ref.shape == (500, 257)
+    assert torch.allclose(mine, ref, atol=2e-6, rtol=1e-5)
+    g_ref = net.gradient(x.clone(), no_grad=True)[:, 0]
+    assert torch.allclose(mlp.sdf_gradient(params, x), g_ref, atol=2e-5, rtol=1e-4)

@@ -52,3 +52,30 @@ def test_count_and_reference_width_256(cuda_device):
     assert (sdf[:600].double() - ref[:600, 0]).abs().max().item() < 5e-5
     gref = mlp.sdf_gradient(params.to(dev, torch.float64), x.double())
     assert ((grad[:600].double() - gref[:600]).norm(dim=-1) / gref[:600].norm(dim=-1).clamp_min(0.5)).max().item() < 1e-3
+
+
+def test_neus_layout_width_256_features_from_last_linear(cuda_device):
+    """confs_sg/conf_neus.conf: 8 x 256, use_last_as_f = False -- the feature vector is rows 1.. of the last Linear
+    (reference implicit_differentiable_renderer.py:39-42,85-108).  ImplicitNetwork.forward / .gradient of nefii_b200 with
+    that layout against the oracle in float64."""
+    from nefii_b200.model.implicit_differentiable_renderer import ImplicitNetwork
+    from oracle import mlp
+    dev = cuda_device
+    params = mlp.sdf_init(seed=5, width=256, bias=0.5, bumps=0.05, d_feat=256)
+    net = ImplicitNetwork(256, d_in=3, d_out=1, dims=[256] * 8, geometric_init=True, bias=0.5, skip_in=[4], weight_norm=True,
+                          multires=6, use_last_as_f=False).to(dev)
+    net.load_state_dict(params.state_dict(""))
+    for p in net.parameters():
+        p.requires_grad_(False)
+    x = (torch.rand(5000, 3, generator=torch.Generator().manual_seed(0)) * 1.6 - 0.8).to(dev)
+    p64 = params.to(dev, torch.float64)
+    with torch.no_grad():
+        out = net(x)
+        ref = mlp.sdf_forward(p64, x.double())
+        g = net.gradient(x, no_grad=True)[:, 0]
+        g_ref = mlp.sdf_gradient(p64, x.double())
+    assert out.shape == (5000, 257)
+    assert (out[:, 0].double() - ref[:, 0]).abs().max().item() < 5e-5
+    assert (out[:, 1:].double() - ref[:, 1:]).abs().max().item() < 1e-4
+    rel = (g.double() - g_ref).norm(dim=-1) / g_ref.norm(dim=-1)
+    assert rel.kthvalue(int(0.99 * rel.numel()))[0].item() < 5e-4
