@@ -20,7 +20,7 @@ BASE_FLAGS = [
 ]
 # Translation units whose results feed comparisons / ill-conditioned cancellations replicate the
 # reference's per-op float32 rounding: no FMA contraction, IEEE div/sqrt (see sg_math.cuh).
-EXACT_FP32 = {"sg_render.cu", "tracer.cu", "mis.cu", "ray_setup.cu", "sample_network.cu"}
+EXACT_FP32 = {"sg_render.cu", "tracer.cu", "mis.cu", "sample_network.cu"}
 EXACT_FLAGS = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
 
 

@@ -10,7 +10,7 @@ Restates
                                      fix_specular_albedo)
 and the parameter initialisers those classes use (so synthetic weights look like the reference's).
 
-Parity status: PINNED by tests/test_oracle_mlp.py, which loads these weights into the real reference
+Parity status: PINNED by tests/test_oracle_hotpath.py, which loads these weights into the real reference
 modules (when /root/reference is present) and by tests/golden/mlp_*.npz generated from them.
 
 Weights are kept as *effective* matrices: weight_norm layers are folded (w = g * v / ||v||_row,

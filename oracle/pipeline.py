@@ -10,7 +10,7 @@ on top of the restated pieces in oracle/{mlp,tracer,mis,sg}.py.  All random numb
 inputs: `u7` [N_hit,7] for the importance samplers and one [n_steps] vector per tracer call in
 training mode (the reference draws them with torch.rand / Tensor.uniform_).
 
-Parity status: PINNED -- tests/test_oracle_pipeline.py runs the real IDRNetwork (weights copied in, RNG
+Parity status: PINNED -- tests/test_oracle_hotpath.py runs the real IDRNetwork (weights copied in, RNG
 patched) against this file when /root/reference is present; tests/golden/pipeline_*.npz otherwise.
 """
 import torch

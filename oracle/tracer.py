@@ -18,7 +18,7 @@ torch.bmm are fixed here to ((a0*b0 + a1*b1) + a2*b2) without fused multiply-add
 that feeds a comparison is an explicit mul followed by an add.  The CUDA kernels follow the same
 order, which is what makes hit masks bit-comparable for an analytic SDF.
 
-Parity status: PINNED -- tests/test_oracle_tracer.py runs this against the real RayTracing module
+Parity status: PINNED -- tests/test_oracle_hotpath.py runs this against the real RayTracing module
 (with analytic and MLP SDF callables) when /root/reference is present, and against
 tests/golden/tracer_*.npz generated from it.
 """
