@@ -100,6 +100,9 @@ int nefii_gemm_set_cluster(int cluster_size);
 /* development only: disables pieces of the GEMM pipeline (1 epilogue math, 2 TMA loads, 4 MMAs, 8 TMEM flush, 16 plane staging +
  * stores, 32 plane stores) for timing experiments; results are then garbage */
 int nefii_gemm_set_debug(int mask);
+/* programmatic dependent launch of the layer GEMMs (a launch's prologue overlaps the tail of the previous kernel in the stream;
+ * default on, NEFII_GEMM_PDL=0 switches it off at load) */
+int nefii_gemm_set_pdl(int on);
 /* accuracy / overlap knob of the layer GEMM: 64-wide K blocks accumulated inside TMEM before the partial sum moves to the fp32
  * register accumulators (1 = most accurate; default 4, NEFII_GEMM_KFLUSH sets the default at load) */
 int nefii_gemm_set_k_flush(int k_blocks);

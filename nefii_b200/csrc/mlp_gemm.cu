@@ -150,6 +150,7 @@ constexpr int kDefaultKFlush = 8;
 int g_k_flush = env_int("NEFII_GEMM_KFLUSH", kDefaultKFlush, 1, 64);
 int g_store_tma = getenv("NEFII_GEMM_NO_TMA_STORE") ? 0 : 1;   // development switch for A/B timing
 int g_k_flush_head = env_int("NEFII_GEMM_KFLUSH", kDefaultKFlush, 1, 64);   // ... for the first two partials of a column chunk (gemm_set_k_flush_head)
+int g_pdl = env_int("NEFII_GEMM_PDL", 1, 0, 1);   // programmatic dependent launch of the layer GEMMs (gemm_set_pdl)
 int g_debug = 0;          // development only: bit mask that disables pipeline pieces for timing experiments
 // 1: single-CTA kernel, 2: cta_group::2 pairs (nefii_gemm_set_cluster; NEFII_GEMM_CLUSTER overrides the default at load).
 // Pairs are the default: the single-CTA kernel is bound by shared-memory bandwidth (TMA writes + tensor-core operand reads +
@@ -236,6 +237,7 @@ int gemm_set_cluster(int cl) {
 }
 
 int gemm_set_debug(int mask) { g_debug = mask; ++g_epoch; return NEFII_OK; }
+int gemm_set_pdl(int on) { g_pdl = on ? 1 : 0; ++g_epoch; return NEFII_OK; }
 int gemm_set_k_flush(int k) {
   NEFII_CHECK_ARG(k >= 1 && k <= 64, "gemm_set_k_flush: out of range");
   g_k_flush = k;
@@ -363,11 +365,18 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (g_pdl) {
+      // programmatic dependent launch: this kernel's prologue (barriers, TMEM, cluster sync) may run while the previous kernel
+      // of the stream is still draining; the kernel waits (griddepcontrol.wait) before it reads anything that kernel wrote
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.numAttrs = 2;
+    }
     const int kf_tail = p.k_flush > 0 ? p.k_flush : g_k_flush;
     const int kf_head = p.k_flush > 0 ? p.k_flush : g_k_flush_head;
     // Partial schedule of a column chunk (PartSched): partials of kf K blocks, the last one takes what is left.  Split-K

@@ -65,6 +65,8 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p);
 // upper bound for the TMA-multicast cluster size the launcher picks (tuning / A-B measurements)
 int gemm_set_cluster(int cl);
 int gemm_set_debug(int mask);
+// programmatic dependent launch of the layer GEMMs (default on; NEFII_GEMM_PDL=0 at load)
+int gemm_set_pdl(int on);
 // accuracy / overlap knob: number of 64-wide K blocks accumulated inside TMEM (truncating adder) before the partial sum is
 // added to the fp32 register accumulators (round to nearest).  1 = most accurate, 2 = default, >= K/64 = everything in TMEM.
 int gemm_set_k_flush(int k);

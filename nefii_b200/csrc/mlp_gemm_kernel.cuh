@@ -555,11 +555,6 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   const int k_blocks = min(k_blocks_total, kb_begin + kb_per_split) - kb_begin;
   GemmEpilogue epi = epi_in;
   if (epi.dst_f32 != nullptr) epi.dst_f32 += (long long)blockIdx.y * f32_split_stride;
-  int m_limit = rows_cap;
-  if (count_ptr != nullptr) {
-    int c = *count_ptr;
-    if (c < m_limit) m_limit = c;
-  }
   // uniform over the cluster: leave only if the cluster's FIRST tile is already past the valid rows
   static_assert(CL == 1 || CL == 2, "single CTA or a cta_group::2 pair");
   using R = Ring<CL>;
@@ -569,27 +564,9 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   constexpr int kBTileBytes = R::kBTileBytes;
   constexpr int kBK = R::kBK;
   const int cta_rank = (CL > 1) ? (int)cluster_ctarank() : 0;
-  // Few live row tiles (the march / bisection rounds of a trace; decided from the DEVICE-side row count): the column chunks of
-  // a tile go to different clusters instead of running one after the other in the same one, which halves the latency of a
-  // layer when less than half of the grid has work.  Cluster c takes (tile group c % G, chunk c / G), G = live tile groups.
-  // Not for the fused output layer (its dot product needs the whole row) and not together with split-K.
-  if (!FUSE && n_chunks > 1 && gridDim.y == 1) {
-    const int live_tiles = (m_limit + BM - 1) / BM;
-    const int groups = (live_tiles + CL - 1) / CL;
-    const int clusters = (int)gridDim.x / CL;
-    if (groups > 0 && groups * n_chunks <= clusters) {
-      const int c = (int)blockIdx.x / CL;
-      if (c >= groups * n_chunks) return;              // uniform over the cluster
-      m_tile0 = (c % groups) * CL + cta_rank;
-      nc_begin = c / groups;
-      nc_end = nc_begin + 1;
-      tile_stride = 1 << 28;                            // one tile per CTA
-    }
-  }
-  // every loop below runs while the PAIR's first tile is live, so both CTAs of a pair take the same trips
-  if ((long long)(m_tile0 - cta_rank) * BM >= m_limit || k_blocks <= 0) return;
-#define NEFII_TILE_LIVE(t) ((long long)((t) - cta_rank) * BM < m_limit)
 
+  // ---- prologue: nothing here reads what the previous kernel in the stream wrote, so under programmatic dependent launch
+  // (cudaLaunchAttributeProgrammaticStreamSerialization, set by the launcher) it runs while that kernel is still draining ----
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw;   // no integer round-trip: keeps every access below a shared-window (LDS/STS) access
   if (smem_u32(smem_raw) & 1023u) __trap();
@@ -631,6 +608,38 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // ---- from here on the kernel reads what its predecessor produced (row count, activation planes) ----
+  asm volatile("griddepcontrol.wait;" ::: "memory");                // no-op without the launch attribute
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may start ITS prologue on free SMs
+
+  int m_limit = rows_cap;
+  if (count_ptr != nullptr) {
+    int c = *count_ptr;
+    if (c < m_limit) m_limit = c;
+  }
+  bool live = true;
+  // Few live row tiles (the march / bisection rounds of a trace; decided from the DEVICE-side row count): the column chunks of
+  // a tile go to different clusters instead of running one after the other in the same one, which halves the latency of a
+  // layer when less than half of the grid has work.  Cluster c takes (tile group c % G, chunk c / G), G = live tile groups.
+  // Not for the fused output layer (its dot product needs the whole row) and not together with split-K.
+  if (!FUSE && n_chunks > 1 && gridDim.y == 1) {
+    const int live_tiles = (m_limit + BM - 1) / BM;
+    const int groups = (live_tiles + CL - 1) / CL;
+    const int clusters = (int)gridDim.x / CL;
+    if (groups > 0 && groups * n_chunks <= clusters) {
+      const int c = (int)blockIdx.x / CL;
+      if (c >= groups * n_chunks) live = false;         // uniform over the cluster
+      m_tile0 = (c % groups) * CL + cta_rank;
+      nc_begin = c / groups;
+      nc_end = nc_begin + 1;
+      tile_stride = 1 << 28;                            // one tile per CTA
+    }
+  }
+  // every loop below runs while the PAIR's first tile is live, so both CTAs of a pair take the same trips
+  if ((long long)(m_tile0 - cta_rank) * BM >= m_limit || k_blocks <= 0) live = false;
+#define NEFII_TILE_LIVE(t) ((long long)((t) - cta_rank) * BM < m_limit)
+
+  if (live) {
   // Register re-partitioning (168 regs/thread at launch): the role warpgroup keeps 40, each epilogue
   // warpgroup grows to 232 so the 128 fp32 partial sums per thread stay in registers.
   if (role >= 0) {
@@ -864,6 +873,8 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     }   // tile loop
     if (lane == 0) bulk_wait_all();   // this warp's bulk stores have left shared memory and are on their way
   }
+
+  }   // live
 
   tc_fence_before();
   __syncthreads();

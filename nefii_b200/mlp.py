@@ -236,3 +236,46 @@ def dense_mlp(segments, weights, biases, act, skip=0, skip_scale=1.0, want_hidde
     y, hidden = _DenseMlp.apply(act, seg_freqs, len(weights) - 1, int(skip), float(skip_scale), bool(want_hidden), need_grad,
                                 *seg_src, *params)
     return (y, hidden) if want_hidden else y
+
+
+# --------------------------------------------------------------------------------------------------------------------------
+# A matrix product that can be differentiated any number of times (the eikonal / un-frozen-geometry path)
+# --------------------------------------------------------------------------------------------------------------------------
+def _gemm_nt_raw(a, b):
+    """a [M,K] @ b[N,K]^T -> fp32 [M,N] on the tcgen05 layer GEMM (operands split into bf16 hi/lo planes here)."""
+    a, b = _lib.f32c(a), _lib.f32c(b)
+    m, k = a.shape
+    n = b.shape[0]
+    out = torch.empty(m, n, device=a.device, dtype=torch.float32)
+    if m == 0 or n == 0:
+        return out
+    if k == 0:
+        return out.zero_()
+    k_pad = ops.round_up(k, 64)
+    ap = ops.split_to_planes(a, rows_pad=m, cols_pad=k_pad)
+    bp = ops.split_to_planes(b, rows_pad=ops.round_up(n, 256), cols_pad=k_pad)
+    ops.gemm_split_bf16(ap, bp, k_pad, n, dst_f32=out, f32_begin=0, f32_end=n, f32_ld=n, rows_cap=m)
+    return out
+
+
+class _GemmNT(torch.autograd.Function):
+    """y = a @ b^T.  Its backward is two more products of the same kind, built from the same Function, so autograd can
+    differentiate it again: this is what `ImplicitNetwork.gradient(create_graph=True)` (the eikonal term and the normals of a
+    trainable geometry, reference implicit_differentiable_renderer.py:110-123) runs on."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return _gemm_nt_raw(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ga = gemm_nt(g, b.t()) if ctx.needs_input_grad[0] else None          # [M,N] @ [N,K]
+        gb = gemm_nt(g.t(), a.t()) if ctx.needs_input_grad[1] else None      # [N,M] @ [M,K]
+        return ga, gb
+
+
+def gemm_nt(a, b):
+    """a [M,K], b [N,K] -> a @ b^T [M,N]; differentiable to any order w.r.t. both operands."""
+    return _GemmNT.apply(a, b)

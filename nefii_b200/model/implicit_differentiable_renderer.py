@@ -167,19 +167,55 @@ class ImplicitNetwork(nn.Module):
                             skip_scale=float(1.0 / np.sqrt(2)), want_hidden=True)
         return torch.cat([y, feat], dim=-1)
 
+    def _forward_autograd(self, input):
+        """The same network as a composition of twice-differentiable pieces: every Linear is `mlp.gemm_nt` (tcgen05 layer GEMM
+        whose backward is built from itself), the positional encoding, bias, Softplus(100) and the skip concat are torch ops.
+        Slower than the fused paths (activations round-trip in fp32, no epilogue fusion); used where a graph THROUGH the input
+        is needed: gradient(create_graph=True) and inputs that carry a gradient (reference :85-123)."""
+        from ..mlp import gemm_nt
+        pe = self.embed_fn(input) if self.embed_fn is not None else input
+        x = pe
+        layers = self._layers()
+        feature_vector = None
+        for l, lin in enumerate(layers):
+            if self.use_last_as_f and l == self.num_layers - 2:
+                feature_vector = x
+            if l in self.skip_in:
+                x = torch.cat([x, pe], 1) / np.sqrt(2)
+            x = gemm_nt(x, _effective_weight(lin)) + lin.bias
+            if l < self.num_layers - 2:
+                x = self.softplus(x)
+        if self.use_last_as_f:
+            x = torch.cat([x, feature_vector], dim=-1)
+        return x
+
     # ---- reference API -----------------------------------------------------------------------------
     def forward(self, input, compute_grad=False):
+        if torch.is_grad_enabled() and input.requires_grad:
+            return self._forward_autograd(input)
         if self._trainable():
             return self._forward_trainable(input)
         sdf, feat, _ = self.evaluate(input, want_feat=True)
         return torch.cat([sdf.unsqueeze(-1), feat], dim=-1)
 
     def gradient(self, x, no_grad=False):
-        if not no_grad:
-            raise _lib.NefiiError("nefii_b200: ImplicitNetwork.gradient(create_graph=True) needs a trainable geometry, "
-                                  "which is outside the accelerated path")
-        _, _, g = self.evaluate(x, want_grad=True)
-        return g.unsqueeze(1)
+        """d sdf / d x, [N,1,3] (reference :110-123).  no_grad=True: the fused inference chain (closed-form reverse sweep on the
+        layer GEMM).  no_grad=False: `create_graph=True` -- the result carries a graph to the parameters (eikonal term) and to
+        x, through the twice-differentiable composition above."""
+        if no_grad:
+            if self._trainable():
+                with torch.no_grad():
+                    _, _, g = self._sync(x.device).eval(x.detach(), want_grad=True, k_flush=self.EVAL_FLUSH)
+                return g.unsqueeze(1)
+            _, _, g = self.evaluate(x, want_grad=True)
+            return g.unsqueeze(1)
+        x.requires_grad_(True)
+        with torch.enable_grad():
+            y = self._forward_autograd(x)[:, :1]
+            d_output = torch.ones_like(y, requires_grad=False)
+            gradients = torch.autograd.grad(outputs=y, inputs=x, grad_outputs=d_output, create_graph=True, retain_graph=True,
+                                            only_inputs=True)[0]
+        return gradients.unsqueeze(1)
 
 
 class RenderingNetwork(nn.Module):
