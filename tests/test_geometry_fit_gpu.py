@@ -82,9 +82,12 @@ def test_a_few_adam_steps_reduce_the_loss(cuda_device):
     assert (sdf_inf - net_ref_out).abs().max().item() < 5e-5
 
 
-def test_eikonal_path_is_refused(cuda_device):
-    from nefii_b200._lib import NefiiError
+def test_eikonal_path_returns_a_graph(cuda_device):
+    """gradient(x, no_grad=False) -- create_graph=True in the reference (:110-123) -- carries a graph to the parameters
+    (round 1 refused it; the parity of its gradients is in tests/test_second_order_gpu.py)"""
     net = _net(cuda_device)
     net.train()
-    with pytest.raises(NefiiError):
-        net.gradient(torch.rand(8, 3, device=cuda_device), no_grad=False)
+    g = net.gradient(torch.rand(8, 3, device=cuda_device), no_grad=False)
+    assert g.shape == (8, 1, 3) and g.requires_grad
+    ((g.norm(2, dim=-1) - 1) ** 2).mean().backward()
+    assert net.lin3.weight_v.grad is not None and torch.isfinite(net.lin3.weight_v.grad).all()
