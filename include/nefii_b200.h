@@ -190,6 +190,10 @@ int nefii_trace_set_tiers(int march_flush, int bulk_flush);
 /* 0: fixed launch schedule (every loop unrolled to its worst case, empty rounds exit at once); 1: CUDA graph with
  * conditional WHILE nodes (default; NEFII_TRACE_GRAPH=0 selects the fixed schedule at load) */
 int nefii_trace_set_graph_mode(int mode);
+/* bisection rounds apply TWO iterations of the reference's loop (both possible second mid-points are evaluated with the first
+ * one: 3 n rows instead of n, bit-identical results, half the latency-bound rounds) while 3 * n_root <= rows; 0 switches it
+ * off (default 12288; NEFII_TRACE_QUAD_ROWS at load) */
+int nefii_trace_set_quad_rows(int rows);
 /* drops the cached trace graphs (they hold raw pointers into workspaces and SDF handles) */
 int nefii_trace_graph_clear(void);
 /* the analytic test SDF alone: x [n,3] -> sdf [n] */

@@ -45,7 +45,7 @@ struct Ctrl {
   int any_work;      // bisection: OR of the surviving work bits
   int bis_step;      // bisection iterations applied
   int bis_alive;     // the bisection loop is still running
-  int pad;
+  int bis_quad;      // two bisection iterations per round (few rays: the rounds are latency-bound)
   long long evals;   // SDF point evaluations (stats)
 };
 
@@ -324,43 +324,78 @@ sample_reduce_kernel(RayState S, int chunk_rays, int n_steps, const float* __res
 
 // Bisection (RayTracing.rootfind, ray_tracing.py:259-280).  The reference bisects *every* passed ray while ANY ray still has
 // work, so the loop is batch-coupled: Ctrl::bis_alive says whether the next iteration runs.
-//   init : work = (s_lo > 0) & (s_hi < 0) & (z_hi > z_lo) (:261); emits the first mid-points when any ray has work
-//   step : applies one iteration (:265-277), emits the next mid-points while any ray has work left and steps remain
-//   finish: z_pred = (z_lo + z_hi) / 2 -> dists / points
+//   phase INIT  : work = (s_lo > 0) & (s_hi < 0) & (z_hi > z_lo) (:261); emits the first mid-points when any ray has work
+//   phase STEP  : applies one iteration (:265-277), emits the next mid-points while any ray has work left and steps remain
+//   finish      : z_pred = (z_lo + z_hi) / 2 -> dists / points
+// Two iterations per round ("quad" mode) when few rays are being refined: a round is latency-bound then (8 dependent layer
+// GEMMs on a handful of row tiles), so both possible second mid-points are evaluated together with the first one (3 n rows
+// instead of n) and a round applies TWO iterations of the reference -- bit-identical values, half the rounds:
+//   rows [0, n): m1 = (lo + hi) / 2;  [n, 2n): (lo + m1) / 2 (taken if sdf(m1) <= 0);  [2n, 3n): (m1 + hi) / 2 (if sdf(m1) > 0)
+//   phase STEP  applies the first iteration (and stops everybody if no ray has work left, as the reference would);
+//   phase STEP2 applies the second one from the candidate that matches, then emits the next three points.
+enum { BIS_INIT = 0, BIS_STEP = 1, BIS_STEP2 = 2 };
+
+__device__ __forceinline__ void bisect_emit(const RayState& S, int k, int n_root, int quad, float zl, float zh) {
+  const int r = S.root_list[k];
+  float o[3], d[3];
+  ray_od(S, r, o, d);
+  const float m1 = (zl + zh) * 0.5f;
+  emit_point(S, k, o, m1, d);                     // only evaluated if the loop goes on
+  if (quad) {
+    emit_point(S, n_root + k, o, (zl + m1) * 0.5f, d);
+    emit_point(S, 2 * n_root + k, o, (m1 + zh) * 0.5f, d);
+  }
+}
+
 __global__ void __launch_bounds__(kBlock)
-bisect_kernel(RayState S, int init, int n_rootfind_steps, unsigned long long cond) {
+bisect_kernel(RayState S, int phase, int n_rootfind_steps, int quad_rows, unsigned long long cond) {
   Ctrl* C = S.ctrl;
-  if (!init && !C->bis_alive) return;          // uniform over the grid: the flag only changes in the last CTA
+  if (phase != BIS_INIT && !C->bis_alive) return;          // uniform over the grid: the flag only changes in the last CTA
   const int n_root = C->n_root;
+  const int quad = (phase == BIS_INIT) ? ((n_root > 0 && 3 * (long long)n_root <= quad_rows) ? 1 : 0) : C->bis_quad;
+  if (phase == BIS_STEP2 && !quad) return;
   const int k = blockIdx.x * kBlock + threadIdx.x;
   if (k < n_root) {
     float zl = S.z_lo[k], zh = S.z_hi[k];
     unsigned char w;
-    if (init) {
+    if (phase == BIS_INIT) {
       w = (S.s_lo[k] > 0.f && S.s_hi[k] < 0.f && zh > zl) ? 1 : 0;
     } else {
       const float zm = (zl + zh) * 0.5f;
-      const float sm = S.req_sdf[k];
+      float sm;
+      if (phase == BIS_STEP) {
+        sm = S.req_sdf[k];
+        if (quad) S.ls[k] = sm > 0.f ? 1 : 0;        // which candidate of this round the second iteration uses (ls[] is free after the march)
+      } else {
+        sm = S.ls[k] ? S.req_sdf[2 * n_root + k] : S.req_sdf[n_root + k];
+      }
       if (sm > 0.f) { zl = zm; S.z_lo[k] = zl; S.s_lo[k] = sm; }
       if (sm <= 0.f) { zh = zm; S.z_hi[k] = zh; S.s_hi[k] = sm; }
       w = (S.work[k] && ((zh - zl) > 1e-6f)) ? 1 : 0;
     }
     S.work[k] = w;
     if (w) C->any_work = 1;
-    const int r = S.root_list[k];
-    float o[3], d[3];
-    ray_od(S, r, o, d);
-    emit_point(S, k, o, (zl + zh) * 0.5f, d);   // only evaluated if the loop goes on
+    // the next request: after INIT, after a plain STEP, after STEP2 (a quad round's STEP emits nothing: its second iteration
+    // already has its value)
+    if (!(phase == BIS_STEP && quad)) bisect_emit(S, k, n_root, quad, zl, zh);
   }
   if (last_block(&C->ticket) && threadIdx.x == 0) {
-    const int step = init ? 0 : C->bis_step + 1;
+    const int step = (phase == BIS_INIT) ? 0 : C->bis_step + 1;
     const bool alive = (*(volatile int*)&C->any_work != 0) && step < n_rootfind_steps && n_root > 0;
     C->bis_step = step;
     C->any_work = 0;
     C->bis_alive = alive ? 1 : 0;
-    C->cnt_eval = alive ? n_root : 0;
-    if (alive) C->evals += n_root;
-    set_cond(cond, alive);
+    if (phase == BIS_INIT) C->bis_quad = quad;
+    if (phase == BIS_STEP && quad) {
+      // first half of a quad round: the loop condition is set here too (STEP2 returns at once when the batch has stopped)
+      if (!alive) C->cnt_eval = 0;
+      set_cond(cond, alive);
+    } else {
+      const int rows = quad ? 3 * n_root : n_root;
+      C->cnt_eval = alive ? rows : 0;
+      if (alive) C->evals += rows;
+      set_cond(cond, alive);
+    }
   }
 }
 
@@ -471,6 +506,14 @@ TraceTiers env_tiers() {
   return t;
 }
 TraceTiers g_tiers = env_tiers();
+// bisection: two iterations per round while 3 * (rays being refined) <= this many rows; 0 switches the mode off
+// (NEFII_TRACE_QUAD_ROWS at load)
+int env_quad_rows() {
+  const char* e = getenv("NEFII_TRACE_QUAD_ROWS");
+  const int v = e ? atoi(e) : 12288;
+  return v < 0 ? 0 : v;
+}
+int g_bisect_quad_rows = env_quad_rows();
 
 }  // namespace
 
@@ -481,6 +524,12 @@ int trace_set_tiers(int march_flush, int bulk_flush) {
   return NEFII_OK;
 }
 TraceTiers trace_tiers() { return g_tiers; }
+int trace_set_quad_rows(int rows) {
+  NEFII_CHECK_ARG(rows >= 0, "trace_set_quad_rows: negative");
+  g_bisect_quad_rows = rows;
+  return NEFII_OK;
+}
+int trace_quad_rows() { return g_bisect_quad_rows; }
 
 size_t trace_workspace_bytes(const SdfSource& src, int n_rays, int n_steps) { return make_layout(src, n_rays, n_steps).total; }
 
@@ -601,12 +650,16 @@ int ray_trace_enqueue(cudaStream_t stream, const TraceConfig& cfg, const SdfSour
 
   // ---- bisection between the bracketing samples ----------------------------------------------------------------------
   unsigned long long h_bis = next_cond();
-  bisect_kernel<<<grid, kBlock, 0, stream>>>(S, 1, cfg.n_rootfind_steps, h_bis);
+  // two iterations per round while 3 n_root rows still fit a latency-bound evaluation (decided on the device from n_root)
+  const int quad_rows = std::min(g_bisect_quad_rows, L.cap_pts);
+  bisect_kernel<<<grid, kBlock, 0, stream>>>(S, BIS_INIT, cfg.n_rootfind_steps, quad_rows, h_bis);
   NEFII_LAUNCH_CHECK();
   if ((rc = loop(cfg.n_rootfind_steps, [&](cudaStream_t st, unsigned long long h) -> int {
         int rc2;
-        if ((rc2 = eval(st, std::min(R, L.cap_pts), tiers.march_flush))) return rc2;
-        bisect_kernel<<<grid, kBlock, 0, st>>>(S, 0, cfg.n_rootfind_steps, h);
+        if ((rc2 = eval(st, std::min(std::max(R, quad_rows), L.cap_pts), tiers.march_flush))) return rc2;
+        bisect_kernel<<<grid, kBlock, 0, st>>>(S, BIS_STEP, cfg.n_rootfind_steps, quad_rows, h);
+        NEFII_LAUNCH_CHECK();
+        bisect_kernel<<<grid, kBlock, 0, st>>>(S, BIS_STEP2, cfg.n_rootfind_steps, quad_rows, h);
         NEFII_LAUNCH_CHECK();
         return NEFII_OK;
       })))

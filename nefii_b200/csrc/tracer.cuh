@@ -40,6 +40,9 @@ struct TraceTiers {
 };
 int trace_set_tiers(int march_flush, int bulk_flush);
 TraceTiers trace_tiers();
+// bisection: two iterations per round (3 n rows per evaluation) while 3 * n_root <= rows; 0 = always one iteration per round
+int trace_set_quad_rows(int rows);
+int trace_quad_rows();
 
 size_t trace_workspace_bytes(const SdfSource& src, int n_rays, int n_steps);
 int trace_max_rounds(const TraceConfig& cfg);
