@@ -40,8 +40,11 @@ def round_up(x, m):
 
 def split_to_planes(src, rows_pad=None, cols_pad=None, transpose=False, scale=1.0):
     """fp32 [rows, cols] -> (hi, lo) bf16 planes, zero padded to [rows_pad, cols_pad]."""
-    assert src.is_cuda and src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
+    assert src.is_cuda and src.dtype == torch.float32 and src.dim() == 2
     rows, cols = src.shape
+    if cols > 1 and src.stride(1) != 1:
+        src = src.contiguous()
+    # (a size-1 dimension may carry any stride: only its index 0 is ever addressed)
     orow, ocol = (cols, rows) if transpose else (rows, cols)
     rows_pad = rows_pad or orow
     cols_pad = cols_pad or round_up(ocol, 64)

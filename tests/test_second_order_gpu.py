@@ -27,7 +27,7 @@ def _oracle_params(net, dtype):
     return omlp.SdfParams(ws, bs, n_freqs=net.multires, skip_layer=net.skip_in[0]), ws, bs
 
 
-@pytest.mark.parametrize("width,n_hidden,skip,n", [(512, 8, 4, 4096), (128, 4, 2, 777)])
+@pytest.mark.parametrize("width,n_hidden,skip,n", [(512, 8, 4, 4096), (256, 4, 2, 777)])
 def test_eikonal_gradients_reach_the_parameters(cuda_device, width, n_hidden, skip, n):
     from nefii_b200.model.implicit_differentiable_renderer import _effective_weight
     from oracle import mlp as omlp
