@@ -243,13 +243,14 @@ int nefii_mis_shade_fwd(void* stream, int n, int n_sg, const float* lgt_sgs, con
                         const float* indirect, float* out_rgb, float* out_specular, float* out_diffuse, float* light);
 /* g_rgb / g_specular / g_diffuse: upstream gradients [n,3] (any may be NULL).  Outputs: g_roughness [n],
  * g_albedo [n,3], g_specular_refl [n,3] or NULL, g_indirect [3,n,3]; g_lgt_acc [n_sg,7] is ACCUMULATED
- * (atomicAdd) in the unit parametrisation {d axis, d sharpness, d amplitude} -- convert with nefii_sg_param_grad. */
+ * (atomicAdd) in the unit parametrisation {d axis, d sharpness, d amplitude} -- convert with nefii_sg_param_grad;
+ * g_normal [n,3] or NULL: d / d normal (needed when the geometry trains: the normal is d sdf/dx with a graph). */
 int nefii_mis_shade_bwd(void* stream, int n, int n_sg, const float* lgt_sgs, const float* specular, int spec_per_point,
                         const float* roughness, const float* albedo, const float* normal, const float* view,
                         const float* wi, const float* pdf, const float* weight, const uint8_t* hit,
                         const float* indirect, const float* light, const float* g_rgb, const float* g_specular,
                         const float* g_diffuse, float* g_roughness, float* g_albedo, float* g_specular_refl,
-                        float* g_indirect, float* g_lgt_acc);
+                        float* g_indirect, float* g_lgt_acc, float* g_normal);
 /* backward of nefii_background_sg_fwd: accumulates into g_lgt_acc [n_sg,7] (unit parametrisation, eps 1e-8) */
 int nefii_background_sg_bwd(void* stream, int n_rays, int n_sg, const float* lgt_sgs, const float* dirs,
                             const float* g_out, float* g_lgt_acc);

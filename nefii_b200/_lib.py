@@ -40,7 +40,7 @@ SIGNATURES = {
     "nefii_reduce_splits": [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_void_p],
     "nefii_mis_sample": [c_void_p, c_int, c_int] + [c_void_p] * 9,
     "nefii_mis_shade_fwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 13,
-    "nefii_mis_shade_bwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 18,
+    "nefii_mis_shade_bwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 19,
     "nefii_background_sg_bwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "nefii_sg_param_grad": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int],
     "nefii_trace_workspace_bytes": [c_int, c_void_p, c_int, c_int],

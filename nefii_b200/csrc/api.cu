@@ -39,7 +39,7 @@ int mis_shade_fwd(cudaStream_t, int, int, const float*, const float*, int, const
                   const float*, const float*, const float*, const unsigned char*, const float*, float*, float*, float*, float*);
 int mis_shade_bwd(cudaStream_t, int, int, const float*, const float*, int, const float*, const float*, const float*, const float*,
                   const float*, const float*, const float*, const unsigned char*, const float*, const float*, const float*,
-                  const float*, const float*, float*, float*, float*, float*, float*);
+                  const float*, const float*, float*, float*, float*, float*, float*, float*);
 int background_sg_bwd(cudaStream_t, int, int, const float*, const float*, const float*, float*);
 int sg_param_grad(cudaStream_t, int, const float*, const float*, float, float*, int);
 int assemble_input(cudaStream_t, int, int, const float* const*, const int*, const int*, __nv_bfloat16*, __nv_bfloat16*, int, int);
@@ -179,10 +179,11 @@ int nefii_mis_shade_bwd(void* stream, int n, int n_sg, const float* lgt_sgs, con
                         const float* roughness, const float* albedo, const float* normal, const float* view,
                         const float* wi, const float* pdf, const float* weight, const uint8_t* hit, const float* indirect,
                         const float* light, const float* g_rgb, const float* g_specular, const float* g_diffuse,
-                        float* g_roughness, float* g_albedo, float* g_specular_refl, float* g_indirect, float* g_lgt_acc) {
+                        float* g_roughness, float* g_albedo, float* g_specular_refl, float* g_indirect, float* g_lgt_acc,
+                        float* g_normal) {
   return nefii::mis_shade_bwd((cudaStream_t)stream, n, n_sg, lgt_sgs, specular, spec_per_point, roughness, albedo, normal,
                               view, wi, pdf, weight, hit, indirect, light, g_rgb, g_specular, g_diffuse, g_roughness,
-                              g_albedo, g_specular_refl, g_indirect, g_lgt_acc);
+                              g_albedo, g_specular_refl, g_indirect, g_lgt_acc, g_normal);
 }
 int nefii_background_sg_bwd(void* stream, int n_rays, int n_sg, const float* lgt_sgs, const float* dirs, const float* g_out,
                             float* g_lgt_acc) {

@@ -105,7 +105,7 @@ mis_shade_bwd_kernel(int n, int n_sg, const float* __restrict__ lgt, const float
                      const float* __restrict__ indirect, const float* __restrict__ light_in,
                      const float* __restrict__ g_rgb, const float* __restrict__ g_spec, const float* __restrict__ g_diff,
                      float* __restrict__ g_rough, float* __restrict__ g_albedo, float* __restrict__ g_specrefl,
-                     float* __restrict__ g_indirect, float* __restrict__ g_lgt_acc) {
+                     float* __restrict__ g_indirect, float* __restrict__ g_lgt_acc, float* __restrict__ g_normal) {
   extern __shared__ unsigned char smem_raw[];
   MixLobe<float>* sL = reinterpret_cast<MixLobe<float>*>(smem_raw);
   float* sAcc = reinterpret_cast<float*>(sL + n_sg);   // [n_sg][7]
@@ -132,7 +132,7 @@ mis_shade_bwd_kernel(int n, int n_sg, const float* __restrict__ lgt, const float
         gd[c] = gr + (g_diff ? g_diff[i * 3 + c] : 0.f);
       }
       const float r = rough[i];
-      float gr_acc = 0.f, ga[3] = {0.f, 0.f, 0.f}, gsr[3] = {0.f, 0.f, 0.f};
+      float gr_acc = 0.f, ga[3] = {0.f, 0.f, 0.f}, gsr[3] = {0.f, 0.f, 0.f}, gn[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int s = 0; s < 3; ++s) {
         const size_t si = (size_t)s * n + i;
@@ -142,8 +142,10 @@ mis_shade_bwd_kernel(int n, int n_sg, const float* __restrict__ lgt, const float
         const float vis = 1.0f - (hit[si] ? 1.0f : 0.0f);
         ShadeGeom<float> g;
         mism::shade_geom(nn, vv, w, g);
-        float glight[3], gind[3];
-        mism::shade_sample_bwd(g, r, sr, al, light, vis, ind, weight[si], pdf[si], gs, gd, gr_acc, ga, gsr, glight, gind);
+        float glight[3], gind[3], gdots[3];
+        mism::shade_sample_bwd(g, r, sr, al, light, vis, ind, weight[si], pdf[si], gs, gd, gr_acc, ga, gsr, glight, gind,
+                               g_normal ? gdots : nullptr);
+        if (g_normal) mism::shade_geom_bwd_normal(g, vv, w, gdots, gn);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           g_indirect[si * 3 + c] = gind[c];
@@ -153,7 +155,11 @@ mis_shade_bwd_kernel(int n, int n_sg, const float* __restrict__ lgt, const float
       }
       g_rough[i] = gr_acc;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { g_albedo[i * 3 + c] = ga[c]; if (g_specrefl) g_specrefl[i * 3 + c] = gsr[c]; }
+      for (int c = 0; c < 3; ++c) {
+        g_albedo[i * 3 + c] = ga[c];
+        if (g_specrefl) g_specrefl[i * 3 + c] = gsr[c];
+        if (g_normal) g_normal[i * 3 + c] = gn[c];
+      }
     }
     if (g_lgt_acc) {
       for (int t = 0; t < lobes_per_lane; ++t) {
@@ -301,7 +307,7 @@ int mis_shade_bwd(cudaStream_t stream, int n, int n_sg, const float* lgt, const 
                   const float* rough, const float* albedo, const float* normal, const float* view, const float* wi,
                   const float* pdf, const float* weight, const unsigned char* hit, const float* indirect,
                   const float* light, const float* g_rgb, const float* g_spec, const float* g_diff, float* g_rough,
-                  float* g_albedo, float* g_specrefl, float* g_indirect, float* g_lgt_acc) {
+                  float* g_albedo, float* g_specrefl, float* g_indirect, float* g_lgt_acc, float* g_normal) {
   NEFII_CHECK_ARG(n >= 0 && n_sg > 0, "mis_shade_bwd: bad sizes");
   if (n == 0) return NEFII_OK;
   NEFII_CHECK_ARG(lgt && spec && rough && albedo && normal && view && wi && pdf && weight && hit && indirect && light &&
@@ -313,7 +319,7 @@ int mis_shade_bwd(cudaStream_t stream, int n, int n_sg, const float* lgt, const 
   if (grid > kNumSMs * 4) grid = kNumSMs * 4;
   mis_shade_bwd_kernel<<<grid, kBlock, smem, stream>>>(n, n_sg, lgt, spec, spec_per_point ? 3 : 0, rough, albedo, normal,
                                                         view, wi, pdf, weight, hit, indirect, light, g_rgb, g_spec, g_diff,
-                                                        g_rough, g_albedo, g_specrefl, g_indirect, g_lgt_acc);
+                                                        g_rough, g_albedo, g_specrefl, g_indirect, g_lgt_acc, g_normal);
   NEFII_LAUNCH_CHECK();
   return NEFII_OK;
 }

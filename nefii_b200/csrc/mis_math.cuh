@@ -186,18 +186,33 @@ template <typename T> NEFII_HD void env_light(const MixLobe<T>* lobes, int n_sg,
 // geometry-only factors of one shading sample (no gradient flows through them)
 template <typename T> struct ShadeGeom {
   T nh, E, d1, d2, cosn;
+  T hu[3];             // unit half vector (for the gradient w.r.t. the normal)
+  T nh_raw, d1_raw, d2_raw;   // the three dot products with the normal before clamp(min=0)
 };
 
 template <typename T> NEFII_HD void shade_geom(const T* n, const T* v, const T* w, ShadeGeom<T>& g) {
   T h[3] = {w[0] + v[0], w[1] + v[1], w[2] + v[2]};
-  T hu[3];
-  sgm::unit3(h, hu);
-  g.nh = clamp_min(dot3(n, hu), T(0));
-  const T vh = clamp_min(dot3(v, hu), T(0));
+  sgm::unit3(h, g.hu);
+  g.nh_raw = dot3(n, g.hu);
+  g.nh = clamp_min(g.nh_raw, T(0));
+  const T vh = clamp_min(dot3(v, g.hu), T(0));
   g.E = m_pow(T(2), -(T(5.55473) * vh + T(6.8316)) * vh);
-  g.d1 = clamp_min(dot3(v, n), T(0));
-  g.d2 = clamp_min(dot3(w, n), T(0));
+  g.d1_raw = dot3(v, n);
+  g.d2_raw = dot3(w, n);
+  g.d1 = clamp_min(g.d1_raw, T(0));
+  g.d2 = clamp_min(g.d2_raw, T(0));
   g.cosn = g.d2;
+}
+
+// d/d normal from the gradients w.r.t. the three clamped dot products (n.h, v.n, w.n); torch.clamp(min=0) passes the
+// gradient where its input is >= 0.  Only needed when the geometry trains (the normal is d sdf/dx with a graph).
+template <typename T>
+NEFII_HD void shade_geom_bwd_normal(const ShadeGeom<T>& g, const T* v, const T* w, const T* g_dots, T* g_n) {
+  const T a = (g.nh_raw >= T(0)) ? g_dots[0] : T(0);
+  const T b = (g.d1_raw >= T(0)) ? g_dots[1] : T(0);
+  const T c = (g.d2_raw >= T(0)) ? g_dots[2] : T(0);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) g_n[i] += (a * g.hu[i] + b * v[i]) + c * w[i];
 }
 
 // One sample of the estimator (path_tracing_render.py:1406-1476): spec[3], diff[3] after the clamp.
@@ -231,7 +246,7 @@ NEFII_HD void shade_sample(const ShadeGeom<T>& g, T rough, const T* spec_refl, c
 template <typename T>
 NEFII_HD void shade_sample_bwd(const ShadeGeom<T>& g, T rough, const T* spec_refl, const T* albedo, const T* light, T vis,
                                const T* indirect, T weight, T pdf, const T* gs, const T* gd, T& g_rough, T* g_albedo,
-                               T* g_spec_refl, T* g_light, T* g_indirect) {
+                               T* g_spec_refl, T* g_light, T* g_indirect, T* g_dots = nullptr) {
   const T r2 = rough * rough;
   const T r4 = r2 * r2;
   const T nh2 = g.nh * g.nh;
@@ -244,7 +259,7 @@ NEFII_HD void shade_sample_bwd(const ShadeGeom<T>& g, T rough, const T* spec_ref
   const T G = G1 * G2;
   const T den = (T(4) * g.d1) * g.d2 + K<T>::eps();
   const T q = (weight * g.cosn) / pdf;
-  T g_DG = T(0);
+  T g_DG = T(0), g_den = T(0), g_cosn = T(0);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const T F = spec_refl[c] + (T(1) - spec_refl[c]) * g.E;
@@ -263,11 +278,21 @@ NEFII_HD void shade_sample_bwd(const ShadeGeom<T>& g, T rough, const T* spec_ref
     const T g_F = g_fs * (D * G) / den;
     g_spec_refl[c] += g_F * (T(1) - g.E);
     g_DG += g_fs * F / den;
+    g_den += g_fs * (-fs / den);
+    g_cosn += (ms * fs + md * a_pi) * ((weight * la) / pdf);
   }
   const T g_D = g_DG * G, g_G = g_DG * D;
   const T dD_dr4 = -D / r4 + T(2) * D * (T(1) - nh2) / (root * r4 * r4);
   const T dG_dk = (-g.d1 * (T(1) - g.d1) / (den1 * den1)) * G2 + G1 * (-g.d2 * (T(1) - g.d2) / (den2 * den2));
   g_rough += g_D * dD_dr4 * (T(4) * rough * r2) + g_G * dG_dk * ((rough + T(1)) * T(0.25));
+  if (g_dots != nullptr) {
+    // gradients w.r.t. the clamped dot products n.h (through D), v.n (through G1 and the denominator) and w.n (G2, the
+    // denominator and the cosine factor)
+    const T droot_dnh = T(2) * g.nh * (T(1) - T(1) / r4);
+    g_dots[0] = g_D * (T(-2) * D / root) * droot_dnh;
+    g_dots[1] = g_G * G2 * ((k + K<T>::eps()) / (den1 * den1)) + g_den * (T(4) * g.d2);
+    g_dots[2] = g_G * G1 * ((k + K<T>::eps()) / (den2 * den2)) + g_den * (T(4) * g.d1) + g_cosn;
+  }
 }
 
 }  // namespace mism

@@ -55,6 +55,7 @@ class _MisShade(torch.autograd.Function):
         g_ind = torch.zeros(3, n, 3, device=dev)
         acc = torch.zeros(lgt.shape[0], 7, device=dev)
         g_lgt = torch.zeros_like(lgt)
+        g_nrm = torch.zeros(n, 3, device=dev) if ctx.needs_input_grad[4] else None
         if n:
             lib = _lib.raw()
             _lib.check(lib.nefii_mis_shade_bwd(
@@ -62,12 +63,12 @@ class _MisShade(torch.autograd.Function):
                 rough.data_ptr(), albedo.data_ptr(), normal.data_ptr(), view.data_ptr(), wi.data_ptr(), pdf.data_ptr(),
                 weight.data_ptr(), hit8.data_ptr(), indirect.data_ptr(), light.data_ptr(), g_out[0].data_ptr(),
                 g_out[1].data_ptr(), g_out[2].data_ptr(), g_rough.data_ptr(), g_alb.data_ptr(), g_sr.data_ptr(),
-                g_ind.data_ptr(), acc.data_ptr()))
+                g_ind.data_ptr(), acc.data_ptr(), g_nrm.data_ptr() if g_nrm is not None else None))
             _lib.check(lib.nefii_sg_param_grad(_lib.stream_ptr(dev), lgt.shape[0], lgt.data_ptr(), acc.data_ptr(), 1e-6,
                                                g_lgt.data_ptr(), 0))
         rough_shape, spec_shape = ctx.shapes
         g_spec = g_sr if ctx.per_point else g_sr.sum(0, keepdim=True)
-        return (g_lgt, g_spec.reshape(spec_shape), g_rough.reshape(rough_shape), g_alb, None, None, None, None, None, None, g_ind)
+        return (g_lgt, g_spec.reshape(spec_shape), g_rough.reshape(rough_shape), g_alb, g_nrm, None, None, None, None, None, g_ind)
 
 
 def mis_shade(lgtSGs, specular, roughness, albedo, normal, view, wi, pdf, weight, hit, indirect):

@@ -223,10 +223,11 @@ def dense_mlp(segments, weights, biases, act, skip=0, skip_scale=1.0, want_hidde
     Returns the output layer's raw result [N, n_out] (n_out <= 4); with want_hidden also the last hidden activation
     [N, width] (fp32, detached).  skip / skip_scale: see _DenseMlp."""
     seg_src = [t for t, _ in segments]
-    for t in seg_src:
-        if t.requires_grad:
-            raise _lib.NefiiError("dense_mlp: gradients w.r.t. the MLP inputs are outside the hot-path scope "
-                                  "(geometry must be frozen, as in the reference's step 2)")
+    if torch.is_grad_enabled() and any(t.requires_grad for t in seg_src):
+        # inputs that carry a graph (a trainable geometry: points from SampleNetwork, normals = d sdf/dx, features): the same
+        # stack as a composition of differentiable pieces -- every Linear on the tcgen05 layer GEMM through gemm_nt (defined
+        # below), encoding / bias / activation as torch ops.  Slower than the fused path; step 2 (frozen geometry) never takes it.
+        return _dense_mlp_autograd(segments, weights, biases, act, skip, skip_scale, want_hidden)
     seg_freqs = tuple(f for _, f in segments)
     params = []
     for w, b in zip(weights, biases):
@@ -279,3 +280,27 @@ class _GemmNT(torch.autograd.Function):
 def gemm_nt(a, b):
     """a [M,K], b [N,K] -> a @ b^T [M,N]; differentiable to any order w.r.t. both operands."""
     return _GemmNT.apply(a, b)
+
+
+def _dense_mlp_autograd(segments, weights, biases, act, skip=0, skip_scale=1.0, want_hidden=False):
+    cols = []
+    for t, f in segments:
+        t = t.float()
+        cols.append(t)
+        for k in range(max(f, 0)):
+            cols += [torch.sin(t * float(2 ** k)), torch.cos(t * float(2 ** k))]
+    x0 = torch.cat(cols, dim=-1)
+    fn = {ops.ACT_NONE: lambda z: z, ops.ACT_SOFTPLUS100: lambda z: torch.nn.functional.softplus(z, beta=100),
+          ops.ACT_RELU: torch.relu, ops.ACT_ELU: torch.nn.functional.elu}[act]
+    h = x0
+    n_lin = len(weights)
+    hidden = None
+    for l, (w, b) in enumerate(zip(weights, biases)):
+        if l == n_lin - 1:
+            hidden = h
+        if skip and l == skip:
+            h = torch.cat([h, x0], dim=-1) * skip_scale
+        h = gemm_nt(h, w) + b
+        if l < n_lin - 1:
+            h = fn(h)
+    return (h, hidden.detach()) if want_hidden else h

@@ -89,6 +89,9 @@ class ImplicitNetwork(nn.Module):
         self._n_hidden = self.num_layers - 2
         self._sdf_mlp = None
         self._packed_versions = None
+        # set by IDRNetwork while it renders with a TRAINABLE geometry: forward() then keeps a graph from the feature columns to
+        # the parameters (the fused trainable path returns them detached, which is all the step-1 recipe needs)
+        self.differentiable_features = False
 
     # ---- packed-weight management ---------------------------------------------------------------
     def _layers(self):
@@ -191,7 +194,7 @@ class ImplicitNetwork(nn.Module):
 
     # ---- reference API -----------------------------------------------------------------------------
     def forward(self, input, compute_grad=False):
-        if torch.is_grad_enabled() and input.requires_grad:
+        if torch.is_grad_enabled() and (input.requires_grad or (self.differentiable_features and self._trainable())):
             return self._forward_autograd(input)
         if self._trainable():
             return self._forward_trainable(input)
@@ -367,10 +370,13 @@ class IDRNetwork(nn.Module):
         return self.forward_with_point(input)
 
     # ---- implicit_differentiable_renderer.py:312-501 ---------------------------------------------------
-    def forward_with_uv(self, input, uniforms=None, trace_uniforms=None):
-        if self.training and not self.state_freeze_geo:
-            raise _lib.NefiiError("nefii_b200: training with an un-frozen geometry (step 1 / eikonal + SampleNetwork) is "
-                                  "outside the accelerated path; call freeze_geometry() as run_s2.sh does")
+    def forward_with_uv(self, input, uniforms=None, trace_uniforms=None, eikonal_points=None):
+        """uniforms / trace_uniforms / eikonal_points: optional injected random numbers (parity tests); by default they are
+        drawn like the reference draws them."""
+        unfrozen = self.training and not self.state_freeze_geo and torch.is_grad_enabled()
+        if unfrozen and self.render_type != "pt_render_indirect_mlp":
+            raise _lib.NefiiError("nefii_b200: a trainable geometry is supported with render_type pt_render_indirect_mlp "
+                                  "(render_with_sg has no gradient w.r.t. the normals)")
         intrinsics = input["intrinsics"]
         uv = input["uv"]
         pose = input["pose"]
@@ -391,10 +397,13 @@ class IDRNetwork(nn.Module):
                                                                  object_mask=object_mask, ray_directions=ray_dirs,
                                                                  uniforms=trace_uniforms)
             points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
-            sdf_all, _, _ = self.implicit_network.evaluate(points)
-            sdf_output = sdf_all.unsqueeze(-1)
+            if not unfrozen:
+                sdf_all, _, _ = self.implicit_network.evaluate(points)
+                sdf_output = sdf_all.unsqueeze(-1)
+        if unfrozen:      # the mask loss reaches the geometry through sdf_output (:354): fused trainable stack
+            sdf_output = self.implicit_network._forward_trainable(points)[:, 0:1]
         ray_dirs = ray_dirs.reshape(-1, 3)
-        surface_mask = network_object_mask
+        surface_mask = (network_object_mask & object_mask) if unfrozen else network_object_mask
         n_rays = points.shape[0]
         # host sync 1 of 2 per forward: the number of surface hits sizes everything downstream.  All gathers / scatters below
         # use the index list (index_select / index_copy): no further boolean-mask round trips.
@@ -402,6 +411,22 @@ class IDRNetwork(nn.Module):
         n_hit = surface_idx.shape[0]
         differentiable_surface_points = points.index_select(0, surface_idx)
         grad_theta = None
+        if unfrozen:
+            # reference :357-389 -- eikonal samples, d sdf/dx with a graph (second-order path), differentiable intersection
+            bound = self.object_bounding_sphere
+            n_eik = batch_size * num_pixels // 2
+            if eikonal_points is None:      # same draw as the reference (CPU generator, :369)
+                eikonal_points = torch.empty(n_eik, 3).uniform_(-bound, bound)
+            eik = torch.cat([eikonal_points.to(points.device, torch.float32), points.detach()], 0)
+            points_all = torch.cat([differentiable_surface_points, eik], dim=0)
+            g = self.implicit_network.gradient(points_all, False)
+            grad_theta = g[n_hit:, 0, :]
+            if n_hit > 0:
+                surface_output = sdf_output.index_select(0, surface_idx)
+                cam_all = cam_loc.unsqueeze(1).expand(batch_size, num_pixels, 3).reshape(-1, 3)
+                differentiable_surface_points = self.sample_network(
+                    surface_output, surface_output.detach(), g[:n_hit, 0, :].detach(), dists.index_select(0, surface_idx).unsqueeze(-1),
+                    cam_all.index_select(0, surface_idx), ray_dirs.index_select(0, surface_idx))
 
         ones = torch.ones_like(points)
         idr_rgb_values, sg_rgb_values, normal_values = ones, ones, ones
@@ -412,7 +437,11 @@ class IDRNetwork(nn.Module):
         ret = {}
         if n_hit > 0:
             view_dirs = -ray_dirs.index_select(0, surface_idx)
-            ret = self.get_rbg_value(differentiable_surface_points, view_dirs, uniforms=uniforms)
+            self.implicit_network.differentiable_features = unfrozen
+            try:
+                ret = self.get_rbg_value(differentiable_surface_points, view_dirs, uniforms=uniforms)
+            finally:
+                self.implicit_network.differentiable_features = False
             idr_rgb_values = ones.index_copy(0, surface_idx, ret['idr_rgb'])
             sg_rgb_values = ones.index_copy(0, surface_idx, ret['sg_rgb'])
             normal_values = ones.index_copy(0, surface_idx, ret['normals'])
@@ -477,10 +506,17 @@ class IDRNetwork(nn.Module):
 
     # ---- implicit_differentiable_renderer.py:529-599 ---------------------------------------------------
     def get_rbg_value(self, points, view_dirs, multi_ray_data_shape=None, uniforms=None):
-        with torch.no_grad():
-            _, feature_vectors, g = self.implicit_network.evaluate(points, want_feat=True, want_grad=True)
+        if self.implicit_network.differentiable_features and torch.is_grad_enabled():
+            # trainable geometry (:533-541): features and normals carry a graph to the SDF parameters and to the points
+            feature_vectors = self.implicit_network(points)[:, 1:]
+            g = self.implicit_network.gradient(points, False)[:, 0, :]
             normals = g / (torch.norm(g, dim=-1, keepdim=True) + 1e-6)
             view_dirs = view_dirs / (torch.norm(view_dirs, dim=-1, keepdim=True) + 1e-6)
+        else:
+            with torch.no_grad():
+                _, feature_vectors, g = self.implicit_network.evaluate(points, want_feat=True, want_grad=True)
+                normals = g / (torch.norm(g, dim=-1, keepdim=True) + 1e-6)
+                view_dirs = view_dirs / (torch.norm(view_dirs, dim=-1, keepdim=True) + 1e-6)
         ret = {'normals': normals}
         idr_rgb = self.rendering_network(points, normals, view_dirs, feature_vectors)
         sg_envmap_material = self.envmap_material_network(points, feature_vectors, normals)

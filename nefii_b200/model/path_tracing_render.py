@@ -35,7 +35,13 @@ def get_visibility_and_indirect_light(light_points, hit_mask, wi, model):
     indirect = torch.zeros(light_points.shape, device=light_points.device, dtype=torch.float32).reshape(-1, 3)
     if idx.shape[0] > 0:
         xs = light_points.reshape(-1, 3).index_select(0, idx)
-        _, feats, grads = model.implicit_network.evaluate(xs, want_feat=True, want_grad=True)
+        if model.implicit_network.differentiable_features and torch.is_grad_enabled():
+            # trainable geometry, diff_geo = False (:2111-2160): the FEATURES at the secondary hits keep their graph to the SDF
+            # parameters (the reference evaluates the network there with grad enabled); the normals are detached
+            feats = model.implicit_network(xs)[:, 1:]
+            grads = model.implicit_network.gradient(xs, no_grad=True)[:, 0, :]
+        else:
+            _, feats, grads = model.implicit_network.evaluate(xs, want_feat=True, want_grad=True)
         normals = grads / (torch.norm(grads, dim=-1, keepdim=True) + 1e-6)
         view = -wi.reshape(-1, 3).index_select(0, idx)
         view = view / (torch.norm(view, dim=-1, keepdim=True) + 1e-6)
@@ -73,8 +79,10 @@ def pt_render_indirect_mlp(lgtSGs, specular_reflectance, roughness, diffuse_albe
         l_pts = l_pts.reshape(3, n, 3)
         l_hit = l_hit.reshape(3, n, 1)
     indirect = get_visibility_and_indirect_light(l_pts, l_hit, wi, model)
+    # a normal that carries a graph (trainable geometry) keeps it through the shading: d / d normal is part of the backward
+    nrm_in = normal.reshape(n, 3) if (torch.is_grad_enabled() and normal.requires_grad) else nrm
     out = integrator.mis_shade(lgtSGs, specular_reflectance.reshape(-1, 3), roughness.reshape(n, 1),
-                               diffuse_albedo.reshape(n, 3), nrm, view, wi, pdf, weight, l_hit, indirect)
+                               diffuse_albedo.reshape(n, 3), nrm_in, view, wi, pdf, weight, l_hit, indirect)
     return {'sg_rgb': out['sg_rgb'].reshape(dots_shape + [3]),
             'sg_specular_rgb': out['sg_specular_rgb'].reshape(dots_shape + [3]),
             'sg_diffuse_rgb': out['sg_diffuse_rgb'].reshape(dots_shape + [3]),

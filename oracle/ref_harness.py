@@ -39,9 +39,10 @@ def build_reference_model(om, render_type="pt_render_indirect_mlp"):
 
 
 @contextlib.contextmanager
-def injected_rng(u7_fn, uniform_vectors):
+def injected_rng(u7_fn, uniform_vectors, eikonal_points=None):
     """Patch torch.rand (7 draws per pt_render call, shapes [N,1] / [N,1,1]) and Tensor.uniform_ on
-    torch.empty(n) (one [n_steps] vector per training-mode tracer call)."""
+    torch.empty(n) (one [n_steps] vector per training-mode tracer call) and on torch.empty(n, 3) (the eikonal samples of a
+    trainable geometry, implicit_differentiable_renderer.py:369)."""
     state = {"u7": None, "col": 0}
     vecs = list(uniform_vectors)
     real_empty = torch.empty
@@ -63,9 +64,16 @@ def injected_rng(u7_fn, uniform_vectors):
         def uniform_(self, a, b):
             return vecs.pop(0).clone()
 
+    class _Eik:
+        def uniform_(self, a, b):
+            return eikonal_points.clone()
+
     def fake_empty(*size, **kw):
         if len(size) == 1 and isinstance(size[0], int) and not kw:
             return _Vec(size[0])
+        if eikonal_points is not None and len(size) == 2 and size[1] == 3 and isinstance(size[0], int) and not kw:
+            assert size[0] == eikonal_points.shape[0], (size, eikonal_points.shape)
+            return _Eik()
         return real_empty(*size, **kw)
 
     with mock.patch.object(torch, "rand", fake_rand), mock.patch.object(torch, "empty", fake_empty):

@@ -25,13 +25,13 @@ template <typename T>
 static void mis_shade_t(int n, int n_sg, const T* lgt, const T* spec, int spec_stride, const T* rough, const T* albedo,
                         const T* normal, const T* view, const T* wi, const T* pdf, const T* weight, const T* vis,
                         const T* indirect, T* out_rgb, T* out_spec, T* out_diff,
-                        const T* g_rgb, T* g_rough, T* g_albedo, T* g_specrefl, T* g_indirect, T* g_lgt_acc) {
+                        const T* g_rgb, T* g_rough, T* g_albedo, T* g_specrefl, T* g_indirect, T* g_lgt_acc, T* g_normal) {
   std::vector<MixLobe<T>> L(n_sg);
   for (int m = 0; m < n_sg; ++m) load_mix_lobe(lgt + 7 * m, L[m]);
   for (int i = 0; i < n; ++i) {
     const T* nn = normal + 3 * i; const T* vv = view + 3 * i;
     T rgb[3] = {0, 0, 0}, st[3] = {0, 0, 0}, dt[3] = {0, 0, 0};
-    T gr = 0, ga[3] = {0, 0, 0}, gsr[3] = {0, 0, 0};
+    T gr = 0, ga[3] = {0, 0, 0}, gsr[3] = {0, 0, 0}, gn[3] = {0, 0, 0};
     for (int s = 0; s < 3; ++s) {
       const size_t si = (size_t)s * n + i;
       T light[3];
@@ -44,9 +44,10 @@ static void mis_shade_t(int n, int n_sg, const T* lgt, const T* spec, int spec_s
       for (int c = 0; c < 3; ++c) { st[c] += sp[c]; dt[c] += df[c]; rgb[c] += sp[c] + df[c]; }
       if (g_rgb) {
         T gs[3] = {g_rgb[3 * i], g_rgb[3 * i + 1], g_rgb[3 * i + 2]};
-        T glight[3], gind[3];
+        T glight[3], gind[3], gdots[3];
         shade_sample_bwd(g, rough[i], spec + (size_t)i * spec_stride, albedo + 3 * i, light, vis[si], indirect + si * 3,
-                         weight[si], pdf[si], gs, gs, gr, ga, gsr, glight, gind);
+                         weight[si], pdf[si], gs, gs, gr, ga, gsr, glight, gind, gdots);
+        shade_geom_bwd_normal(g, vv, wi + si * 3, gdots, gn);
         for (int c = 0; c < 3; ++c) g_indirect[si * 3 + c] = gind[c];
         const T* w = wi + si * 3;
         for (int k = 0; k < n_sg; ++k) {
@@ -63,7 +64,7 @@ static void mis_shade_t(int n, int n_sg, const T* lgt, const T* spec, int spec_s
     for (int c = 0; c < 3; ++c) { out_rgb[3 * i + c] = rgb[c]; out_spec[3 * i + c] = st[c]; out_diff[3 * i + c] = dt[c]; }
     if (g_rgb) {
       g_rough[i] = gr;
-      for (int c = 0; c < 3; ++c) { g_albedo[3 * i + c] = ga[c]; g_specrefl[3 * i + c] = gsr[c]; }
+      for (int c = 0; c < 3; ++c) { g_albedo[3 * i + c] = ga[c]; g_specrefl[3 * i + c] = gsr[c]; if (g_normal) g_normal[3 * i + c] = gn[c]; }
     }
   }
 }
@@ -81,8 +82,8 @@ void emu_mis_shade_f64(int n, int n_sg, const double* lgt, const double* spec, i
                        const double* albedo, const double* normal, const double* view, const double* wi, const double* pdf,
                        const double* weight, const double* vis, const double* indirect, double* out_rgb, double* out_spec,
                        double* out_diff, const double* g_rgb, double* g_rough, double* g_albedo, double* g_specrefl,
-                       double* g_indirect, double* g_lgt_acc) {
+                       double* g_indirect, double* g_lgt_acc, double* g_normal) {
   mis_shade_t<double>(n, n_sg, lgt, spec, spec_stride, rough, albedo, normal, view, wi, pdf, weight, vis, indirect, out_rgb,
-                      out_spec, out_diff, g_rgb, g_rough, g_albedo, g_specrefl, g_indirect, g_lgt_acc);
+                      out_spec, out_diff, g_rgb, g_rough, g_albedo, g_specrefl, g_indirect, g_lgt_acc, g_normal);
 }
 }

@@ -62,19 +62,19 @@ def test_shading_forward_and_backward_f64(emu):
     vis = (torch.rand(3, n, generator=g) > 0.4).to(dt)
     indirect = torch.rand(3, n, 3, generator=g).to(dt)
     spec = torch.rand(n, 3, generator=g).to(dt) * 0.3
-    lgt_r, rough_r, alb_r, spec_r, ind_r = [t.clone().requires_grad_(True) for t in (lgt, rough, albedo, spec, indirect)]
-    ref = mis.shade(lgt_r, spec_r, rough_r, alb_r, normal, view, wi, pdf, mat, vis.unsqueeze(-1), ind_r)
+    lgt_r, rough_r, alb_r, spec_r, ind_r, n_r = [t.clone().requires_grad_(True) for t in (lgt, rough, albedo, spec, indirect, normal)]
+    ref = mis.shade(lgt_r, spec_r, rough_r, alb_r, n_r, view, wi, pdf, mat, vis.unsqueeze(-1), ind_r)
     g_rgb = torch.rand(n, 3, generator=g).to(dt)
     # the emulation feeds the same upstream gradient into the specular and the diffuse estimate
     loss = ((ref["sg_specular_rgb"] + ref["sg_diffuse_rgb"]) * g_rgb).sum()
     loss.backward()
     out = [torch.empty(n, 3, dtype=dt) for _ in range(3)]
     g_rough = torch.empty(n, dtype=dt); g_alb = torch.empty(n, 3, dtype=dt); g_sr = torch.empty(n, 3, dtype=dt)
-    g_ind = torch.empty(3, n, 3, dtype=dt); acc = torch.zeros(lgt.shape[0], 7, dtype=dt)
+    g_ind = torch.empty(3, n, 3, dtype=dt); acc = torch.zeros(lgt.shape[0], 7, dtype=dt); g_n = torch.empty(n, 3, dtype=dt)
     wi_c, pdf_c = wi.contiguous(), pdf[..., 0].contiguous()
     emu.emu_mis_shade_f64(n, lgt.shape[0], _p(lgt), _p(spec), 3, _p(rough), _p(albedo), _p(normal), _p(view), _p(wi_c),
                           _p(pdf_c), _p(weight), _p(vis), _p(indirect), _p(out[0]), _p(out[1]), _p(out[2]), _p(g_rgb),
-                          _p(g_rough), _p(g_alb), _p(g_sr), _p(g_ind), _p(acc))
+                          _p(g_rough), _p(g_alb), _p(g_sr), _p(g_ind), _p(acc), _p(g_n))
     assert torch.allclose(out[0], ref["sg_rgb"].detach(), rtol=1e-9, atol=1e-12)
     assert torch.allclose(out[1], ref["sg_specular_rgb"].detach(), rtol=1e-9, atol=1e-12)
     assert torch.allclose(out[2], ref["sg_diffuse_rgb"].detach(), rtol=1e-9, atol=1e-12)
@@ -82,6 +82,8 @@ def test_shading_forward_and_backward_f64(emu):
     assert torch.allclose(g_alb, alb_r.grad, rtol=1e-7, atol=1e-10)
     assert torch.allclose(g_sr, spec_r.grad, rtol=1e-7, atol=1e-10)
     assert torch.allclose(g_ind, ind_r.grad, rtol=1e-7, atol=1e-10)
+    # d / d normal (only needed when the geometry trains: the normal is d sdf/dx with a graph to the SDF parameters)
+    assert torch.allclose(g_n, n_r.grad, rtol=1e-6, atol=1e-9), (g_n - n_r.grad).abs().max()
     # unit-parametrisation accumulator -> raw parameter gradient (what nefii_sg_param_grad does)
     raw = lgt
     ln = raw[:, :3].norm(dim=-1, keepdim=True)

@@ -142,3 +142,57 @@ def test_neus_layout_sdf_network_matches_reference():
     assert torch.allclose(mine, ref, atol=2e-6, rtol=1e-5)
     g_ref = net.gradient(x.clone(), no_grad=True)[:, 0]
     assert torch.allclose(mlp.sdf_gradient(params, x), g_ref, atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present")
+def test_trainable_geometry_forward_and_gradients_match_reference():
+    """training and not freeze_geometry (implicit_differentiable_renderer.py:354-389, 529-599): eikonal samples, d sdf/dx with
+    create_graph, SampleNetwork, features / normals with a graph through both MLPs and the shading.  The oracle's
+    forward_with_uv_trainable against the REAL IDRNetwork: outputs and the gradients that reach the SDF network."""
+    om = rh.small_model(seed=0)
+    net = rh.build_reference_model(om)
+    net.unfreeze_geometry()
+    net.train()
+    uv, pose, K = rh.camera_batch(10, 2, seed=1)
+    S = uv.shape[1]
+    obj = torch.ones(1, S, dtype=torch.bool)
+    obj[0, ::5] = False
+    g = torch.Generator().manual_seed(7)
+    U = torch.rand(2048, 7, generator=g)
+    vecs = [torch.rand(100, generator=g) for _ in range(2)]
+    eik = (torch.rand(S * 2 // 2, 3, generator=g) * 2 - 1)
+    gt = torch.rand(S, 3, generator=g)
+
+    def loss_of(out):
+        m = out['network_object_mask'] & out['object_mask']
+        l = (out['sg_rgb_values'][m] - gt[m]).abs().mean() + (out['idr_rgb_values'][m] - gt[m]).abs().mean()
+        l = l + 0.1 * ((out['grad_theta'].norm(2, dim=1) - 1) ** 2).mean()
+        nm = ~m
+        l = l + torch.nn.functional.binary_cross_entropy_with_logits(-50 * out['sdf_output'][nm].reshape(-1), out['object_mask'][nm].float()) / 50
+        return l
+
+    with rh.injected_rng(lambda n_: U[:n_], [v.clone() for v in vecs], eikonal_points=eik):
+        ref = net({'uv': uv, 'pose': pose, 'intrinsics': K, 'object_mask': obj})
+    loss_of(ref).backward()
+    for t in om.sdf.W + om.sdf.b + om.radiance.tensors() + om.material.tensors() + [om.lgtSGs]:
+        t.requires_grad_(True)
+    mine = pipeline.forward_with_uv_trainable(om, uv, pose, K, obj, lambda n_: U[:n_], eik, vecs[0], vecs[1])
+    loss_of(mine).backward()
+    assert torch.equal(mine['network_object_mask'], ref['network_object_mask'])
+    for k in ('sg_rgb_values', 'idr_rgb_values', 'normal_values', 'sdf_output', 'grad_theta', 'sg_roughness_values'):
+        assert torch.allclose(mine[k], ref[k].detach(), rtol=2e-4, atol=2e-5), (k, (mine[k] - ref[k]).abs().max())
+    # gradients reaching the SDF network: biases directly, weights through the weight-norm fold (tangential part, g == |v|)
+    for l in range(9):
+        lin = getattr(net.implicit_network, "lin%d" % l)
+        gb_ref, gb = lin.bias.grad, om.sdf.b[l].grad
+        relb = (gb - gb_ref).norm().item() / (gb_ref.norm().item() + 1e-30)
+        assert relb < 5e-3, ("bias", l, relb)            # float32 second-order autograd on both sides, different op orders
+        v = om.sdf.W[l].detach()
+        gW = om.sdf.W[l].grad
+        nrm = v.norm(dim=1, keepdim=True)
+        gv = gW - (gW * v).sum(1, keepdim=True) * v / (nrm * nrm)
+        gv_ref = lin.weight_v.grad
+        rel = (gv - gv_ref).norm().item() / (gv_ref.norm().item() + 1e-30)
+        assert rel < 5e-3, ("weight_v", l, rel)
+    # ... and the light / material / radiance parameters as in the frozen case
+    assert torch.allclose(om.lgtSGs.grad, net.envmap_material_network.lgtSGs.grad, rtol=1e-3, atol=1e-7)
