@@ -61,7 +61,10 @@ int nefii_background_sg_fwd(void* stream, int n_rays, int n_sg,
  * MLP layer GEMM on tcgen05 -- the building block that replaces nn.Linear (+ Softplus/ReLU/ELU) in
  * ImplicitNetwork.forward/.gradient (implicit_differentiable_renderer.py:85-123),
  * RenderingNetwork.forward (:196-241) and EnvmapMaterialNetwork.forward (sg_envmap_material.py:357-425).
- * fp32 values travel as two bf16 planes (hi, lo); see csrc/mlp_gemm.cu.
+ * fp32 values travel as two 16-bit planes (hi, lo); see csrc/mlp_gemm.cu.  Plane format `fmt` of a launch: 0 = bf16 split
+ * (hi = bf16(x), lo = bf16(x - hi): 16 significant bits, fp32's exponent range; the trainable stacks and every backward pass),
+ * 1 = fp16 split (22 significant bits for |x| >= 2^-3, absolute error <= 2^-25 below, |x| < 65504; the SDF network's
+ * inference chain).  Three kind::f16 MMAs per product either way.
  * The struct is a host-side argument block (all pointers inside are device pointers).
  * ------------------------------------------------------------------------------------------- */
 typedef struct nefii_gemm_desc {
@@ -82,6 +85,7 @@ typedef struct nefii_gemm_desc {
   int32_t k_splits; int64_t f32_split_stride; int32_t k_splits_used;   /* split-K: partial s -> dst_f32 + s*stride (floats); k_splits_used is an output */
   int32_t k_flush;                /* K blocks per TMEM partial for this launch (1 = most accurate); 0 = library default */
   int32_t dst_pad_ok;             /* 1: plane columns [dst_ncols, round_up(dst_ncols,128)) may be overwritten (caller refills them) */
+  int32_t fmt;                    /* plane format of a, b, dst, seed and sav: 0 bf16 split, 1 fp16 split */
 } nefii_gemm_desc;
 
 int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* desc /* host */);
@@ -111,12 +115,17 @@ int nefii_gemm_set_k_flush_head(int k_blocks);
 /* first-order compensation of the tensor core's round-toward-zero accumulation: TMEM partial sums of `k_blocks` K blocks are
  * scaled by (1 + rho) when they are added to the fp32 register accumulators; rho = 0 (default): plain sum */
 int nefii_gemm_set_trunc_comp(int k_blocks, float rho);
+/* ... for the partial sums of launches in plane format `fmt` (nefii_gemm_set_trunc_comp sets the bf16 table) */
+int nefii_gemm_set_trunc_comp_fmt(int fmt, int k_blocks, float rho);
 int nefii_gemm_profile_fetch(double* out3 /* host */);
 
 /* fp32 [rows, cols] (row stride ld_src) -> zero-padded bf16 hi/lo planes [rows_pad, cols_pad];
  * transpose != 0 writes the transpose.  Used to pack weights (and test inputs). */
 int nefii_split_to_planes(void* stream, const float* src, int rows, int cols, int ld_src, int transpose, float scale,
                           void* dst_hi, void* dst_lo, int rows_pad, int cols_pad);
+/* ... into planes of format `fmt` (0 bf16 split = nefii_split_to_planes, 1 fp16 split) */
+int nefii_split_to_planes_fmt(void* stream, const float* src, int rows, int cols, int ld_src, int transpose, float scale,
+                              void* dst_hi, void* dst_lo, int rows_pad, int cols_pad, int fmt);
 
 /* ---------------------------------------------------------------------------------------------
  * SDF / feature MLP -- replaces ImplicitNetwork.forward and .gradient(x, no_grad=True),
@@ -137,6 +146,12 @@ typedef struct nefii_sdf_config {
 
 int nefii_sdf_create(void** handle, const nefii_sdf_config* cfg /* host */);
 int nefii_sdf_destroy(void* handle);
+/* Plane format of the network's inference chain (weights, activations, gradient chain): 1 = fp16 split (default; the SDF value
+ * then agrees with an fp32 evaluation to ~2e-7, which is what the depth / shading parity with the reference rests on),
+ * 0 = bf16 split (~2e-6; for networks whose activations or input gradients could exceed fp16's range, |x| < 65504).
+ * NEFII_SDF_FORMAT=bf16|fp16 sets the default at load.  Call before nefii_sdf_set_weights (it drops the packed weights). */
+int nefii_sdf_set_format(void* handle, int fmt);
+int nefii_sdf_get_format(void* handle);
 /* weights / biases: host arrays of n_hidden+1 device pointers; weights[l] is the EFFECTIVE fp32 matrix
  * [out_l, in_l] (weight_norm folded: g * v / |v|), row-major contiguous; the last one is [1 + d_feat, width].
  * Call again whenever the parameters change. */

@@ -57,6 +57,10 @@ SIGNATURES = {
     "nefii_sdf_workspace_bytes": [c_void_p, c_int, c_int],
     "nefii_sdf_eval": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_int],
     "nefii_split_to_planes": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int],
+    "nefii_split_to_planes_fmt": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int],
+    "nefii_sdf_set_format": [c_void_p, c_int],
+    "nefii_sdf_get_format": [c_void_p],
+    "nefii_gemm_set_trunc_comp_fmt": [c_int, c_int, c_float],
     "nefii_idr_loss_fwd": [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_int, c_int, c_float, c_void_p],
     "nefii_idr_loss_bwd": [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_int, c_int, c_float] + [c_void_p] * 6,
 }

@@ -89,7 +89,7 @@ int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* d) {
   e.sav_hi = (const __nv_bfloat16*)d->sav_hi; e.sav_lo = (const __nv_bfloat16*)d->sav_lo; e.sav_ld = d->sav_ld;
   e.sav_ncols = d->sav_ncols; e.sav_scale = d->sav_scale;
   p.k_splits = d->k_splits; p.f32_split_stride = d->f32_split_stride;
-  p.k_flush = d->k_flush; e.dst_pad_ok = d->dst_pad_ok;
+  p.k_flush = d->k_flush; e.dst_pad_ok = d->dst_pad_ok; e.fmt = d->fmt;
   int used = 1;
   p.k_splits_used = &used;
   int rc = nefii::gemm_split_bf16((cudaStream_t)stream, p);
@@ -101,6 +101,12 @@ int nefii_split_to_planes(void* stream, const float* src, int rows, int cols, in
                           void* dst_hi, void* dst_lo, int rows_pad, int cols_pad) {
   return nefii::split_to_planes((cudaStream_t)stream, src, rows, cols, ld_src, transpose, scale, (__nv_bfloat16*)dst_hi,
                                 (__nv_bfloat16*)dst_lo, rows_pad, cols_pad);
+}
+
+int nefii_split_to_planes_fmt(void* stream, const float* src, int rows, int cols, int ld_src, int transpose, float scale,
+                              void* dst_hi, void* dst_lo, int rows_pad, int cols_pad, int fmt) {
+  return nefii::split_to_planes((cudaStream_t)stream, src, rows, cols, ld_src, transpose, scale, (__nv_bfloat16*)dst_hi,
+                                (__nv_bfloat16*)dst_lo, rows_pad, cols_pad, fmt);
 }
 
 int nefii_sdf_create(void** handle, const nefii_sdf_config* cfg) {
@@ -118,6 +124,15 @@ int nefii_sdf_destroy(void* handle) {
   nefii::trace_graph_clear();     // cached trace graphs point into the handle's packed weights
   delete static_cast<nefii::SdfNet*>(handle);
   return NEFII_OK;
+}
+int nefii_sdf_set_format(void* handle, int fmt) {
+  if (!handle) return nefii::set_error(NEFII_ERR_ARG, "nefii_sdf_set_format: null handle");
+  nefii::trace_graph_clear();     // cached trace graphs carry the plane format in their kernel arguments
+  return static_cast<nefii::SdfNet*>(handle)->set_format(fmt);
+}
+int nefii_sdf_get_format(void* handle) {
+  if (!handle) return -1;
+  return static_cast<nefii::SdfNet*>(handle)->format();
 }
 int nefii_sdf_set_weights(void* handle, void* stream, const float* const* weights, const float* const* biases) {
   if (!handle || !weights || !biases) return nefii::set_error(NEFII_ERR_ARG, "nefii_sdf_set_weights: null argument");
@@ -240,6 +255,7 @@ int nefii_gemm_set_pdl(int on) { return nefii::gemm_set_pdl(on); }
 int nefii_gemm_set_k_flush(int k) { return nefii::gemm_set_k_flush(k); }
 int nefii_gemm_set_k_flush_head(int k) { return nefii::gemm_set_k_flush_head(k); }
 int nefii_gemm_set_trunc_comp(int k_blocks, float rho) { return nefii::gemm_set_trunc_comp(k_blocks, rho); }
+int nefii_gemm_set_trunc_comp_fmt(int fmt, int k_blocks, float rho) { return nefii::gemm_set_trunc_comp(k_blocks, rho, fmt); }
 int nefii_gemm_profile_fetch(double* out3) { return nefii::gemm_profile_fetch(out3); }
 
 int nefii_sg_render_bwd(void* stream, int n_rays, int n_sg, int n_mat, const float* lgt_sgs, const float* specular,

@@ -113,7 +113,7 @@ int make_store_map_uncached(CUtensorMap* map, const void* base, int rows, int ld
 
 __global__ void split_to_planes_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, int transpose,
                                        float scale, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                       int rows_pad, int cols_pad) {
+                                       int rows_pad, int cols_pad, int fmt) {
   const long long total = (long long)rows_pad * cols_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols_pad), c = (int)(i % cols_pad);
@@ -125,7 +125,7 @@ __global__ void split_to_planes_kernel(const float* __restrict__ src, int rows, 
     }
     x *= scale;
     __nv_bfloat16 h, l;
-    split2(x, h, l);
+    split2(x, fmt, h, l);
     hi[i] = h;
     lo[i] = l;
   }
@@ -173,10 +173,12 @@ std::atomic<long long> g_epoch{0};
 // truncates it towards zero, so a partial sum comes out short by a factor that depends on its length only.  Measured on B200
 // with `tools/diag_gpu.py trunccomp` (slope of the accumulation error against the exact sum of the three bf16 products, 16384 x
 // 512 x 512, Gaussian and all-positive activations agree to 3 %): 1.02 / 3.9 / 9.9 / 22.1 ulp of 2^-24 at 1 / 2 / 4 / 8 blocks.
+// fp16-split planes (22-bit products instead of 16-bit ones): 1.50 / 4.82 / 11.4 / 24.4 ulp (DIAG_FMT=1, same tool).
 // Other lengths: log-log interpolation.  gemm_set_trunc_comp overrides an entry; NEFII_GEMM_TRUNC_COMP=0 switches it off.
-float default_rho(int L) {
+float default_rho(int L, int fmt) {
   static const float kL[4] = {1.f, 2.f, 4.f, 8.f};
-  static const float kRho[4] = {6.10e-8f, 2.34e-7f, 5.92e-7f, 1.32e-6f};
+  static const float kRhoFmt[2][4] = {{6.10e-8f, 2.34e-7f, 5.92e-7f, 1.32e-6f}, {8.93e-8f, 2.87e-7f, 6.82e-7f, 1.456e-6f}};
+  const float* kRho = kRhoFmt[fmt];
   if (L <= 1) return kRho[0];
   int i = 0;
   while (i < 2 && (float)L > kL[i + 1]) ++i;
@@ -185,14 +187,14 @@ float default_rho(int L) {
 }
 struct RhoTable {
   float v[65];
-  RhoTable() {
+  explicit RhoTable(int fmt) {
     const char* e = getenv("NEFII_GEMM_TRUNC_COMP");
     const bool on = !(e && e[0] == '0');
     v[0] = 0.f;
-    for (int L = 1; L <= 64; ++L) v[L] = on ? default_rho(L) : 0.f;
+    for (int L = 1; L <= 64; ++L) v[L] = on ? default_rho(L, fmt) : 0.f;
   }
 };
-RhoTable g_trunc;
+RhoTable g_trunc[2] = {RhoTable(PLANES_BF16), RhoTable(PLANES_FP16)};   // per PlaneFormat
 std::mutex g_dev_mu;
 bool g_dev_ready[64] = {};
 int g_dev_sms[64] = {};
@@ -252,10 +254,11 @@ int gemm_set_k_flush_head(int k) {
   return NEFII_OK;
 }
 
-int gemm_set_trunc_comp(int k_blocks, float rho) {
+int gemm_set_trunc_comp(int k_blocks, float rho, int fmt) {
   NEFII_CHECK_ARG(k_blocks >= 1 && k_blocks <= 64, "gemm_set_trunc_comp: partial length out of range");
   NEFII_CHECK_ARG(rho > -1e-3f && rho < 1e-3f, "gemm_set_trunc_comp: |rho| must be below 1e-3");
-  g_trunc.v[k_blocks] = rho;
+  NEFII_CHECK_ARG(fmt == PLANES_BF16 || fmt == PLANES_FP16, "gemm_set_trunc_comp: unknown plane format %d", fmt);
+  g_trunc[fmt].v[k_blocks] = rho;
   ++g_epoch;
   return NEFII_OK;
 }
@@ -298,6 +301,7 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   NEFII_CHECK_ARG(p.epi.n_valid > 0 && p.epi.n_valid <= p.n_pad, "gemm_split_bf16: n_valid out of range");
   NEFII_CHECK_ARG(p.epi.n_last <= kMaxLast, "gemm_split_bf16: fused output layer supports at most %d outputs", kMaxLast);
   NEFII_CHECK_ARG(p.k_flush >= 0 && p.k_flush <= 64, "gemm_split_bf16: k_flush out of range");
+  NEFII_CHECK_ARG(p.epi.fmt == PLANES_BF16 || p.epi.fmt == PLANES_FP16, "gemm_split_bf16: unknown plane format %d", p.epi.fmt);
   if (p.rows_cap <= 0) return NEFII_OK;
   int rc;
   if ((rc = gemm_prepare_device())) return rc;
@@ -387,8 +391,9 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
       const int len_full = kf_tail < kb_per ? kf_tail : kb_per;
       const int n_parts = ceil_div(kb_per, len_full);
       const int len_last = kb_per - (n_parts - 1) * len_full;
-      scale_full = 1.0f + g_trunc.v[len_full < 64 ? len_full : 64];
-      scale_last = (splits == 1) ? 1.0f + g_trunc.v[len_last < 64 ? len_last : 64] : scale_full;
+      const RhoTable& rho = g_trunc[p.epi.fmt];
+      scale_full = 1.0f + rho.v[len_full < 64 ? len_full : 64];
+      scale_last = (splits == 1) ? 1.0f + rho.v[len_last < 64 ? len_last : 64] : scale_full;
     }
     NEFII_CUDA(cudaLaunchKernelEx(&cfg, fn, ma_hi, ma_lo, mb_hi, mb_lo, md_hi, md_lo, store_tma, p.count, p.rows_cap, k_blocks, n_chunks, kb_per,
                                   (long long)p.f32_split_stride, g_debug, kf_tail | (kf_head << 8), scale_full, scale_last, p.epi));
@@ -399,15 +404,16 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
 }
 
 int split_to_planes(cudaStream_t stream, const float* src, int rows, int cols, int ld_src, int transpose, float scale,
-                    __nv_bfloat16* hi, __nv_bfloat16* lo, int rows_pad, int cols_pad) {
+                    __nv_bfloat16* hi, __nv_bfloat16* lo, int rows_pad, int cols_pad, int fmt) {
   NEFII_CHECK_ARG(src && hi && lo, "split_to_planes: null pointer");
+  NEFII_CHECK_ARG(fmt == PLANES_BF16 || fmt == PLANES_FP16, "split_to_planes: unknown plane format %d", fmt);
   const int out_rows = transpose ? cols : rows, out_cols = transpose ? rows : cols;
   NEFII_CHECK_ARG(rows_pad >= out_rows && cols_pad >= out_cols, "split_to_planes: padded shape too small");
   const long long total = (long long)rows_pad * cols_pad;
   if (total == 0) return NEFII_OK;
   int blocks = ceil_div(total, 256);
   if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
-  split_to_planes_kernel<<<blocks, 256, 0, stream>>>(src, rows, cols, ld_src, transpose, scale, hi, lo, rows_pad, cols_pad);
+  split_to_planes_kernel<<<blocks, 256, 0, stream>>>(src, rows, cols, ld_src, transpose, scale, hi, lo, rows_pad, cols_pad, fmt);
   NEFII_LAUNCH_CHECK();
   return NEFII_OK;
 }

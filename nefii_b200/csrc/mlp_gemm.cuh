@@ -6,8 +6,10 @@
 namespace nefii {
 
 enum Act : int { ACT_NONE = 0, ACT_SOFTPLUS100 = 1, ACT_RELU = 2, ACT_ELU = 3 };
+// Plane format of one launch (operands, output planes, seed planes and saved activations alike; see mlp_gemm_kernel.cuh)
+enum PlaneFormat : int { PLANES_BF16 = 0, PLANES_FP16 = 1 };
 
-// A value x is carried between layers as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)).
+// A value x is carried between layers as two 16-bit planes (hi = r16(x), lo = r16(x - hi); r16 = bf16 or fp16 rounding).
 struct Planes {
   __nv_bfloat16* hi = nullptr;
   __nv_bfloat16* lo = nullptr;
@@ -17,6 +19,7 @@ struct Planes {
 struct GemmEpilogue {
   int mode = 0;             // 0: forward layer (bias + activation), 1: backward layer (x act'(saved))
   int act = ACT_NONE;
+  int fmt = PLANES_BF16;    // PlaneFormat of every plane this launch reads or writes
   int n_valid = 0;          // output columns [0, n_valid) are real
   const float* bias = nullptr;
   float out_scale = 1.f;    // applied to what is written to dst planes (e.g. 1/sqrt(2) before a skip concat)
@@ -73,7 +76,7 @@ int gemm_set_k_flush(int k);
 int gemm_set_k_flush_head(int k);
 // First-order compensation of the truncating accumulator: a TMEM partial sum of `k_blocks` K blocks is multiplied by
 // (1 + rho) when it is added to the register accumulators.  rho = 0 (default) leaves the sum untouched.
-int gemm_set_trunc_comp(int k_blocks, float rho);
+int gemm_set_trunc_comp(int k_blocks, float rho, int fmt = PLANES_BF16);
 int gemm_profile_enable(int on);
 int gemm_profile_fetch(double* out3);
 bool gemm_profile_active();
@@ -85,6 +88,6 @@ long long gemm_config_epoch();
 // fp32 [rows, cols] (row stride ld_src) -> zero-padded bf16 planes [rows_pad, cols_pad];
 // transpose=1 writes src^T.
 int split_to_planes(cudaStream_t stream, const float* src, int rows, int cols, int ld_src, int transpose,
-                    float scale, __nv_bfloat16* hi, __nv_bfloat16* lo, int rows_pad, int cols_pad);
+                    float scale, __nv_bfloat16* hi, __nv_bfloat16* lo, int rows_pad, int cols_pad, int fmt = PLANES_BF16);
 
 }  // namespace nefii

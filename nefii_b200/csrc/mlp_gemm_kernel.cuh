@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include "mlp_gemm.cuh"
 
@@ -184,10 +185,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M=128, N=256
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: 16-bit operands -> fp32, both operands K-major, M=128, N=256.  Operand format bits
+// (a: 7..9, b: 10..12): 1 = bf16 (kIdescBf16 added for PLANES_BF16), 0 = fp16 (PLANES_FP16).
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 // CTA pair: M = 256 (128 rows in each CTA's TMEM), N = 256
-constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr uint32_t kIdescPair = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr uint32_t kIdescBf16 = (1u << 7) | (1u << 10);
 
 // ---- branch-free activation helpers (fast intrinsics: the error they add, <= 1e-9 absolute on a
 // softplus output, is far below the bf16x3 product error; the SG kernels never use them) ----------
@@ -225,29 +228,58 @@ template <int ACT> __device__ __forceinline__ float act_bwd_from_output(float h)
   return 1.f;
 }
 
-__device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// Plane formats (`fmt`, uniform over a launch).  PLANES_BF16: hi = bf16(x), lo = bf16(x - hi): 16 significant bits, fp32's
+// exponent range (gradients of any magnitude).  PLANES_FP16: hi = fp16(x), lo = fp16(x - hi): 22 significant bits while
+// |x| >= 2^-3 and an absolute error <= 2^-25 below that (lo becomes subnormal), |x| < 65504 -- the format of the SDF
+// network's inference chain, whose activations and input gradients are O(1) (csrc/sdf_mlp.cu).  The planes are 16-bit storage
+// either way (the pointers are typed __nv_bfloat16 for both).
+__device__ __forceinline__ void split_pair(float a, float b, int fmt, uint32_t& wh, uint32_t& wl) {
+  if (fmt == PLANES_FP16) {
+    const __half2 h2 = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+    wh = *reinterpret_cast<const uint32_t*>(&h2);
+    wl = *reinterpret_cast<const uint32_t*>(&l2);
+  } else {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    wh = *reinterpret_cast<const uint32_t*>(&h2);
+    wl = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+}
+// hi + lo of two neighbouring plane elements
+__device__ __forceinline__ float2 join_pair(uint32_t wh, uint32_t wl, int fmt) {
+  float2 hf, lf;
+  if (fmt == PLANES_FP16) {
+    hf = __half22float2(*reinterpret_cast<const __half2*>(&wh));
+    lf = __half22float2(*reinterpret_cast<const __half2*>(&wl));
+  } else {
+    hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wh));
+    lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wl));
+  }
+  return make_float2(hf.x + lf.x, hf.y + lf.y);
+}
+__device__ __forceinline__ void split2(float x, int fmt, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  uint32_t wh, wl;
+  split_pair(x, 0.f, fmt, wh, wl);
+  const unsigned short h = (unsigned short)(wh & 0xFFFFu), l = (unsigned short)(wl & 0xFFFFu);
+  hi = *reinterpret_cast<const __nv_bfloat16*>(&h);
+  lo = *reinterpret_cast<const __nv_bfloat16*>(&l);
 }
 
-// pack 8 floats into 8 bf16 hi (uint4) + 8 bf16 lo (uint4)
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+// pack 8 floats into 8 hi (uint4) + 8 lo (uint4) plane elements
+__device__ __forceinline__ void split8(const float* v, int fmt, uint4& hi, uint4& lo) {
   uint32_t wh[4], wl[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    const float2 hf = __bfloat1622float2(h2);
-    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-    wh[j] = *reinterpret_cast<const uint32_t*>(&h2);
-    wl[j] = *reinterpret_cast<const uint32_t*>(&l2);
-  }
+  for (int j = 0; j < 4; ++j) split_pair(v[2 * j], v[2 * j + 1], fmt, wh[j], wl[j]);
   hi = make_uint4(wh[0], wh[1], wh[2], wh[3]);
   lo = make_uint4(wl[0], wl[1], wl[2], wl[3]);
 }
 
 // Store 32 consecutive values of one row as planes starting at plane column `col` (= col_base + n0);
 // elements with n0 + j >= n_limit are not written.  16-byte stores when a group of 8 is complete and aligned.
-__device__ __forceinline__ void store_planes32(const Planes& dst, long long row, int col, int n0, int n_limit,
+__device__ __forceinline__ void store_planes32(const Planes& dst, int fmt, long long row, int col, int n0, int n_limit,
                                                const float* vals) {
   __nv_bfloat16* ph = dst.hi + row * dst.ld + col;
   __nv_bfloat16* pl = dst.lo + row * dst.ld + col;
@@ -256,7 +288,7 @@ __device__ __forceinline__ void store_planes32(const Planes& dst, long long row,
   for (int g = 0; g < 4; ++g) {
     if (aligned && n0 + 8 * g + 8 <= n_limit) {
       uint4 h, l;
-      split8(vals + 8 * g, h, l);
+      split8(vals + 8 * g, fmt, h, l);
       *reinterpret_cast<uint4*>(ph + 8 * g) = h;
       *reinterpret_cast<uint4*>(pl + 8 * g) = l;
     } else if (n0 + 8 * g < n_limit) {
@@ -264,7 +296,7 @@ __device__ __forceinline__ void store_planes32(const Planes& dst, long long row,
       for (int j = 0; j < 8; ++j) {
         if (n0 + 8 * g + j < n_limit) {
           __nv_bfloat16 h, l;
-          split2(vals[8 * g + j], h, l);
+          split2(vals[8 * g + j], fmt, h, l);
           ph[8 * g + j] = h;
           pl[8 * g + j] = l;
         }
@@ -316,7 +348,8 @@ struct FastStore {
 };
 
 template <int ACT, bool TMA>
-__device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bias4, int n_span0, float scale, const FastStore& fs, int dbg) {
+__device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bias4, int n_span0, float scale, const FastStore& fs, int dbg,
+                                                 int fmt) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int c = 0; c < kColsPerWarp / 32; ++c) {
@@ -330,7 +363,7 @@ __device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bia
       o[2] = act_fwd<ACT>(v[8 * g + 2] + ba.z) * scale; o[3] = act_fwd<ACT>(v[8 * g + 3] + ba.w) * scale;
       o[4] = act_fwd<ACT>(v[8 * g + 4] + bb.x) * scale; o[5] = act_fwd<ACT>(v[8 * g + 5] + bb.y) * scale;
       o[6] = act_fwd<ACT>(v[8 * g + 6] + bb.z) * scale; o[7] = act_fwd<ACT>(v[8 * g + 7] + bb.w) * scale;
-      split8(o, hq[g], lq[g]);
+      split8(o, fmt, hq[g], lq[g]);
     }
     if (dbg & 16) {   // timing ablation: math only
       if (hq[0].x == 0x7fc07fc1u && lq[3].w == 0x12345678u) fs.p_hi[c] = __float2bfloat16(1.f);
@@ -381,7 +414,7 @@ __device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bia
 // leave as bf16 planes through the same staged bulk tensor stores as the forward path; no per-element predicates.
 template <int ACT>
 __device__ __forceinline__ void finish_span_bwd_fast(float* acc, const __nv_bfloat16* sav_hi_row, const __nv_bfloat16* sav_lo_row,
-                                                     float sav_scale, int n_span0, float scale, const FastStore& fs) {
+                                                     float sav_scale, int n_span0, float scale, const FastStore& fs, int fmt) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int c = 0; c < kColsPerWarp / 32; ++c) {
@@ -396,12 +429,11 @@ __device__ __forceinline__ void finish_span_bwd_fast(float* acc, const __nv_bflo
       float o[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
-        const float2 lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[j]));
-        o[2 * j] = v[8 * g + 2 * j] * act_bwd_from_output<ACT>((hf.x + lf.x) * sav_scale) * scale;
-        o[2 * j + 1] = v[8 * g + 2 * j + 1] * act_bwd_from_output<ACT>((hf.y + lf.y) * sav_scale) * scale;
+        const float2 sv = join_pair(hw[j], lw[j], fmt);
+        o[2 * j] = v[8 * g + 2 * j] * act_bwd_from_output<ACT>(sv.x * sav_scale) * scale;
+        o[2 * j + 1] = v[8 * g + 2 * j + 1] * act_bwd_from_output<ACT>(sv.y * sav_scale) * scale;
       }
-      split8(o, hq[g], lq[g]);
+      split8(o, fmt, hq[g], lq[g]);
     }
     if (lane == 0) bulk_wait_read_all();   // the previous bulk stores have read the staging tile
     __syncwarp();
@@ -434,8 +466,10 @@ __device__ __forceinline__ void finish_span_fused_fast(const float* acc, const f
 #pragma unroll
     for (int q = 0; q < kMaxLast; ++q) {
       if (q < n_last) {
+        // group of four summed as a tree, then one add into the running sum: the chain of roundings per row is 32 long
+        // instead of 128 (the output layer's own rounding error was 2.4e-7 rms on an SDF value, as much as the layers before it)
         const float4 w = s_w4[q * (kBiasSmemFloats / 4) + n_span0 / 4 + g];
-        part[q] = fmaf(h3, w.w, fmaf(h2, w.z, fmaf(h1, w.y, fmaf(h0, w.x, part[q]))));
+        part[q] += fmaf(h1, w.y, h0 * w.x) + fmaf(h3, w.w, h2 * w.z);
       }
     }
   }
@@ -458,14 +492,18 @@ __device__ __forceinline__ void finish_group(const GemmEpilogue& epi, float* v, 
 #pragma unroll
       for (int q = 0; q < kMaxLast; ++q) {
         if (q < epi.n_last) {
-          float acc = part[q];
+          // the same association as finish_span_fused_fast (groups of four as a tree, one add per group): an evaluation
+          // returns the same SDF bits whether or not features / gradient seeds leave the tile
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            const float w = (n < epi.n_valid) ? __ldg(epi.w_last + (size_t)q * epi.w_last_ld + n) : 0.f;
-            acc = fmaf(v[j], w, acc);
+          for (int g = 0; g < 8; ++g) {
+            float w4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = n0 + 4 * g + j;
+              w4[j] = (n < epi.n_valid) ? __ldg(epi.w_last + (size_t)q * epi.w_last_ld + n) : 0.f;
+            }
+            part[q] += fmaf(v[4 * g + 1], w4[1], v[4 * g] * w4[0]) + fmaf(v[4 * g + 3], w4[3], v[4 * g + 2] * w4[2]);
           }
-          part[q] = acc;
         }
       }
       if (epi.seed.hi != nullptr && row_ok) {
@@ -480,7 +518,7 @@ __device__ __forceinline__ void finish_group(const GemmEpilogue& epi, float* v, 
           }
           // the seed buffer is a full-width plane buffer: 16-byte stores are always aligned and in range
           uint4 h, l;
-          split8(sv, h, l);
+          split8(sv, epi.fmt, h, l);
           *reinterpret_cast<uint4*>(epi.seed.hi + row * epi.seed.ld + n0 + 8 * g) = h;
           *reinterpret_cast<uint4*>(epi.seed.lo + row * epi.seed.ld + n0 + 8 * g) = l;
         }
@@ -496,11 +534,10 @@ __device__ __forceinline__ void finish_group(const GemmEpilogue& epi, float* v, 
         const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
-          const float2 lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[j]));
+          const float2 sv = join_pair(hw[j], lw[j], epi.fmt);
           const int n = n0 + 8 * g + 2 * j;
-          const float d0 = act_bwd_from_output<ACT>((hf.x + lf.x) * epi.sav_scale);
-          const float d1 = act_bwd_from_output<ACT>((hf.y + lf.y) * epi.sav_scale);
+          const float d0 = act_bwd_from_output<ACT>(sv.x * epi.sav_scale);
+          const float d1 = act_bwd_from_output<ACT>(sv.y * epi.sav_scale);
           v[8 * g + 2 * j] *= (n < epi.sav_ncols) ? d0 : 1.f;
           v[8 * g + 2 * j + 1] *= (n + 1 < epi.sav_ncols) ? d1 : 1.f;
         }
@@ -514,7 +551,7 @@ __device__ __forceinline__ void finish_group(const GemmEpilogue& epi, float* v, 
   if (epi.dst.hi != nullptr && n0 < dst_end) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (n0 + j < epi.dst_ncols) ? v[j] * epi.out_scale : 0.f;
-    store_planes32(epi.dst, row, epi.dst_col0 + n0, n0, dst_end, v);
+    store_planes32(epi.dst, epi.fmt, row, epi.dst_col0 + n0, n0, dst_end, v);
   }
 }
 
@@ -685,6 +722,7 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       // buffers let the MMAs of up to two partials run ahead of the epilogue's final math.
       const PartSched sched{(k_flush >> 8) ? (k_flush >> 8) : (k_flush & 255), k_flush & 255, k_blocks};
       const int parts_per_chunk = sched.count();
+      const uint32_t idesc = (CL == 1 ? kIdesc : kIdescPair) | (epi.fmt == PLANES_FP16 ? 0u : kIdescBf16);
       uint32_t pcount = 0;
       for (int m_tile = m_tile0; NEFII_TILE_LIVE(m_tile); m_tile += tile_stride)
       for (int nc = nc_begin; nc < nc_end; ++nc) {
@@ -707,18 +745,18 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
               for (int k = 0; k < kBK / UMMA_K; ++k) {
                 const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step inside the swizzle row
                 if (CL == 1) {
-                  tc_mma_bf16(tmem_d, a_hi + koff, b_lo + koff, kIdesc, (k != 0) ? 1u : fresh);
-                  tc_mma_bf16(tmem_d, a_lo + koff, b_hi + koff, kIdesc, 1);
+                  tc_mma_bf16(tmem_d, a_hi + koff, b_lo + koff, idesc, (k != 0) ? 1u : fresh);
+                  tc_mma_bf16(tmem_d, a_lo + koff, b_hi + koff, idesc, 1);
                 } else {
-                  tc_mma_bf16_pair(tmem_d, a_hi + koff, b_lo + koff, kIdescPair, (k != 0) ? 1u : fresh);
-                  tc_mma_bf16_pair(tmem_d, a_lo + koff, b_hi + koff, kIdescPair, 1);
+                  tc_mma_bf16_pair(tmem_d, a_hi + koff, b_lo + koff, idesc, (k != 0) ? 1u : fresh);
+                  tc_mma_bf16_pair(tmem_d, a_lo + koff, b_hi + koff, idesc, 1);
                 }
               }
 #pragma unroll
               for (int k = 0; k < kBK / UMMA_K; ++k) {
                 const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-                if (CL == 1) tc_mma_bf16(tmem_d, a_hi + koff, b_hi + koff, kIdesc, 1);
-                else tc_mma_bf16_pair(tmem_d, a_hi + koff, b_hi + koff, kIdescPair, 1);
+                if (CL == 1) tc_mma_bf16(tmem_d, a_hi + koff, b_hi + koff, idesc, 1);
+                else tc_mma_bf16_pair(tmem_d, a_hi + koff, b_hi + koff, idesc, 1);
               }
             }
             // frees the operand stage (in both CTAs of a pair) once these MMAs retire
@@ -833,15 +871,15 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       if (fast_layer && n_span0 + kColsPerWarp <= n_fast) {
         // whole 32-row tiles leave by bulk tensor store; the ragged last tile keeps per-row predicates
         if (store_tma && row - lane + 32 <= m_limit)
-          finish_span_fast<ACT, true>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg);
+          finish_span_fast<ACT, true>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg, epi.fmt);
         else
-          finish_span_fast<ACT, false>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg);
+          finish_span_fast<ACT, false>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg, epi.fmt);
         continue;
       }
       if (fast_bwd && row - lane + 32 <= m_limit && n_span0 + kColsPerWarp <= epi.n_valid && n_span0 + kColsPerWarp <= epi.dst_ncols &&
           n_span0 + kColsPerWarp <= epi.sav_ncols) {
         finish_span_bwd_fast<ACT>(acc, epi.sav_hi + row * epi.sav_ld, epi.sav_lo + row * epi.sav_ld, epi.sav_scale, n_span0,
-                                  epi.out_scale, fs);
+                                  epi.out_scale, fs, epi.fmt);
         continue;
       }
       if (fast_fused && n_span0 + kColsPerWarp <= epi.n_valid) {

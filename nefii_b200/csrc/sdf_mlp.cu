@@ -2,8 +2,11 @@
 // sequenced over the tcgen05 layer GEMM: positional encoding -> n_hidden x (Linear + Softplus(100)),
 // skip concat at `skip_layer`, fused 1-wide output layer, and the closed-form input gradient
 // (d sdf / d x, what ImplicitNetwork.gradient obtains through autograd) as a reverse chain of GEMMs.
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "mlp_gemm.cuh"
 #include "sdf_mlp.cuh"
 
@@ -14,9 +17,21 @@ namespace {
 constexpr float kInvSqrt2 = 0.70710678118654752f;
 constexpr float kSqrt2 = 1.41421356237309505f;
 
-__device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// two neighbouring plane elements (hi words, lo words) of format fmt (PlaneFormat, mlp_gemm.cuh)
+__device__ __forceinline__ void split_pair(float a, float b, int fmt, uint32_t& wh, uint32_t& wl) {
+  if (fmt == PLANES_FP16) {
+    const __half2 h2 = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+    wh = *reinterpret_cast<const uint32_t*>(&h2);
+    wl = *reinterpret_cast<const uint32_t*>(&l2);
+  } else {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    wh = *reinterpret_cast<const uint32_t*>(&h2);
+    wl = *reinterpret_cast<const uint32_t*>(&l2);
+  }
 }
 
 // Writes PE(x) * scale into plane columns [col0, col0 + d_pe) and zeros up to col0 + zero_to.
@@ -29,7 +44,7 @@ constexpr int kEncStride = kEncMaxWidth + 1;   // odd stride: conflict-free row-
 
 __global__ void __launch_bounds__(kEncWarps * 32)
 encode_kernel(const float* __restrict__ x, const int* __restrict__ count, int rows_cap, int n_freqs, float scale, Planes dst,
-              int col0, int zero_to) {
+              int col0, int zero_to, int fmt) {
   __shared__ float s_v[kEncWarps][32 * kEncStride];
   int limit = rows_cap;
   if (count) limit = min(limit, *count);
@@ -68,13 +83,7 @@ encode_kernel(const float* __restrict__ x, const int* __restrict__ count, int ro
         const float* v = sv + r * kEncStride + c0;
         uint32_t wh[4], wl[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-          const float2 hf = __bfloat1622float2(h2);
-          const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * q] - hf.x, v[2 * q + 1] - hf.y);
-          wh[q] = *reinterpret_cast<const uint32_t*>(&h2);
-          wl[q] = *reinterpret_cast<const uint32_t*>(&l2);
-        }
+        for (int q = 0; q < 4; ++q) split_pair(v[2 * q], v[2 * q + 1], fmt, wh[q], wl[q]);
         const size_t off = (size_t)(row0 + r) * dst.ld + col0 + c0;
         *reinterpret_cast<uint4*>(dst.hi + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
         *reinterpret_cast<uint4*>(dst.lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
@@ -82,11 +91,11 @@ encode_kernel(const float* __restrict__ x, const int* __restrict__ count, int ro
     } else {
       for (int e = lane; e < n_rows * width; e += 32) {
         const int r = e / width, j = e % width;
-        __nv_bfloat16 h, l;
-        split2(sv[r * kEncStride + j], h, l);
+        uint32_t wh, wl;
+        split_pair(sv[r * kEncStride + j], 0.f, fmt, wh, wl);
         const size_t off = (size_t)(row0 + r) * dst.ld + col0 + j;
-        dst.hi[off] = h;
-        dst.lo[off] = l;
+        reinterpret_cast<unsigned short*>(dst.hi)[off] = (unsigned short)(wh & 0xFFFFu);
+        reinterpret_cast<unsigned short*>(dst.lo)[off] = (unsigned short)(wl & 0xFFFFu);
       }
     }
     __syncwarp();
@@ -123,6 +132,13 @@ __global__ void pe_backward_kernel(const float* __restrict__ x, const int* __res
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// fp16 split by default: the depth / shading parity with the reference rests on SDF values that agree with an fp32 evaluation
+// to a few 1e-7; NEFII_SDF_FORMAT=bf16 selects the wide-range format at load.
+int default_format() {
+  const char* e = getenv("NEFII_SDF_FORMAT");
+  return (e && (!strcmp(e, "bf16") || !strcmp(e, "0"))) ? PLANES_BF16 : PLANES_FP16;
+}
+
 }  // namespace
 
 struct SdfNet::Impl {
@@ -141,6 +157,7 @@ struct SdfNet::Impl {
   float* b_feat = nullptr;
   void* blob = nullptr;
   bool has_weights = false;
+  int fmt = default_format();
 };
 
 SdfNet::SdfNet() : impl_(new Impl) {}
@@ -150,6 +167,13 @@ SdfNet::~SdfNet() {
 }
 
 const SdfConfig& SdfNet::config() const { return impl_->cfg; }
+int SdfNet::format() const { return impl_->fmt; }
+int SdfNet::set_format(int fmt) {
+  NEFII_CHECK_ARG(fmt == PLANES_BF16 || fmt == PLANES_FP16, "sdf: unknown plane format %d", fmt);
+  if (fmt != impl_->fmt) impl_->has_weights = false;
+  impl_->fmt = fmt;
+  return NEFII_OK;
+}
 
 int SdfNet::init(const SdfConfig& cfg) {
   NEFII_CHECK_ARG(cfg.d_in == 3, "sdf: d_in must be 3");
@@ -219,10 +243,10 @@ int SdfNet::set_weights(cudaStream_t stream, const float* const* weights, const 
   int rc;
   for (int l = 0; l < s.n_lin - 1; ++l) {
     if ((rc = split_to_planes(stream, weights[l], s.out_dim[l], s.in_dim[l], s.in_dim[l], 0, 1.f, s.w_fwd[l].hi,
-                              s.w_fwd[l].lo, s.n_pad[l], s.k_pad[l])))
+                              s.w_fwd[l].lo, s.n_pad[l], s.k_pad[l], s.fmt)))
       return rc;
     if ((rc = split_to_planes(stream, weights[l], s.out_dim[l], s.in_dim[l], s.in_dim[l], 1, 1.f, s.w_bwd[l].hi,
-                              s.w_bwd[l].lo, round_up(s.in_dim[l], 256), round_up(s.out_dim[l], 64))))
+                              s.w_bwd[l].lo, round_up(s.in_dim[l], 256), round_up(s.out_dim[l], 64), s.fmt)))
       return rc;
     NEFII_CUDA(cudaMemcpyAsync(s.bias[l], biases[l], (size_t)s.out_dim[l] * 4, cudaMemcpyDeviceToDevice, stream));
   }
@@ -232,7 +256,7 @@ int SdfNet::set_weights(cudaStream_t stream, const float* const* weights, const 
   NEFII_CUDA(cudaMemcpyAsync(s.b_last, biases[s.n_lin - 1], (size_t)s.cfg.d_out * 4, cudaMemcpyDeviceToDevice, stream));
   if (s.cfg.d_feat > 0) {
     if ((rc = split_to_planes(stream, weights[s.n_lin - 1] + (size_t)s.cfg.d_out * s.cfg.width, s.cfg.d_feat, s.cfg.width, s.cfg.width, 0,
-                              1.f, s.w_feat.hi, s.w_feat.lo, round_up(s.cfg.d_feat, 256), s.cfg.width)))
+                              1.f, s.w_feat.hi, s.w_feat.lo, round_up(s.cfg.d_feat, 256), s.cfg.width, s.fmt)))
       return rc;
     NEFII_CUDA(cudaMemcpyAsync(s.b_feat, biases[s.n_lin - 1] + s.cfg.d_out, (size_t)s.cfg.d_feat * 4, cudaMemcpyDeviceToDevice, stream));
   }
@@ -288,7 +312,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
 
   const int enc_blocks = kNumSMs * 6;
   int rc;
-  encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, 1.f, in0, 0, 64);
+  encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, 1.f, in0, 0, 64, s.fmt);
   NEFII_LAUNCH_CHECK();
 
   // ---------------------------------------------------------------- forward
@@ -300,6 +324,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
   for (int l = 0; l < H; ++l) {
     GemmProblem g{};
     g.k_flush = k_flush;
+    g.epi.fmt = s.fmt;
     const Planes& a = (l == 0) ? in0 : in_of(l);
     g.a_hi = a.hi; g.a_lo = a.lo; g.a_ld = a.ld; g.rows_cap = rows_cap;
     g.b_hi = s.w_fwd[l].hi; g.b_lo = s.w_fwd[l].lo; g.b_ld = s.w_fwd[l].ld; g.n_pad = s.n_pad[l];
@@ -325,6 +350,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
     if (l == H - 1 && feat && s.cfg.d_feat > 0) {
       GemmProblem f{};     // feature = W_last[1:] h + b_last[1:]  (no activation), fp32 out
       f.k_flush = k_flush;
+      f.epi.fmt = s.fmt;
       f.a_hi = feat_in.hi; f.a_lo = feat_in.lo; f.a_ld = feat_in.ld; f.rows_cap = rows_cap;
       f.b_hi = s.w_feat.hi; f.b_lo = s.w_feat.lo; f.b_ld = s.w_feat.ld; f.n_pad = round_up(s.cfg.d_feat, 256);
       f.k_pad = W;
@@ -335,7 +361,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
     }
     if (l + 1 == skip) {
       // the skip layer's input = [h / sqrt2 | PE / sqrt2]: the encoding goes next to the h columns the GEMM just wrote
-      encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, kInvSqrt2, in_of(skip), W - s.d_pe, 0);
+      encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, kInvSqrt2, in_of(skip), W - s.d_pe, 0, s.fmt);
       NEFII_LAUNCH_CHECK();
     }
   }
@@ -348,6 +374,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
   for (int l = H - 1; l >= 1; --l) {
     GemmProblem g{};
     g.k_flush = k_flush;
+    g.epi.fmt = s.fmt;
     g.a_hi = cur.hi; g.a_lo = cur.lo; g.a_ld = cur.ld; g.rows_cap = rows_cap;
     g.b_hi = s.w_bwd[l].hi; g.b_lo = s.w_bwd[l].lo; g.b_ld = s.w_bwd[l].ld; g.n_pad = round_up(s.in_dim[l], 256);
     g.k_pad = round_up(s.out_dim[l], 64);
@@ -374,6 +401,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
   {
     GemmProblem g{};   // layer 0: gradient w.r.t. the encoding, fp32 out
     g.k_flush = k_flush;
+    g.epi.fmt = s.fmt;
     g.a_hi = cur.hi; g.a_lo = cur.lo; g.a_ld = cur.ld; g.rows_cap = rows_cap;
     g.b_hi = s.w_bwd[0].hi; g.b_lo = s.w_bwd[0].lo; g.b_ld = s.w_bwd[0].ld; g.n_pad = round_up(s.in_dim[0], 256);
     g.k_pad = round_up(s.out_dim[0], 64);

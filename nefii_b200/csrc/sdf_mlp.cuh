@@ -21,6 +21,9 @@ class SdfNet {
   SdfNet();
   ~SdfNet();
   int init(const SdfConfig& cfg);
+  // PlaneFormat of the inference chain (mlp_gemm.cuh); drops the packed weights: call set_weights afterwards
+  int set_format(int fmt);
+  int format() const;
   // weights[l]: device fp32 [out_l, in_l] (weight-norm already folded), biases[l]: [out_l]; l = 0..n_hidden
   int set_weights(cudaStream_t stream, const float* const* weights, const float* const* biases);
   size_t workspace_bytes(int rows_cap, bool with_grad) const;

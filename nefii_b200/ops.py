@@ -8,6 +8,8 @@ from . import _lib
 c_void_p, c_int, c_float = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
 
 ACT_NONE, ACT_SOFTPLUS100, ACT_RELU, ACT_ELU = 0, 1, 2, 3
+# plane formats (include/nefii_b200.h): bf16 split (trainable stacks, backward passes), fp16 split (SDF inference chain)
+PLANES_BF16, PLANES_FP16 = 0, 1
 
 
 class GemmDesc(ctypes.Structure):
@@ -26,7 +28,7 @@ class GemmDesc(ctypes.Structure):
         ("seed_hi", c_void_p), ("seed_lo", c_void_p), ("seed_ld", c_int),
         ("sav_hi", c_void_p), ("sav_lo", c_void_p), ("sav_ld", c_int), ("sav_ncols", c_int), ("sav_scale", c_float),
         ("k_splits", c_int), ("f32_split_stride", ctypes.c_int64), ("k_splits_used", c_int),
-        ("k_flush", c_int), ("dst_pad_ok", c_int),
+        ("k_flush", c_int), ("dst_pad_ok", c_int), ("fmt", c_int),
     ]
 
 
@@ -38,8 +40,8 @@ def round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def split_to_planes(src, rows_pad=None, cols_pad=None, transpose=False, scale=1.0):
-    """fp32 [rows, cols] -> (hi, lo) bf16 planes, zero padded to [rows_pad, cols_pad]."""
+def split_to_planes(src, rows_pad=None, cols_pad=None, transpose=False, scale=1.0, fmt=PLANES_BF16):
+    """fp32 [rows, cols] -> (hi, lo) 16-bit planes of format `fmt`, zero padded to [rows_pad, cols_pad]."""
     assert src.is_cuda and src.dtype == torch.float32 and src.dim() == 2
     rows, cols = src.shape
     if cols > 1 and src.stride(1) != 1:
@@ -48,21 +50,23 @@ def split_to_planes(src, rows_pad=None, cols_pad=None, transpose=False, scale=1.
     orow, ocol = (cols, rows) if transpose else (rows, cols)
     rows_pad = rows_pad or orow
     cols_pad = cols_pad or round_up(ocol, 64)
-    hi = torch.empty(rows_pad, cols_pad, device=src.device, dtype=torch.bfloat16)
+    hi = torch.empty(rows_pad, cols_pad, device=src.device, dtype=torch.float16 if fmt == PLANES_FP16 else torch.bfloat16)
     lo = torch.empty_like(hi)
-    _lib.check(_lib.raw().nefii_split_to_planes(
+    _lib.check(_lib.raw().nefii_split_to_planes_fmt(
         _lib.stream_ptr(src.device), _lib.dptr(src) if src.is_contiguous() else c_void_p(src.data_ptr()),
         rows, cols, src.stride(0), 1 if transpose else 0, float(scale),
-        c_void_p(hi.data_ptr()), c_void_p(lo.data_ptr()), rows_pad, cols_pad))
+        c_void_p(hi.data_ptr()), c_void_p(lo.data_ptr()), rows_pad, cols_pad, int(fmt)))
     return hi, lo
 
 
 def gemm_split_bf16(a, b, k_pad, n_valid, *, mode=0, act=ACT_NONE, bias=None, out_scale=1.0, count=None,
                     dst=None, dst_col0=0, dst_ncols=0, dst_zero_to=0, dst_f32=None, f32_begin=0, f32_end=0, f32_ld=None,
                     w_last=None, b_last=None, dst_last=None, seed=None, sav=None, sav_ncols=0, sav_scale=1.0,
-                    k_splits=1, f32_split_stride=0, rows_cap=None, k_flush=0):
-    """a=(hi,lo) activations planes [rows_cap, a_ld], b=(hi,lo) weight planes [n_pad, b_ld]."""
+                    k_splits=1, f32_split_stride=0, rows_cap=None, k_flush=0, fmt=None):
+    """a=(hi,lo) activations planes [rows_cap, a_ld], b=(hi,lo) weight planes [n_pad, b_ld].  fmt: plane format of every
+    plane of the launch (default: from the dtype of a)."""
     d = GemmDesc()
+    d.fmt = (PLANES_FP16 if a[0].dtype == torch.float16 else PLANES_BF16) if fmt is None else fmt
     d.a_hi, d.a_lo, d.a_ld, d.rows_cap = _p(a[0]), _p(a[1]), a[0].stride(0), (a[0].shape[0] if rows_cap is None else rows_cap)
     d.b_hi, d.b_lo, d.b_ld, d.n_pad = _p(b[0]), _p(b[1]), b[0].stride(0), b[0].shape[0]
     d.k_pad = k_pad
@@ -99,8 +103,9 @@ class SdfConfig(ctypes.Structure):
 class SdfMlp:
     """Owner of a ``nefii_sdf_*`` handle: packed weights live in the library, workspaces are torch tensors."""
 
-    def __init__(self, n_freqs=6, width=512, n_hidden=8, skip_layer=4, device=None, d_feat=0):
-        """d_feat = 0: feature vector = input of the last layer (use_last_as_f); > 0: rows 1.. of the last Linear."""
+    def __init__(self, n_freqs=6, width=512, n_hidden=8, skip_layer=4, device=None, d_feat=0, fmt=None):
+        """d_feat = 0: feature vector = input of the last layer (use_last_as_f); > 0: rows 1.. of the last Linear.
+        fmt: plane format of the inference chain (None = library default: fp16 split, NEFII_SDF_FORMAT overrides)."""
         self.device = torch.device(device if device is not None else "cuda")
         self.cfg = SdfConfig(3, n_freqs, width, n_hidden, skip_layer, 1, d_feat)
         self.width, self.n_hidden = width, n_hidden
@@ -111,6 +116,8 @@ class SdfMlp:
         self._h = h
         self._ws = None
         self._keep = None
+        if fmt is not None:
+            self.set_format(fmt)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -120,6 +127,14 @@ class SdfMlp:
     @property
     def handle(self):
         return self._h
+
+    def set_format(self, fmt):
+        """Plane format of the inference chain; the packed weights are dropped (call set_weights again)."""
+        _lib.check(_lib.raw().nefii_sdf_set_format(self._h, int(fmt)))
+
+    @property
+    def format(self):
+        return int(_lib.raw().nefii_sdf_get_format(self._h))
 
     def set_weights(self, weights, biases):
         """weights[l]: effective fp32 [out_l, in_l] CUDA tensors (weight norm folded)."""

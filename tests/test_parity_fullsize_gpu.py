@@ -4,15 +4,16 @@ device with identical weights, rays and random numbers (tests/parity_util.py).
 
 north_star tolerances and what is asserted here (measured values in the comments; `tools/diag_gpu.py fullsize` prints them):
   * hit masks: bit-exact is only defined for an analytic SDF (tests/test_tracer_gpu.py).  With the MLP in the loop the two
-    sides evaluate the SDF with different arithmetic (tcgen05 split-bf16 vs cuBLAS SGEMM, ~2e-6 apart); measured 0 mismatching
-    rays of 32768 and 0 mismatching pixels of 2048 -- asserted as such.
-  * depth abs 1e-4: asserted on >= 99.9 % of the agreeing hits (measured 99.95 %; median 6e-7).  The rest are rays that graze a
-    bump, where the first of two nearby sign changes is a different 1/100-sample bracket on the two sides.
-  * gradients rel 1e-3 (lgtSGs, material MLP, radiance MLP): asserted.
-  * shading rel 1e-4 (abs floor 1e-6): reached on 96 % of the per-pixel lanes, not the 99 % the target asks for: the error
-    is the DEPTH error (1e-6) seen through the 2^9-frequency positional encodings of the radiance / material networks and
-    through secondary hit points -- the 17 significant bits of the bf16 hi/lo operand split against fp32's 24.  Asserted at
-    >= 94 % with p95 <= 1e-4; the fraction is printed.
+    sides evaluate the SDF with different arithmetic (tcgen05 fp16-split products vs cuBLAS SGEMM, ~4e-7 apart; torch's own
+    fp32 result is 1.5e-7 from the f64 value); measured 0 mismatching rays of 32768 and 0 mismatching pixels of 2048 --
+    asserted as such.
+  * depth abs 1e-4: asserted on >= 99.5 % of the agreeing hits (measured 99.8 - 100 %; median 1.2e-7).  The rest are rays that
+    graze a bump, where the first of two nearby sign changes is a different 1/100-sample bracket on the two sides.
+  * gradients rel 1e-3 (lgtSGs, material MLP, radiance MLP): asserted (measured <= 3.5e-4).
+  * shading rel 1e-4 (abs floor 1e-6): reached on 98.4 - 99.2 % of the per-pixel lanes (the figure moves by +-0.4 % with
+    any change of the rounding order, e.g. the accuracy tier: a pixel is the mean of 64 primary x 3 secondary rays, and one
+    grazing secondary ray that brackets differently moves it), p95 1.7e-5, p99 4e-4.  Asserted at >= 97.5 % with p95 <= 5e-5.
+    Round 1 / early round 2 (bf16-split planes, SDF error 1.9e-6): 96 %, p95 4.3e-5.
 """
 import pytest
 import torch
@@ -26,14 +27,15 @@ def test_training_step_at_configs2_size(cuda_device):
     r = fullsize_compare(cuda_device, bumps=0.08, n_px=2048, n_rays=64, training=True, grads=True, verbose=True)
     assert r['pixels'] == 2048 and r['hits'] > 300
     assert r['mask_mismatch'] == 0, r['mask_mismatch']                 # per pixel: all 64 rays of the pixel agree
-    assert r['depth'][0] < 2e-6 and r['depth'][1] < 1e-5, r['depth']   # median / p95 of |d points| on hits (pixel means)
-    assert r['sdf_output_hit'][2] < 1e-5, r['sdf_output_hit']
+    assert r['depth'][0] < 5e-7 and r['depth'][1] < 3e-6, r['depth']   # median / p95 of |d points| on hits (pixel means)
+    assert r['depth_frac_1e4'] >= 0.995, r['depth_frac_1e4']           # north_star: depth abs 1e-4
+    assert r['sdf_output_hit'][2] < 3e-6, r['sdf_output_hit']
     k = r['keys']
-    assert k['sg_rgb_values']['frac_1e4'] >= 0.94, k['sg_rgb_values']         # measured 0.963
-    assert k['sg_rgb_values']['q'][1] <= 1e-4, k['sg_rgb_values']      # p95 within the north_star tolerance
-    assert k['sg_diffuse_rgb_values']['frac_1e4'] >= 0.94                     # measured 0.968
+    assert k['sg_rgb_values']['frac_1e4'] >= 0.975, k['sg_rgb_values']        # measured 0.984 - 0.992
+    assert k['sg_rgb_values']['q'][1] <= 5e-5, k['sg_rgb_values']      # p95 well within the north_star tolerance
+    assert k['sg_diffuse_rgb_values']['frac_1e4'] >= 0.975                    # measured 0.985
     assert k['sg_roughness_values']['frac_1e4'] >= 0.999 and k['sg_diffuse_albedo_values']['frac_1e4'] >= 0.999
-    assert k['normal_values']['absq'][2] < 2e-4, k['normal_values']    # unit vectors: absolute, p99
+    assert k['normal_values']['absq'][2] < 5e-5, k['normal_values']    # unit vectors: absolute, p99 (measured 1.4e-5)
     assert r['background_rel'][3] < 1e-5                               # environment lookup on miss rays: max rel
     assert r['secondary_mismatch'] is not None and r['secondary_mismatch'] <= 1e-4 * r['secondary_rays'], r['secondary_mismatch']
     # north_star: gradients within rel 1e-3
@@ -47,15 +49,15 @@ def test_per_ray_lanes_at_32768_rays(cuda_device):
     r = fullsize_compare(cuda_device, bumps=0.08, n_px=32768, n_rays=0, training=True, grads=False, verbose=True)
     assert r['hits'] > 5000
     assert r['mask_mismatch'] == 0, r['mask_mismatch']
-    assert r['depth_frac_1e4'] >= 0.995, r['depth_frac_1e4']
-    assert r['depth'][0] < 2e-6 and r['depth'][2] < 5e-5, r['depth']
-    assert r['keys']['sg_rgb_values']['frac_1e4'] >= 0.88, r['keys']['sg_rgb_values']
-    assert r['keys']['sg_rgb_values']['q'][0] < 3e-5
+    assert r['depth_frac_1e4'] >= 0.999, r['depth_frac_1e4']            # measured 0.99988
+    assert r['depth'][0] < 5e-7 and r['depth'][2] < 1e-5, r['depth']
+    assert r['keys']['sg_rgb_values']['frac_1e4'] >= 0.95, r['keys']['sg_rgb_values']      # measured 0.964 (single rays)
+    assert r['keys']['sg_rgb_values']['q'][0] < 1e-5
 
 
 def test_eval_render_at_8192_rays(cuda_device):
     r = fullsize_compare(cuda_device, bumps=0.08, n_px=8192, n_rays=0, training=False, grads=False, verbose=True)
     assert r['mask_mismatch'] == 0
     assert r['depth_frac_1e4'] >= 0.999
-    assert r['keys']['sg_rgb_values']['frac_1e4'] >= 0.93, r['keys']['sg_rgb_values']
-    assert r['keys']['sg_rgb_values']['q'][1] < 2e-4
+    assert r['keys']['sg_rgb_values']['frac_1e4'] >= 0.985, r['keys']['sg_rgb_values']     # measured 0.993
+    assert r['keys']['sg_rgb_values']['q'][1] < 5e-5

@@ -1,7 +1,9 @@
 """GPU: the tcgen05 SDF/feature MLP (forward + closed-form input gradient) against the oracle.
 
-The CUDA path computes each fp32 product as three bf16 MMAs (hi*hi + hi*lo + lo*hi); the bound
-asserted here (abs 5e-5 on the SDF, rel 2e-4 on the normal direction) is what DESIGN.md reports."""
+The CUDA path computes each fp32 product as three 16-bit MMAs (hi*hi + hi*lo + lo*hi) on one of two plane formats
+(include/nefii_b200.h): the fp16 split (the default of the SDF network: 22 significant bits, SDF within 5e-6 of the f64
+value, 4e-7 on average -- torch's own fp32 evaluation is 1.5e-7 on average) and the bf16 split (16 bits, fp32's range;
+1e-5 / 2e-6).  The bounds asserted here are what DESIGN.md reports."""
 import pytest
 import torch
 
@@ -10,32 +12,48 @@ from oracle import mlp
 pytestmark = pytest.mark.gpu
 
 
-def _net(dev, params):
+def _net(dev, params, fmt=None):
     from nefii_b200 import ops
     net = ops.SdfMlp(n_freqs=params.n_freqs, width=params.W[1].shape[0], n_hidden=params.n_layers - 1,
-                     skip_layer=params.skip_layer, device=dev)
+                     skip_layer=params.skip_layer, device=dev, fmt=fmt)
     net.set_weights([w.to(dev) for w in params.W], [b.to(dev) for b in params.b])
     return net
 
 
+# (format, max |sdf err|, mean |sdf err|, p99 of the normal's direction error)
+FORMATS = {"fp16": (1, 6e-6, 8e-7, 4e-5), "bf16": (0, 5e-5, 4e-6, 1.5e-4)}
+
+
+def test_default_format_is_the_fp16_split(cuda_device):
+    from nefii_b200 import ops
+    net = _net(cuda_device, mlp.sdf_init(seed=1, bumps=0.3))
+    assert net.format == ops.PLANES_FP16
+
+
+@pytest.mark.parametrize("fmt", ["fp16", "bf16"])
 @pytest.mark.parametrize("n", [1, 127, 4096, 20001])
-def test_forward_features_gradient(cuda_device, n):
+def test_forward_features_gradient(cuda_device, n, fmt):
     dev = cuda_device
+    fmt_id, tol_max, tol_mean, tol_dir = FORMATS[fmt]
     params = mlp.sdf_init(seed=1, bumps=0.3)
-    net = _net(dev, params)
+    net = _net(dev, params, fmt_id)
+    assert net.format == fmt_id
     g = torch.Generator().manual_seed(n)
     x = (torch.rand(n, 3, generator=g) * 1.8 - 0.9).to(dev)
     sdf, feat, grad = net.eval(x, want_feat=True, want_grad=True)
     p64 = params.to(dev, torch.float64)
     ref = mlp.sdf_forward(p64, x.double())
     gref = mlp.sdf_gradient(p64, x.double())
-    assert (sdf.double() - ref[:, 0]).abs().max().item() < 5e-5
-    assert (feat.double() - ref[:, 1:]).abs().max().item() < 5e-5
+    err = (sdf.double() - ref[:, 0]).abs()
+    assert err.max().item() < tol_max, err.max().item()
+    if n >= 4096:
+        assert err.mean().item() < tol_mean, err.mean().item()
+    assert (feat.double() - ref[:, 1:]).abs().max().item() < tol_max
     # direction error of the normal; points where |grad| is tiny (critical points of the random field)
     # are ill-conditioned for the fp32 reference as well, hence the floor on the denominator
     rel = (grad.double() - gref).norm(dim=-1) / gref.norm(dim=-1).clamp_min(0.5)
     assert rel.max().item() < 1e-3, rel.max().item()
-    assert rel.kthvalue(max(1, int(0.99 * n)))[0].item() < 1.5e-4
+    assert rel.kthvalue(max(1, int(0.99 * n)))[0].item() < tol_dir
     # forward-only path (ping-pong workspace) returns the same SDF bit for bit
     sdf2, _, _ = net.eval(x)
     assert torch.equal(sdf, sdf2)

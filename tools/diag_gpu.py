@@ -89,7 +89,9 @@ def diag_sdf():
     from oracle import mlp
     dev = torch.device("cuda:0")
     params = mlp.sdf_init(seed=1, bumps=0.3)
-    net = ops.SdfMlp(device=dev)
+    fmt = int(os.environ.get("DIAG_FMT", "-1"))
+    net = ops.SdfMlp(device=dev, fmt=None if fmt < 0 else fmt)
+    print("SDF plane format %d" % net.format)
     net.set_weights([w.to(dev) for w in params.W], [b.to(dev) for b in params.b])
     p32 = params.to(dev)
     p64 = params.to(dev, torch.float64)
@@ -430,6 +432,8 @@ def diag_trunccomp():
     from oracle import mlp
     dev = torch.device("cuda:0")
     lib = _lib.raw()
+    fmt = int(os.environ.get("DIAG_FMT", "0"))      # 0 bf16 split, 1 fp16 split
+    print("TRUNCCOMP plane format %d" % fmt)
     rows, k, n = 16384, 512, 512
     g = torch.Generator(device="cpu").manual_seed(0)
     slopes = {}
@@ -439,11 +443,11 @@ def diag_trunccomp():
             x = x.abs()
         w = torch.randn(n, k, generator=g) / k ** 0.5
         x, w = x.to(dev), w.to(dev)
-        a = ops.split_to_planes(x); b = ops.split_to_planes(w)
+        a = ops.split_to_planes(x, fmt=fmt); b = ops.split_to_planes(w, fmt=fmt)
         ah, al, bh, bl = [t.double() for t in (a[0], a[1], b[0], b[1])]
         ref3 = ah @ bh.t() + ah @ bl.t() + al @ bh.t()        # what the three MMAs sum, exactly
         for L in (1, 2, 4, 8):
-            _lib.check(lib.nefii_gemm_set_trunc_comp(L, 0.0))
+            _lib.check(lib.nefii_gemm_set_trunc_comp_fmt(fmt, L, 0.0))
             out = torch.zeros(rows, n, device=dev)
             ops.gemm_split_bf16(a, b, k, n, dst_f32=out, f32_begin=0, f32_end=n, k_flush=L)
             err = out.double() - ref3
@@ -453,7 +457,7 @@ def diag_trunccomp():
             print("TRUNCCOMP %-8s L=%d: slope %.3e (%.2f ulp of 2^-24) | err rms %.3e -> after removing the slope %.3e | mean|ref| %.3f" % (
                 data, L, slope, slope / 2 ** -24, err.pow(2).mean().sqrt().item(), resid.pow(2).mean().sqrt().item(), ref3.abs().mean().item()))
     params = mlp.sdf_init(seed=1, bumps=0.3)
-    net = ops.SdfMlp(device=dev)
+    net = ops.SdfMlp(device=dev, fmt=fmt)
     net.set_weights([t.to(dev) for t in params.W], [t.to(dev) for t in params.b])
     pts = torch.rand(131072, 3, device=dev) * 1.8 - 0.9
     p64 = params.to(dev, torch.float64)
@@ -472,10 +476,10 @@ def diag_trunccomp():
     report("comp off")
     for src in ("positive", "gauss"):
         for L in (1, 2, 4, 8):
-            _lib.check(lib.nefii_gemm_set_trunc_comp(L, -slopes[(src, L)]))
+            _lib.check(lib.nefii_gemm_set_trunc_comp_fmt(fmt, L, -slopes[(src, L)]))
         report("comp from %-8s" % src)
     for L in (1, 2, 4, 8):
-        _lib.check(lib.nefii_gemm_set_trunc_comp(L, 0.0))
+        _lib.check(lib.nefii_gemm_set_trunc_comp_fmt(fmt, L, 0.0))
     r32 = mlp.sdf_forward(params.to(dev), pts)[:, 0]
     e = r32.double() - r64
     print("   torch fp32 for scale: err mean|.| %.2e signed %.2e max %.2e" % (e.abs().mean().item(), e.mean().item(), e.abs().max().item()))
@@ -497,6 +501,39 @@ def diag_l2fit():
         waves = rows / 128 / 148
         print("L2FIT rows %8d (%.1f MB in + out): %.4f ms  %.1f TFLOP/s alg  %.2f us per wave of 148 tiles" % (
             rows, rows * 4096 / 1e6, ms, 2.0 * rows * n * k / ms / 1e9, ms * 1e3 / waves))
+
+
+
+
+def diag_sdfbias():
+    """Where does the signed SDF error come from?  Feature vector (= last hidden activation) against f64, signed, per tier."""
+    from nefii_b200 import ops
+    from oracle import mlp
+    dev = torch.device("cuda:0")
+    fmt = int(os.environ.get("DIAG_FMT", "-1"))
+    params = mlp.sdf_init(seed=1, bumps=0.3)
+    net = ops.SdfMlp(device=dev, fmt=None if fmt < 0 else fmt)
+    net.set_weights([t.to(dev) for t in params.W], [t.to(dev) for t in params.b])
+    pts = torch.rand(16384, 3, device=dev) * 1.8 - 0.9
+    p64 = params.to(dev, torch.float64)
+    out64 = mlp.sdf_forward(p64, pts.double())
+    r64, f64 = out64[:, 0], out64[:, 1:]
+    w_last = p64.W[-1][0]
+    for L in (1, 4, 8):
+        sdf, feat, _ = net.eval(pts, want_feat=True, k_flush=L)
+        e = sdf.double() - r64
+        fe = feat.double() - f64
+        big = f64 > 1e-3
+        relf = (fe / f64)[big]
+        # what the feature error alone explains of the SDF error (the output layer is fp32 FMAs)
+        via_feat = fe @ w_last
+        print("SDFBIAS fmt %d k_flush=%d: sdf err signed %.2e rms %.2e | feat rel err signed %.2e rms %.2e | sdf err explained by feat: signed %.2e, rest signed %.2e rms %.2e" % (
+            net.format, L, e.mean().item(), e.pow(2).mean().sqrt().item(), relf.mean().item(), relf.pow(2).mean().sqrt().item(),
+            via_feat.mean().item(), (e - via_feat).mean().item(), (e - via_feat).pow(2).mean().sqrt().item()))
+    r32 = mlp.sdf_forward(params.to(dev), pts)
+    fe = (r32[:, 1:].double() - f64)
+    print("SDFBIAS torch fp32: sdf err signed %.2e | feat rel signed %.2e rms %.2e" % (
+        (r32[:, 0].double() - r64).mean().item(), (fe / f64)[f64 > 1e-3].mean().item(), (fe / f64)[f64 > 1e-3].pow(2).mean().sqrt().item()))
 
 
 if __name__ == "__main__":
