@@ -205,10 +205,13 @@ int nefii_trace_set_tiers(int march_flush, int bulk_flush);
 /* 0: fixed launch schedule (every loop unrolled to its worst case, empty rounds exit at once); 1: CUDA graph with
  * conditional WHILE nodes (default; NEFII_TRACE_GRAPH=0 selects the fixed schedule at load) */
 int nefii_trace_set_graph_mode(int mode);
-/* bisection rounds apply TWO iterations of the reference's loop (both possible second mid-points are evaluated with the first
- * one: 3 n rows instead of n, bit-identical results, half the latency-bound rounds) while 3 * n_root <= rows; 0 switches it
- * off (default 12288; NEFII_TRACE_QUAD_ROWS at load) */
+/* bisection rounds apply D iterations of the reference's loop at once while few rays are refined: the whole binary tree of
+ * mid-points that D iterations can visit is evaluated in one round ((2^D - 1) n rows instead of n, bit-identical results,
+ * 1 / D of the latency-bound rounds); D = the largest depth <= max depth with (2^D - 1) * n_root <= rows, decided on the
+ * device.  rows = 0 switches it off (default 12288; NEFII_TRACE_QUAD_ROWS at load); max depth 1..4 (default 4;
+ * NEFII_TRACE_BISECT_DEPTH at load). */
 int nefii_trace_set_quad_rows(int rows);
+int nefii_trace_set_bisect_depth(int depth);
 /* drops the cached trace graphs (they hold raw pointers into workspaces and SDF handles) */
 int nefii_trace_graph_clear(void);
 /* the analytic test SDF alone: x [n,3] -> sdf [n] */

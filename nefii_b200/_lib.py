@@ -49,6 +49,7 @@ SIGNATURES = {
     "nefii_trace_set_tiers": [c_int, c_int],
     "nefii_trace_set_graph_mode": [c_int],
     "nefii_trace_set_quad_rows": [c_int],
+    "nefii_trace_set_bisect_depth": [c_int],
     "nefii_trace_graph_clear": [],
     "nefii_analytic_sdf_eval": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "nefii_sdf_create": [c_void_p, c_void_p],

@@ -45,7 +45,9 @@ struct Ctrl {
   int any_work;      // bisection: OR of the surviving work bits
   int bis_step;      // bisection iterations applied
   int bis_alive;     // the bisection loop is still running
-  int bis_quad;      // two bisection iterations per round (few rays: the rounds are latency-bound)
+  int bis_depth;     // bisection iterations applied per round (1..kMaxBisDepth; > 1 while few rays are refined)
+  int bis_rewalk;    // -1, or the number of iterations of the LAST round that the reference executes (< bis_depth)
+  int spec_work[4];  // OR of the surviving work bits after each of a round's iterations
   long long evals;   // SDF point evaluations (stats)
 };
 
@@ -62,6 +64,7 @@ struct RayState {
   // sampler / root-find / min-sdf lists
   int *samp_list, *min_list, *root_list;
   float *z_lo, *z_hi, *s_lo, *s_hi;
+  float *z_lo_prev, *z_hi_prev;   // bracket before the round in flight (speculative bisection)
   unsigned char* work;
   // outputs
   float* points; unsigned char* hit; float* dists;
@@ -325,88 +328,130 @@ sample_reduce_kernel(RayState S, int chunk_rays, int n_steps, const float* __res
 // Bisection (RayTracing.rootfind, ray_tracing.py:259-280).  The reference bisects *every* passed ray while ANY ray still has
 // work, so the loop is batch-coupled: Ctrl::bis_alive says whether the next iteration runs.
 //   phase INIT  : work = (s_lo > 0) & (s_hi < 0) & (z_hi > z_lo) (:261); emits the first mid-points when any ray has work
-//   phase STEP  : applies one iteration (:265-277), emits the next mid-points while any ray has work left and steps remain
+//   phase STEP  : applies the iterations of one round (:265-277), emits the next mid-points
 //   finish      : z_pred = (z_lo + z_hi) / 2 -> dists / points
-// Two iterations per round ("quad" mode) when few rays are being refined: a round is latency-bound then (8 dependent layer
-// GEMMs on a handful of row tiles), so both possible second mid-points are evaluated together with the first one (3 n rows
-// instead of n) and a round applies TWO iterations of the reference -- bit-identical values, half the rounds:
-//   rows [0, n): m1 = (lo + hi) / 2;  [n, 2n): (lo + m1) / 2 (taken if sdf(m1) <= 0);  [2n, 3n): (m1 + hi) / 2 (if sdf(m1) > 0)
-//   phase STEP  applies the first iteration (and stops everybody if no ray has work left, as the reference would);
-//   phase STEP2 applies the second one from the candidate that matches, then emits the next three points.
-enum { BIS_INIT = 0, BIS_STEP = 1, BIS_STEP2 = 2 };
+// Several iterations per round ("speculative" mode) when few rays are being refined: a round is latency-bound then (8
+// dependent layer GEMMs on a handful of row tiles), so a round evaluates the whole binary tree of mid-points that D
+// iterations can visit -- 2^D - 1 candidates per ray, node j of the tree (heap order, root 1, left child = the half that
+// is kept when sdf(mid) <= 0) in request rows [(j - 1) n, j n) -- and applies D iterations of the reference at once: the
+// same float operations on the same values, 1 / D of the rounds.  D is decided on the device at INIT from the number of
+// rays being refined (largest D <= max_depth with (2^D - 1) n <= spec_rows).
+// The batch-coupled stop inside a round: a round keeps the bracket it started from (z_*_prev) and records, per iteration,
+// whether any ray still had work (Ctrl::spec_work); if the reference's loop ends after e < D iterations of the LAST round,
+// the finish kernel re-walks e iterations from the saved bracket.  While the loop goes on, all D iterations were valid.
+enum { BIS_INIT = 0, BIS_STEP = 1 };
+constexpr int kMaxBisDepth = 4;
 
-__device__ __forceinline__ void bisect_emit(const RayState& S, int k, int n_root, int quad, float zl, float zh) {
+__device__ __forceinline__ void bisect_emit(const RayState& S, int k, int n_root, int depth, float zl, float zh) {
   const int r = S.root_list[k];
   float o[3], d[3];
   ray_od(S, r, o, d);
-  const float m1 = (zl + zh) * 0.5f;
-  emit_point(S, k, o, m1, d);                     // only evaluated if the loop goes on
-  if (quad) {
-    emit_point(S, n_root + k, o, (zl + m1) * 0.5f, d);
-    emit_point(S, 2 * n_root + k, o, (m1 + zh) * 0.5f, d);
+  float lo[1 << kMaxBisDepth], hi[1 << kMaxBisDepth];
+  lo[1] = zl; hi[1] = zh;
+#pragma unroll
+  for (int j = 1; j < (1 << kMaxBisDepth); ++j) {
+    if (j < (1 << depth)) {
+      const float m = (lo[j] + hi[j]) * 0.5f;
+      emit_point(S, (j - 1) * n_root + k, o, m, d);          // only evaluated if the loop goes on
+      if (2 * j + 1 < (1 << kMaxBisDepth)) {
+        lo[2 * j] = lo[j]; hi[2 * j] = m;                    // sdf(m) <= 0: the root lies in [lo, m]
+        lo[2 * j + 1] = m; hi[2 * j + 1] = hi[j];            // sdf(m) >  0: in [m, hi]
+      }
+    }
+  }
+}
+
+// `n_iter` iterations of the reference from bracket (zl, zh) with the SDF values of the round's candidate tree
+__device__ __forceinline__ void bisect_walk(const RayState& S, int k, int n_root, int n_iter, float& zl, float& zh, float& sl, float& sh,
+                                            unsigned char& w, Ctrl* C) {
+  int node = 1;
+  for (int i = 0; i < n_iter; ++i) {
+    const float zm = (zl + zh) * 0.5f;
+    const float sm = S.req_sdf[(size_t)(node - 1) * n_root + k];
+    if (sm > 0.f) { zl = zm; sl = sm; node = 2 * node + 1; }
+    if (sm <= 0.f) { zh = zm; sh = sm; node = 2 * node; }
+    w = (w && ((zh - zl) > 1e-6f)) ? 1 : 0;
+    if (C != nullptr && w) C->spec_work[i] = 1;
   }
 }
 
 __global__ void __launch_bounds__(kBlock)
-bisect_kernel(RayState S, int phase, int n_rootfind_steps, int quad_rows, unsigned long long cond) {
+bisect_kernel(RayState S, int phase, int n_rootfind_steps, int spec_rows, int max_depth, unsigned long long cond) {
   Ctrl* C = S.ctrl;
   if (phase != BIS_INIT && !C->bis_alive) return;          // uniform over the grid: the flag only changes in the last CTA
   const int n_root = C->n_root;
-  const int quad = (phase == BIS_INIT) ? ((n_root > 0 && 3 * (long long)n_root <= quad_rows) ? 1 : 0) : C->bis_quad;
-  if (phase == BIS_STEP2 && !quad) return;
+  int depth;
+  if (phase == BIS_INIT) {
+    depth = 1;
+    for (int d = 2; d <= max_depth && d <= kMaxBisDepth; ++d)
+      if (n_root > 0 && (long long)((1 << d) - 1) * n_root <= spec_rows) depth = d;
+  } else {
+    depth = C->bis_depth;
+  }
   const int k = blockIdx.x * kBlock + threadIdx.x;
   if (k < n_root) {
     float zl = S.z_lo[k], zh = S.z_hi[k];
     unsigned char w;
     if (phase == BIS_INIT) {
       w = (S.s_lo[k] > 0.f && S.s_hi[k] < 0.f && zh > zl) ? 1 : 0;
+      if (w) C->any_work = 1;
     } else {
-      const float zm = (zl + zh) * 0.5f;
-      float sm;
-      if (phase == BIS_STEP) {
-        sm = S.req_sdf[k];
-        if (quad) S.ls[k] = sm > 0.f ? 1 : 0;        // which candidate of this round the second iteration uses (ls[] is free after the march)
-      } else {
-        sm = S.ls[k] ? S.req_sdf[2 * n_root + k] : S.req_sdf[n_root + k];
-      }
-      if (sm > 0.f) { zl = zm; S.z_lo[k] = zl; S.s_lo[k] = sm; }
-      if (sm <= 0.f) { zh = zm; S.z_hi[k] = zh; S.s_hi[k] = sm; }
-      w = (S.work[k] && ((zh - zl) > 1e-6f)) ? 1 : 0;
+      S.z_lo_prev[k] = zl; S.z_hi_prev[k] = zh;
+      float sl = S.s_lo[k], sh = S.s_hi[k];
+      w = S.work[k];
+      bisect_walk(S, k, n_root, depth, zl, zh, sl, sh, w, C);
+      S.z_lo[k] = zl; S.z_hi[k] = zh; S.s_lo[k] = sl; S.s_hi[k] = sh;
     }
     S.work[k] = w;
-    if (w) C->any_work = 1;
-    // the next request: after INIT, after a plain STEP, after STEP2 (a quad round's STEP emits nothing: its second iteration
-    // already has its value)
-    if (!(phase == BIS_STEP && quad)) bisect_emit(S, k, n_root, quad, zl, zh);
+    bisect_emit(S, k, n_root, depth, zl, zh);
   }
   if (last_block(&C->ticket) && threadIdx.x == 0) {
-    const int step = (phase == BIS_INIT) ? 0 : C->bis_step + 1;
-    const bool alive = (*(volatile int*)&C->any_work != 0) && step < n_rootfind_steps && n_root > 0;
-    C->bis_step = step;
-    C->any_work = 0;
-    C->bis_alive = alive ? 1 : 0;
-    if (phase == BIS_INIT) C->bis_quad = quad;
-    if (phase == BIS_STEP && quad) {
-      // first half of a quad round: the loop condition is set here too (STEP2 returns at once when the batch has stopped)
-      if (!alive) C->cnt_eval = 0;
-      set_cond(cond, alive);
+    bool alive;
+    if (phase == BIS_INIT) {
+      alive = (*(volatile int*)&C->any_work != 0) && 0 < n_rootfind_steps && n_root > 0;
+      C->bis_step = 0;
+      C->any_work = 0;
+      C->bis_depth = depth;
+      C->bis_rewalk = -1;
     } else {
-      const int rows = quad ? 3 * n_root : n_root;
-      C->cnt_eval = alive ? rows : 0;
-      if (alive) C->evals += rows;
-      set_cond(cond, alive);
+      // how many of this round's iterations the reference's `while work.any() and i < n_steps` executes
+      const int step0 = C->bis_step;
+      int e = 0;
+      alive = true;
+      for (int i = 0; i < depth && alive; ++i) {
+        e = i + 1;
+        alive = (*(volatile int*)&C->spec_work[i] != 0) && (step0 + e < n_rootfind_steps);
+      }
+      C->bis_step = step0 + e;
+      C->bis_rewalk = (e < depth) ? e : -1;
     }
+    for (int i = 0; i < kMaxBisDepth; ++i) C->spec_work[i] = 0;
+    C->bis_alive = alive ? 1 : 0;
+    const int rows = ((1 << depth) - 1) * n_root;
+    C->cnt_eval = alive ? rows : 0;
+    if (alive) C->evals += rows;
+    set_cond(cond, alive);
   }
 }
 
 __global__ void __launch_bounds__(kBlock) bisect_finish_kernel(RayState S, unsigned long long cond_next) {
   Ctrl* C = S.ctrl;
   const int k = blockIdx.x * kBlock + threadIdx.x;
-  if (k < C->n_root) {
+  const int n_root = C->n_root;
+  if (k < n_root) {
     const int r = S.root_list[k];
     float o[3], d[3];
     ray_od(S, r, o, d);
-    const float zm = (S.z_lo[k] + S.z_hi[k]) * 0.5f;
+    float zl = S.z_lo[k], zh = S.z_hi[k];
+    const int e = C->bis_rewalk;
+    if (e >= 0) {
+      // the loop ended inside the last round: only its first e iterations count
+      zl = S.z_lo_prev[k]; zh = S.z_hi_prev[k];
+      float sl = 0.f, sh = 0.f;
+      unsigned char w = 1;
+      bisect_walk(S, k, n_root, e, zl, zh, sl, sh, w, nullptr);
+    }
+    const float zm = (zl + zh) * 0.5f;
     S.dists[r] = zm;
     S.points[(size_t)r * 3 + 0] = o[0] + zm * d[0];
     S.points[(size_t)r * 3 + 1] = o[1] + zm * d[1];
@@ -471,7 +516,7 @@ analytic_sdf_kernel(const float* __restrict__ prims, int n_prims, int n, const i
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
-  size_t off_f[8], off_slot[2], off_bytes[4], off_req_pts, off_req_sdf, off_ctrl, off_lists[3], off_z[4], off_mlp, total;
+  size_t off_f[8], off_slot[2], off_bytes[4], off_req_pts, off_req_sdf, off_ctrl, off_lists[3], off_z[6], off_mlp, total;
   int cap_pts;
 };
 
@@ -490,7 +535,7 @@ Layout make_layout(const SdfSource& src, int n_rays, int n_steps) {
   L.off_req_pts = take((size_t)cap * 12);
   L.off_req_sdf = take((size_t)cap * 4);
   for (int i = 0; i < 3; ++i) L.off_lists[i] = take(R * 4);
-  for (int i = 0; i < 4; ++i) L.off_z[i] = take(R * 4);
+  for (int i = 0; i < 6; ++i) L.off_z[i] = take(R * 4);
   L.off_mlp = p;
   if (src.net) p += align_up(src.net->workspace_bytes((int)cap, false), 256);
   L.total = p + 1024;
@@ -506,14 +551,20 @@ TraceTiers env_tiers() {
   return t;
 }
 TraceTiers g_tiers = env_tiers();
-// bisection: two iterations per round while 3 * (rays being refined) <= this many rows; 0 switches the mode off
-// (NEFII_TRACE_QUAD_ROWS at load)
+// bisection: D iterations per round while (2^D - 1) * (rays being refined) <= this many rows; 0 switches the mode off
+// (NEFII_TRACE_QUAD_ROWS at load); D <= NEFII_TRACE_BISECT_DEPTH (1..4, default 4)
 int env_quad_rows() {
   const char* e = getenv("NEFII_TRACE_QUAD_ROWS");
   const int v = e ? atoi(e) : 12288;
   return v < 0 ? 0 : v;
 }
 int g_bisect_quad_rows = env_quad_rows();
+int env_bisect_depth() {
+  const char* e = getenv("NEFII_TRACE_BISECT_DEPTH");
+  const int v = e ? atoi(e) : kMaxBisDepth;
+  return v < 1 ? 1 : (v > kMaxBisDepth ? kMaxBisDepth : v);
+}
+int g_bisect_max_depth = env_bisect_depth();
 
 }  // namespace
 
@@ -530,6 +581,12 @@ int trace_set_quad_rows(int rows) {
   return NEFII_OK;
 }
 int trace_quad_rows() { return g_bisect_quad_rows; }
+int trace_set_bisect_depth(int depth) {
+  NEFII_CHECK_ARG(depth >= 1 && depth <= kMaxBisDepth, "trace_set_bisect_depth: 1..%d", kMaxBisDepth);
+  g_bisect_max_depth = depth;
+  return NEFII_OK;
+}
+int trace_bisect_depth() { return g_bisect_max_depth; }
 
 size_t trace_workspace_bytes(const SdfSource& src, int n_rays, int n_steps) { return make_layout(src, n_rays, n_steps).total; }
 
@@ -579,6 +636,7 @@ int ray_trace_enqueue(cudaStream_t stream, const TraceConfig& cfg, const SdfSour
   S.ctrl = (Ctrl*)(base + L.off_ctrl);
   S.samp_list = (int*)(base + L.off_lists[0]); S.min_list = (int*)(base + L.off_lists[1]); S.root_list = (int*)(base + L.off_lists[2]);
   S.z_lo = (float*)(base + L.off_z[0]); S.z_hi = (float*)(base + L.off_z[1]); S.s_lo = (float*)(base + L.off_z[2]); S.s_hi = (float*)(base + L.off_z[3]);
+  S.z_lo_prev = (float*)(base + L.off_z[4]); S.z_hi_prev = (float*)(base + L.off_z[5]);
   S.points = points; S.hit = hit; S.dists = dists;
   void* mlp_ws = base + L.off_mlp;
   const size_t mlp_ws_bytes = src.net ? src.net->workspace_bytes(L.cap_pts, false) : 0;
@@ -650,16 +708,16 @@ int ray_trace_enqueue(cudaStream_t stream, const TraceConfig& cfg, const SdfSour
 
   // ---- bisection between the bracketing samples ----------------------------------------------------------------------
   unsigned long long h_bis = next_cond();
-  // two iterations per round while 3 n_root rows still fit a latency-bound evaluation (decided on the device from n_root)
-  const int quad_rows = std::min(g_bisect_quad_rows, L.cap_pts);
-  bisect_kernel<<<grid, kBlock, 0, stream>>>(S, BIS_INIT, cfg.n_rootfind_steps, quad_rows, h_bis);
+  // up to g_bisect_max_depth iterations per round while the candidate tree still fits a latency-bound evaluation (decided on
+  // the device from n_root)
+  const int spec_rows = std::min(g_bisect_quad_rows, L.cap_pts);
+  const int max_depth = spec_rows > 0 ? g_bisect_max_depth : 1;
+  bisect_kernel<<<grid, kBlock, 0, stream>>>(S, BIS_INIT, cfg.n_rootfind_steps, spec_rows, max_depth, h_bis);
   NEFII_LAUNCH_CHECK();
   if ((rc = loop(cfg.n_rootfind_steps, [&](cudaStream_t st, unsigned long long h) -> int {
         int rc2;
-        if ((rc2 = eval(st, std::min(std::max(R, quad_rows), L.cap_pts), tiers.march_flush))) return rc2;
-        bisect_kernel<<<grid, kBlock, 0, st>>>(S, BIS_STEP, cfg.n_rootfind_steps, quad_rows, h);
-        NEFII_LAUNCH_CHECK();
-        bisect_kernel<<<grid, kBlock, 0, st>>>(S, BIS_STEP2, cfg.n_rootfind_steps, quad_rows, h);
+        if ((rc2 = eval(st, std::min(std::max(R, spec_rows), L.cap_pts), tiers.march_flush))) return rc2;
+        bisect_kernel<<<grid, kBlock, 0, st>>>(S, BIS_STEP, cfg.n_rootfind_steps, spec_rows, max_depth, h);
         NEFII_LAUNCH_CHECK();
         return NEFII_OK;
       })))

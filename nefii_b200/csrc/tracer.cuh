@@ -43,6 +43,8 @@ TraceTiers trace_tiers();
 // bisection: two iterations per round (3 n rows per evaluation) while 3 * n_root <= rows; 0 = always one iteration per round
 int trace_set_quad_rows(int rows);
 int trace_quad_rows();
+int trace_set_bisect_depth(int depth);
+int trace_bisect_depth();
 
 size_t trace_workspace_bytes(const SdfSource& src, int n_rays, int n_steps);
 int trace_max_rounds(const TraceConfig& cfg);

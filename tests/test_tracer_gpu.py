@@ -53,16 +53,27 @@ def test_analytic_scene_bit_exact(cuda_device, training, n_side, f):
     assert torch.equal(dist, o_dist), (dist - o_dist).abs().max().item()
     live = st["sphere_hits"]
     assert torch.equal(pts[live], o_pts[live])
-    # with one bisection iteration per round the compacted trace evaluates exactly the reference's points; the default
-    # (two iterations per round while few rays are refined) evaluates 3 candidates per 2 iterations -- same results
+    # with one bisection iteration per round the compacted trace evaluates exactly the reference's points; the default (up to
+    # four iterations per round while few rays are refined) evaluates the 2^D - 1 candidates of D iterations -- same results
     from nefii_b200 import _lib
-    _lib.check(_lib.raw().nefii_trace_set_quad_rows(0))
+    lib = _lib.raw()
+    _lib.check(lib.nefii_trace_set_quad_rows(0))
     try:
         p1, m1, d1 = rt(sdf_dev, loc, obj, dirs, uniforms=u if training else None)
         assert rt.last_stats["n_evals"] <= st["n_evals"]
         assert torch.equal(m1, mask) and torch.equal(d1, dist) and torch.equal(p1[live], pts[live])
     finally:
-        _lib.check(_lib.raw().nefii_trace_set_quad_rows(12288))
+        _lib.check(lib.nefii_trace_set_quad_rows(12288))
+    # every depth, with a row budget that makes the device pick it, and one (1 << 30) that always takes the deepest tree
+    for depth, rows in ((2, 12288), (3, 12288), (4, 1 << 30), (3, 1 << 30)):
+        _lib.check(lib.nefii_trace_set_bisect_depth(depth))
+        _lib.check(lib.nefii_trace_set_quad_rows(rows))
+        try:
+            p1, m1, d1 = rt(sdf_dev, loc, obj, dirs, uniforms=u if training else None)
+            assert torch.equal(m1, mask) and torch.equal(d1, dist) and torch.equal(p1[live], pts[live]), (depth, rows)
+        finally:
+            _lib.check(lib.nefii_trace_set_bisect_depth(4))
+            _lib.check(lib.nefii_trace_set_quad_rows(12288))
 
 
 def test_secondary_style_rays_inside_the_sphere(cuda_device):
