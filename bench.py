@@ -546,6 +546,18 @@ def standalone_configs(model, dev, pose, K, args):
         rps = n / (ms * 1e-3)
         cfg0["gpu_%d_rays" % n] = {"ms": ms, "rays_per_s": rps, "fp32_fraction": rps * SG_FLOPS_PER_RAY / (fp32 * 1e12),
                                    "hbm_fraction": rps * SG_BYTES_PER_RAY / (hbm * 1e9)}
+    # forward + backward (gradients to the light SGs, roughness, specular reflectance, albedo and the normals)
+    a = sg_inputs(1 << 20, dev)
+    leaves = [t.clone().requires_grad_(True) for t in a[:5]]
+    gy = torch.rand(1 << 20, 3, device=dev)
+
+    def fwd_bwd():
+        for t in leaves:
+            t.grad = None
+        (render_with_sg(*leaves, a[5])["sg_rgb"] * gy).sum().backward()
+    ms_fb = ev_ms(fwd_bwd, 5, warm=2)
+    cfg0["gpu_1048576_rays_fwd_bwd"] = {"ms": ms_fb, "ms_backward_only": ms_fb - cfg0["gpu_1048576_rays"]["ms"],
+                                        "note": "hand-derived adjoint (csrc/sg_adjoint_math.cuh); round 1: forward-mode duals, 34-44 ms"}
     cfg0["note"] = "render_with_sg forward, 128 SGs, K = 1: algorithmic 35 kFLOP + 7.5 k exp/div/sqrt and 72 B per ray -> bound by the " \
                    "FP32/MUFU pipes, not HBM (SURVEY 8d); 1024 rays is one launch of ~10 us (latency), 2^20 rays shows the throughput"
     if not args.no_cpu_baseline:

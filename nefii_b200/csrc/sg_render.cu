@@ -7,7 +7,6 @@
 // hemisphere_int that depends on the sharpness only).  Compiled with -fmad=false: see sg_math.cuh.
 #include "common.cuh"
 #include "sg_math.cuh"
-#include "sg_bwd_math.cuh"
 
 namespace nefii {
 
@@ -122,88 +121,6 @@ background_sg_fwd_kernel(int n_rays, int n_sg, const float* __restrict__ lgt,
     }
     out[ray * 3 + 0] = acc[0]; out[ray * 3 + 1] = acc[1]; out[ray * 3 + 2] = acc[2];
   }
-}
-
-// Backward of render_with_sg: one warp per ray, lane l owns the light SGs l, l+32, ...; every (ray, SG, material) term is
-// differentiated with forward-mode duals over the forward math (sg_bwd_math.cuh).  Light gradients are accumulated in the
-// unit parametrisation (shared memory, then one atomicAdd per value per CTA); roughness / specular-reflectance gradients
-// (tiny [K,*] tensors) likewise; the albedo gradient is per ray.
-__global__ void __launch_bounds__(kSgThreads, 4)
-sg_render_bwd_kernel(int n_rays, int n_sg, int n_mat, const float* __restrict__ lgt, const float* __restrict__ spec,
-                     const float* __restrict__ rough, const float* __restrict__ albedo, const float* __restrict__ normal,
-                     const float* __restrict__ view, const float* __restrict__ out_spec, const float* __restrict__ out_diff,
-                     const float* __restrict__ g_rgb, const float* __restrict__ g_spec, const float* __restrict__ g_diff,
-                     float* __restrict__ g_lgt_acc, float* __restrict__ g_rough, float* __restrict__ g_specrefl,
-                     float* __restrict__ g_albedo) {
-  extern __shared__ unsigned char smem_raw[];
-  float* sAcc = reinterpret_cast<float*>(smem_raw);                 // [n_sg][7]
-  float* sMat = sAcc + n_sg * 7;                                     // [n_mat][4]: d rough, d spec rgb
-  for (int j = threadIdx.x; j < n_sg * 7 + n_mat * 4; j += blockDim.x) sAcc[j] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warp_global = (blockIdx.x * kSgThreads + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * kSgThreads) >> 5;
-  for (long long ray = warp_global; ray < n_rays; ray += n_warps) {
-    float n[3], v[3], al[3], gs[3], gd[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      n[c] = normal[ray * 3 + c]; v[c] = view[ray * 3 + c]; al[c] = albedo[ray * 3 + c];
-      const float gr = g_rgb ? g_rgb[ray * 3 + c] : 0.f;
-      // torch.clamp(min=0) passes the gradient where the summed radiance is positive
-      gs[c] = out_spec[ray * 3 + c] > 0.f ? gr + (g_spec ? g_spec[ray * 3 + c] : 0.f) : 0.f;
-      gd[c] = out_diff[ray * 3 + c] > 0.f ? gr + (g_diff ? g_diff[ray * 3 + c] : 0.f) : 0.f;
-    }
-    float ga[3] = {0.f, 0.f, 0.f};
-    for (int m = lane; m < n_sg; m += 32) {
-      float raw[7], acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 7; ++i) raw[i] = lgt[m * 7 + i];
-      for (int k = 0; k < n_mat; ++k) {
-        float sp[3] = {spec[k * 3 + 0], spec[k * 3 + 1], spec[k * 3 + 2]};
-        float gr = 0.f, gsr[3] = {0.f, 0.f, 0.f};
-        sgb::specular_term_bwd<float>(n, v, raw, rough[k], sp, gs, acc, gr, gsr);
-        atomicAdd(&sMat[k * 4 + 0], gr);
-        atomicAdd(&sMat[k * 4 + 1], gsr[0]); atomicAdd(&sMat[k * 4 + 2], gsr[1]); atomicAdd(&sMat[k * 4 + 3], gsr[2]);
-      }
-      sgb::diffuse_term_bwd<float>(n, raw, al, (float)n_mat, gd, acc, ga);
-#pragma unroll
-      for (int i = 0; i < 7; ++i) atomicAdd(&sAcc[m * 7 + i], acc[i]);
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) ga[c] += __shfl_xor_sync(0xffffffffu, ga[c], off);
-    }
-    if (lane == 0) { g_albedo[ray * 3 + 0] = ga[0]; g_albedo[ray * 3 + 1] = ga[1]; g_albedo[ray * 3 + 2] = ga[2]; }
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < n_sg * 7; j += blockDim.x) atomicAdd(&g_lgt_acc[j], sAcc[j]);
-  for (int j = threadIdx.x; j < n_mat; j += blockDim.x) {
-    atomicAdd(&g_rough[j], sMat[j * 4 + 0]);
-    atomicAdd(&g_specrefl[j * 3 + 0], sMat[j * 4 + 1]);
-    atomicAdd(&g_specrefl[j * 3 + 1], sMat[j * 4 + 2]);
-    atomicAdd(&g_specrefl[j * 3 + 2], sMat[j * 4 + 3]);
-  }
-}
-
-int sg_render_bwd(cudaStream_t stream, int n_rays, int n_sg, int n_mat, const float* lgt, const float* spec, const float* rough,
-                  const float* albedo, const float* normal, const float* view, const float* out_spec, const float* out_diff,
-                  const float* g_rgb, const float* g_spec, const float* g_diff, float* g_lgt_acc, float* g_rough,
-                  float* g_specrefl, float* g_albedo) {
-  NEFII_CHECK_ARG(n_rays >= 0 && n_sg > 0 && n_mat > 0 && n_mat <= kMaxMaterials, "sg_render_bwd: bad sizes");
-  if (n_rays == 0) return NEFII_OK;
-  NEFII_CHECK_ARG(lgt && spec && rough && albedo && normal && view && out_spec && out_diff && g_lgt_acc && g_rough && g_specrefl &&
-                      g_albedo,
-                  "sg_render_bwd: null pointer");
-  const size_t smem = sizeof(float) * ((size_t)n_sg * 7 + (size_t)n_mat * 4);
-  NEFII_CHECK_ARG(smem <= 48 * 1024, "sg_render_bwd: too many light SGs (%d)", n_sg);
-  int blocks = ceil_div(n_rays, kSgThreads / 32);
-  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  sg_render_bwd_kernel<<<blocks, kSgThreads, smem, stream>>>(n_rays, n_sg, n_mat, lgt, spec, rough, albedo, normal, view, out_spec,
-                                                             out_diff, g_rgb, g_spec, g_diff, g_lgt_acc, g_rough, g_specrefl,
-                                                             g_albedo);
-  NEFII_LAUNCH_CHECK();
-  return NEFII_OK;
 }
 
 int sg_render_fwd(cudaStream_t stream, int n_rays, int n_sg, int n_mat, const float* lgt, const float* spec,

@@ -60,13 +60,16 @@ void emu_sg_render_fwd_f64(int n_rays, int n_sg, int n_mat, const double* lgt, c
 }
 }
 
-// ---- backward of render_with_sg through forward-mode duals (same code path as csrc/sg_render.cu: sg_render_bwd) ----
-#include "sg_bwd_math.cuh"
+// ---- backward of render_with_sg: the hand-derived adjoint of csrc/sg_adjoint_math.cuh, in the loop structure of the CUDA
+// kernel (csrc/sg_render.cu: sg_render_bwd_kernel) ----
+#include "sg_adjoint_math.cuh"
 
 extern "C" void emu_sg_render_bwd_f64(int n_rays, int n_sg, int n_mat, const double* lgt, const double* spec, const double* rough,
                                       const double* albedo, const double* normal, const double* view,
                                       const double* g_spec, const double* g_diff, double* acc /*[M,7]*/, double* g_rough /*[K]*/,
-                                      double* g_specrefl /*[K,3]*/, double* g_albedo /*[N,3]*/) {
+                                      double* g_specrefl /*[K,3]*/, double* g_albedo /*[N,3]*/, double* g_normal /*[N,3]*/) {
+  namespace sga = nefii::sga;
+  const double inv_pi = 1.0 / K<double>::pi();
   for (int r = 0; r < n_rays; ++r) {
     // the reference clamps the summed specular / diffuse radiance at 0: recompute the sums for the masks
     double out_rgb[3], out_s[3], out_d[3];
@@ -74,18 +77,48 @@ extern "C" void emu_sg_render_bwd_f64(int n_rays, int n_sg, int n_mat, const dou
     double gs[3], gd[3];
     for (int c = 0; c < 3; ++c) {
       gs[c] = out_s[c] > 0 ? g_spec[3 * r + c] : 0.0;
-      gd[c] = out_d[c] > 0 ? g_diff[3 * r + c] : 0.0;
+      gd[c] = out_d[c] > 0 ? g_diff[3 * r + c] * n_mat : 0.0;     // the reference sums the diffuse term over the K axis
     }
-    double ga[3] = {0, 0, 0};
-    for (int m = 0; m < n_sg; ++m) {
-      for (int k = 0; k < n_mat; ++k) {
-        double gr = 0, gsr[3] = {0, 0, 0};
-        nefii::sgb::specular_term_bwd<double>(normal + 3 * r, view + 3 * r, lgt + 7 * m, rough[k], spec + 3 * k, gs, acc + 7 * m, gr, gsr);
-        g_rough[k] += gr;
-        for (int c = 0; c < 3; ++c) g_specrefl[3 * k + c] += gsr[c];
+    const double* n = normal + 3 * r;
+    const double* v = view + 3 * r;
+    double n_bar[3] = {0, 0, 0}, ga[3] = {0, 0, 0};
+    for (int k = 0; k < n_mat; ++k) {
+      BrdfLobe<double> B;
+      make_brdf_lobe(n, v, rough[k], spec + 3 * k, B);
+      double b_bar[3] = {0, 0, 0}, beta_bar = 0, nu_bar[3] = {0, 0, 0};
+      for (int m = 0; m < n_sg; ++m) {
+        LightSG<double> L;
+        load_light(lgt + 7 * m, L);
+        double w = 0;
+        for (int c = 0; c < 3; ++c) w += gs[c] * L.amp[c] * B.amp[c];
+        double a_bar[3] = {0, 0, 0}, l_bar = 0;
+        const double phi = sga::specular_phi_vjp(n, L.axis, L.sharp, B.axis, B.sharp, w, a_bar, l_bar, b_bar, beta_bar, n_bar);
+        for (int i = 0; i < 3; ++i) acc[7 * m + i] += a_bar[i];
+        acc[7 * m + 3] += l_bar;
+        for (int c = 0; c < 3; ++c) {
+          acc[7 * m + 4 + c] += gs[c] * B.amp[c] * phi;
+          nu_bar[c] += gs[c] * L.amp[c] * phi;
+        }
       }
-      nefii::sgb::diffuse_term_bwd<double>(normal + 3 * r, lgt + 7 * m, albedo + 3 * r, (double)n_mat, gd, acc + 7 * m, ga);
+      sga::brdf_lobe_vjp(n, v, rough[k], spec + 3 * k, b_bar, beta_bar, nu_bar, n_bar, g_rough[k], g_specrefl + 3 * k);
     }
-    for (int c = 0; c < 3; ++c) g_albedo[3 * r + c] = ga[c];
+    for (int m = 0; m < n_sg; ++m) {
+      LightSG<double> L;
+      load_light(lgt + 7 * m, L);
+      double w = 0;
+      for (int c = 0; c < 3; ++c) w += gd[c] * L.amp[c] * albedo[3 * r + c] * inv_pi;
+      double a_bar[3] = {0, 0, 0}, l_bar = 0;
+      const double psi = sga::psi_vjp(n, L.axis, L.sharp, w, n_bar, a_bar, l_bar);
+      for (int i = 0; i < 3; ++i) acc[7 * m + i] += a_bar[i];
+      acc[7 * m + 3] += l_bar;
+      for (int c = 0; c < 3; ++c) {
+        acc[7 * m + 4 + c] += gd[c] * albedo[3 * r + c] * inv_pi * psi;
+        ga[c] += gd[c] * L.amp[c] * psi * inv_pi;
+      }
+    }
+    for (int c = 0; c < 3; ++c) {
+      g_albedo[3 * r + c] = ga[c];
+      if (g_normal) g_normal[3 * r + c] = n_bar[c];
+    }
   }
 }

@@ -58,7 +58,8 @@ def test_f32_close_to_oracle(emu):
 
 
 def test_backward_f64_matches_autograd_of_oracle(emu):
-    """render_with_sg backward via forward-mode duals over the forward math (csrc/sg_bwd_math.cuh) == autograd through the oracle."""
+    """render_with_sg backward by the hand-derived adjoint (csrc/sg_adjoint_math.cuh) == autograd through the oracle, the
+    gradient w.r.t. the normals included."""
     dt = torch.float64
     n, M, K = 120, 24, 2
     normal, view, albedo = [x.to(dt) for x in inputs.shading_inputs(n, seed=8)]
@@ -70,16 +71,17 @@ def test_backward_f64_matches_autograd_of_oracle(emu):
     g = torch.Generator().manual_seed(3)
     g_spec = torch.rand(n, 3, generator=g, dtype=dt)
     g_diff = torch.rand(n, 3, generator=g, dtype=dt)
-    leaves = [t.clone().requires_grad_(True) for t in (lgt, spec, rough, albedo)]
-    ref = sg.render_with_sg(leaves[0], leaves[1], leaves[2], leaves[3], normal, view)
+    leaves = [t.clone().requires_grad_(True) for t in (lgt, spec, rough, albedo, normal)]
+    ref = sg.render_with_sg(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], view)
     ((ref["sg_specular_rgb"] * g_spec).sum() + (ref["sg_diffuse_rgb"] * g_diff).sum()).backward()
     acc = torch.zeros(M, 7, dtype=dt)
     g_rough = torch.zeros(K, dtype=dt)
     g_sr = torch.zeros(K, 3, dtype=dt)
     g_alb = torch.zeros(n, 3, dtype=dt)
+    g_nrm = torch.zeros(n, 3, dtype=dt)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     emu.emu_sg_render_bwd_f64(n, M, K, p(lgt), p(spec), p(rough), p(albedo.contiguous()), p(normal.contiguous()), p(view.contiguous()),
-                              p(g_spec), p(g_diff), p(acc), p(g_rough), p(g_sr), p(g_alb))
+                              p(g_spec), p(g_diff), p(acc), p(g_rough), p(g_sr), p(g_alb), p(g_nrm))
     ln = lgt[:, :3].norm(dim=-1, keepdim=True)
     d = ln + 1e-6
     g_axis = acc[:, :3] / d - lgt[:, :3] * (lgt[:, :3] * acc[:, :3]).sum(-1, keepdim=True) / (ln * d * d)
@@ -88,3 +90,4 @@ def test_backward_f64_matches_autograd_of_oracle(emu):
     assert torch.allclose(g_sr, leaves[1].grad, rtol=1e-6, atol=1e-9)
     assert torch.allclose(g_rough, leaves[2].grad[:, 0], rtol=1e-6, atol=1e-9)
     assert torch.allclose(g_alb, leaves[3].grad, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(g_nrm, leaves[4].grad, rtol=1e-6, atol=1e-8), (g_nrm - leaves[4].grad).abs().max()
