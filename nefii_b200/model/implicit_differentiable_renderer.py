@@ -6,9 +6,10 @@
 ``train.model_class = nefii_b200.model.implicit_differentiable_renderer.IDRNetwork`` is the only change a
 conf needs (utils/general.py:10-16 get_class is the plug-in point).
 
-Scope: the per-ray-batch rendering path with FROZEN geometry (step 2 training, rendering,
-evaluation).  Everything device-side runs through the C ABI; there is no PyTorch fallback.  Paths that need
-gradients into the SDF network (step 1 / un-frozen geometry: eikonal points, SampleNetwork) raise.
+Scope: the per-ray-batch rendering path -- step 2 training with FROZEN geometry (the fused fast path),
+rendering, evaluation, and the same forward with a TRAINABLE geometry (`training and not freeze_geometry`, reference
+:354-389: eikonal samples, d sdf/dx with a graph, SampleNetwork; a composition of twice-differentiable tcgen05 products).
+Everything device-side runs through the C ABI; there is no PyTorch fallback.
 """
 import numpy as np
 import torch
@@ -374,9 +375,6 @@ class IDRNetwork(nn.Module):
         """uniforms / trace_uniforms / eikonal_points: optional injected random numbers (parity tests); by default they are
         drawn like the reference draws them."""
         unfrozen = self.training and not self.state_freeze_geo and torch.is_grad_enabled()
-        if unfrozen and self.render_type != "pt_render_indirect_mlp":
-            raise _lib.NefiiError("nefii_b200: a trainable geometry is supported with render_type pt_render_indirect_mlp "
-                                  "(render_with_sg has no gradient w.r.t. the normals)")
         intrinsics = input["intrinsics"]
         uv = input["uv"]
         pose = input["pose"]

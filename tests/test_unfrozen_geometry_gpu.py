@@ -89,3 +89,4 @@ def test_unfrozen_forward_and_gradients_match_oracle(cuda_device):
     with torch.no_grad():
         s1 = net.implicit_network(x)[:, 0]
     assert torch.isfinite(s1).all() and not torch.equal(s0, s1)
+
