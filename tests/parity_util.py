@@ -23,7 +23,7 @@ def _quant(x, qs=(0.5, 0.95, 0.99, 1.0)):
     return tuple(srt[min(srt.numel() - 1, int(q * (srt.numel() - 1) + 0.5))].item() for q in qs)
 
 
-def fullsize_compare(dev, bumps, n_px, n_rays, training, tiers=None, grads=True, seed=0, verbose=True):
+def fullsize_compare(dev, bumps, n_px, n_rays, training, tiers=None, grads=True, seed=0, verbose=True, ref64=False):
     """BASELINE configs[2]-sized parity run: IDRNetwork.forward_with_uv against oracle/pipeline.py on the same device, same
     weights, same uniforms.  Returns a dict of statistics (used by tests/test_parity_fullsize_gpu.py and printed here)."""
     import bench
@@ -115,6 +115,28 @@ def fullsize_compare(dev, bumps, n_px, n_rays, training, tiers=None, grads=True,
         res['secondary_depth'] = _quant(d2)
     else:
         res['secondary_mismatch'] = None
+    if ref64:
+        # SURVEY 8(d) "parity noise floor": the same oracle in float64 as the yardstick -- |ours - ref64| next to |ref32 - ref64|
+        om64 = om.to(torch.float64)
+        om64.sdf_fn = _chunked(om64.sdf_fn, chunk=1 << 19)
+        with torch.no_grad():
+            r64 = pipeline.forward_with_uv(om64, inp['uv'].double(), inp['pose'].double(), inp['intrinsics'].double(), inp['object_mask'],
+                                           lambda n: U[:n].double(), training, vecs[0].double(), vecs[1].double())
+        h3 = hit & r64['network_object_mask']
+        res['f64'] = dict(hits=int(h3.sum()), mask_mismatch_ours=int((a != r64['network_object_mask']).sum()),
+                          mask_mismatch_ref32=int((b != r64['network_object_mask']).sum()), keys={})
+        for k in ('sg_rgb_values', 'idr_rgb_values', 'normal_values', 'points'):
+            y = r64[k][h3]
+            e_ours = ((mine[k][h3].double() - y).abs() / (y.abs() + 1e-6)).flatten()
+            e_ref = ((ref[k][h3].double() - y).abs() / (y.abs() + 1e-6)).flatten()
+            res['f64']['keys'][k] = dict(ours=((e_ours <= 1e-4).double().mean().item(),) + _quant(e_ours),
+                                         ref32=((e_ref <= 1e-4).double().mean().item(),) + _quant(e_ref))
+        if verbose:
+            print("   vs the float64 oracle (hits common to all three: %d; mask mismatches ours %d, fp32 oracle %d):" % (
+                res['f64']['hits'], res['f64']['mask_mismatch_ours'], res['f64']['mask_mismatch_ref32']))
+            for k, v in res['f64']['keys'].items():
+                print("      %-16s lanes<=1e-4 / median / p95 / p99 / max:  ours %.4f %.2e %.2e %.2e %.2e | fp32 oracle %.4f %.2e %.2e %.2e %.2e" % (
+                    (k,) + v['ours'] + v['ref32']))
     if grads:
         def rel(x, y):
             return (x - y).norm().item() / (y.norm().item() + 1e-20)
@@ -149,4 +171,5 @@ def fullsize_compare(dev, bumps, n_px, n_rays, training, tiers=None, grads=True,
                 res['g_lgt'], " ".join("%.1e" % x for x in res['g_mat']), " ".join("%.1e" % x for x in res['g_rad'])))
     if tiers is not None:
         _lib.check(_lib.raw().nefii_trace_set_tiers(0, 0))
+    res['_outputs'] = (mine, ref)      # for diagnostics (tools/diag_tail.py)
     return res

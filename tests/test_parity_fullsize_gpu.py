@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 
 
 def test_training_step_at_configs2_size(cuda_device):
-    r = fullsize_compare(cuda_device, bumps=0.08, n_px=2048, n_rays=64, training=True, grads=True, verbose=True)
+    r = fullsize_compare(cuda_device, bumps=0.08, n_px=2048, n_rays=64, training=True, grads=True, verbose=True, ref64=True)
     assert r['pixels'] == 2048 and r['hits'] > 300
     assert r['mask_mismatch'] == 0, r['mask_mismatch']                 # per pixel: all 64 rays of the pixel agree
     assert r['depth'][0] < 5e-7 and r['depth'][1] < 3e-6, r['depth']   # median / p95 of |d points| on hits (pixel means)
@@ -38,6 +38,14 @@ def test_training_step_at_configs2_size(cuda_device):
     assert k['normal_values']['absq'][2] < 5e-5, k['normal_values']    # unit vectors: absolute, p99 (measured 1.4e-5)
     assert r['background_rel'][3] < 1e-5                               # environment lookup on miss rays: max rel
     assert r['secondary_mismatch'] is not None and r['secondary_mismatch'] <= 1e-4 * r['secondary_rays'], r['secondary_mismatch']
+    # SURVEY 8(d) noise floor: against the SAME oracle run in float64, next to the fp32 oracle's own distance from it.  Measured:
+    # sg_rgb lanes within 1e-4 of the float64 result: ours 98.5 %, the fp32 oracle 99.2 % (p95 1.6e-5 / 6.4e-6); idr_rgb (the
+    # radiance MLP behind a 2^9-frequency encoding of the hit point) 71 % / 91 %; hit masks: 0 mismatches for both.
+    f = r['f64']
+    assert f['mask_mismatch_ours'] == f['mask_mismatch_ref32'] == 0, f
+    assert f['keys']['sg_rgb_values']['ours'][0] >= f['keys']['sg_rgb_values']['ref32'][0] - 0.015, f['keys']['sg_rgb_values']
+    assert f['keys']['sg_rgb_values']['ours'][2] <= 5e-5, f['keys']['sg_rgb_values']        # p95 vs float64
+    assert f['keys']['points']['ours'][0] >= 0.995, f['keys']['points']
     # north_star: gradients within rel 1e-3
     assert r['g_lgt'] < 1e-3, r['g_lgt']
     assert max(r['g_mat']) < 1e-3, r['g_mat']

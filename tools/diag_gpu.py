@@ -419,7 +419,7 @@ def diag_fullsize():
     n_rays = int(os.environ.get("FULL_RAYS", "64"))
     tiers = [tuple(int(v) for v in t.split(",")) for t in os.environ.get("FULL_TIERS", "0,0").split(";")]
     for t in tiers:
-        fullsize_compare(dev, bumps, n_px, n_rays, True, tiers=t, grads=True)
+        fullsize_compare(dev, bumps, n_px, n_rays, True, tiers=t, grads=True, ref64=os.environ.get("FULL_REF64", "0") == "1")
     fullsize_compare(dev, bumps, n_px * 4, 0, False, tiers=tiers[0], grads=False)
     # per-ray lanes (no averaging over the rays of a pixel): the same rays as single-ray pixels
     fullsize_compare(dev, bumps, min(n_px * max(n_rays, 1), 32768), 0, True, tiers=tiers[0], grads=False)
