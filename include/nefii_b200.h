@@ -87,8 +87,13 @@ typedef struct nefii_gemm_desc {
   const void* sav_hi; const void* sav_lo; int32_t sav_ld; int32_t sav_ncols; float sav_scale; /* backward: saved activations */
   int32_t k_splits; int64_t f32_split_stride; int32_t k_splits_used;   /* split-K: partial s -> dst_f32 + s*stride (floats); k_splits_used is an output */
   int32_t k_flush;                /* K blocks per TMEM partial for this launch (1 = most accurate); 0 = library default */
-  int32_t dst_pad_ok;             /* 1: plane columns [dst_ncols, round_up(dst_ncols,128)) may be overwritten (caller refills them) */
+  int32_t dst_pad_ok;             /* 1: a ragged last 128-column span stays on the bulk-store epilogue; plane columns >= dst_ncols are never written */
   int32_t fmt;                    /* plane format of a, b, dst, seed and sav: 0 bf16 split, 1 fp16 split */
+  /* "PE prologue": pe_x != NULL -> row m of A is the positional encoding of pe_x[m] (embedder.py:22-36: [x, sin(2^0 x), cos(2^0 x),
+   * ...], 3 + 6 pe_n_freqs <= 64 columns), computed inside the kernel straight into the shared-memory operand tile; a_hi / a_lo
+   * are ignored and k_pad must be 64.  pe_side_*: optional planes that receive the encoding times pe_side_scale at columns
+   * [pe_side_col0, pe_side_col0 + 3 + 6 pe_n_freqs) (the PE half of a skip layer's input). */
+  const float* pe_x; int32_t pe_n_freqs; void* pe_side_hi; void* pe_side_lo; int32_t pe_side_ld; int32_t pe_side_col0; float pe_side_scale;
 } nefii_gemm_desc;
 
 int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* desc /* host */);
@@ -155,6 +160,11 @@ int nefii_sdf_destroy(void* handle);
  * NEFII_SDF_FORMAT=bf16|fp16 sets the default at load.  Call before nefii_sdf_set_weights (it drops the packed weights). */
 int nefii_sdf_set_format(void* handle, int fmt);
 int nefii_sdf_get_format(void* handle);
+/* Where an evaluation's positional encoding is computed: 0 (default) one encode kernel writes layer 0's input planes and the PE
+ * half of the skip layer's input in a single pass; 1 inside layer 0's GEMM kernel ("PE prologue": two otherwise idle warps
+ * write the encoding straight into the shared-memory operand tile -- no launch, no round trip, but measured SLOWER on B200
+ * because those two warps are latency-bound on the tile's 2 304 sincosf; NEFII_SDF_PE_PROLOGUE=1 at load). */
+int nefii_sdf_set_pe_prologue(int on);
 /* weights / biases: host arrays of n_hidden+1 device pointers; weights[l] is the EFFECTIVE fp32 matrix
  * [out_l, in_l] (weight_norm folded: g * v / |v|), row-major contiguous; the last one is [1 + d_feat, width].
  * Call again whenever the parameters change. */

@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnefii_b200.so")
+LIB_PATH = os.environ.get("NEFII_LIB_PATH") or os.path.join(_HERE, "libnefii_b200.so")   # the override is for A/B builds
 
 c_void_p, c_int, c_float, c_longlong = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
 
@@ -61,6 +61,7 @@ SIGNATURES = {
     "nefii_split_to_planes_fmt": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int],
     "nefii_sdf_set_format": [c_void_p, c_int],
     "nefii_sdf_get_format": [c_void_p],
+    "nefii_sdf_set_pe_prologue": [c_int],
     "nefii_gemm_set_trunc_comp_fmt": [c_int, c_int, c_float],
     "nefii_idr_loss_fwd": [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_int, c_int, c_float, c_void_p],
     "nefii_idr_loss_bwd": [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_int, c_int, c_float] + [c_void_p] * 6,

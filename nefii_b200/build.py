@@ -42,6 +42,7 @@ def _compile(src):
     if not _needs(src, obj, headers + [os.path.abspath(__file__)]):
         return obj, ""
     flags = list(BASE_FLAGS) + (EXACT_FLAGS if name in EXACT_FP32 else []) + (FAST_FLAGS if name in FAST_FP32 else [])
+    flags += os.environ.get("NEFII_NVCC_EXTRA", "").split()      # development: A/B builds (-D switches)
     cmd = [NVCC] + flags + ["-I", CSRC, "-c", src, "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:

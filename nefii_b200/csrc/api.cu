@@ -90,6 +90,9 @@ int nefii_gemm_split_bf16(void* stream, nefii_gemm_desc* d) {
   e.sav_ncols = d->sav_ncols; e.sav_scale = d->sav_scale;
   p.k_splits = d->k_splits; p.f32_split_stride = d->f32_split_stride;
   p.k_flush = d->k_flush; e.dst_pad_ok = d->dst_pad_ok; e.fmt = d->fmt;
+  p.pe.x = d->pe_x; p.pe.n_freqs = d->pe_n_freqs;
+  p.pe.side.hi = (__nv_bfloat16*)d->pe_side_hi; p.pe.side.lo = (__nv_bfloat16*)d->pe_side_lo; p.pe.side.ld = d->pe_side_ld;
+  p.pe.side_col0 = d->pe_side_col0; p.pe.side_scale = d->pe_side_scale;
   int used = 1;
   p.k_splits_used = &used;
   int rc = nefii::gemm_split_bf16((cudaStream_t)stream, p);
@@ -129,6 +132,10 @@ int nefii_sdf_set_format(void* handle, int fmt) {
   if (!handle) return nefii::set_error(NEFII_ERR_ARG, "nefii_sdf_set_format: null handle");
   nefii::trace_graph_clear();     // cached trace graphs carry the plane format in their kernel arguments
   return static_cast<nefii::SdfNet*>(handle)->set_format(fmt);
+}
+int nefii_sdf_set_pe_prologue(int on) {
+  nefii::trace_graph_clear();     // cached trace graphs hold the launch sequence of an evaluation
+  return nefii::sdf_set_pe_prologue(on);
 }
 int nefii_sdf_get_format(void* handle) {
   if (!handle) return -1;

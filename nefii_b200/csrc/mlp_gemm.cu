@@ -211,7 +211,7 @@ int gemm_prepare_device() {
   NEFII_CHECK_ARG(dev >= 0 && dev < 64, "gemm: device index out of range");
   std::lock_guard<std::mutex> lock(g_dev_mu);
   if (g_dev_ready[dev]) return NEFII_OK;
-  for (int key = 0; key < 12; ++key) {
+  for (int key = 0; key < kGemmKernelKeys; ++key) {
     GemmKernelFn f1 = select_gemm_kernel<1>(key);
     GemmKernelFn f2 = reinterpret_cast<GemmKernelFn>(gemm_pair_kernel(key));
     if (f1) NEFII_CUDA(cudaFuncSetAttribute(f1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -293,11 +293,15 @@ int gemm_profile_fetch(double* out3) {
 }
 
 int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
-  NEFII_CHECK_ARG(p.a_hi && p.a_lo && p.b_hi && p.b_lo, "gemm_split_bf16: null operand");
-  NEFII_CHECK_ARG(p.k_pad > 0 && p.k_pad % BK == 0 && p.k_pad <= p.a_ld && p.k_pad <= p.b_ld,
+  const bool pe_mode = p.pe.x != nullptr;
+  NEFII_CHECK_ARG((pe_mode || (p.a_hi && p.a_lo)) && p.b_hi && p.b_lo, "gemm_split_bf16: null operand");
+  NEFII_CHECK_ARG(p.k_pad > 0 && p.k_pad % BK == 0 && (pe_mode || p.k_pad <= p.a_ld) && p.k_pad <= p.b_ld,
                   "gemm_split_bf16: k_pad=%d must be a multiple of %d and <= ld (a_ld=%d b_ld=%d)", p.k_pad, BK, p.a_ld, p.b_ld);
+  NEFII_CHECK_ARG(!pe_mode || (p.k_pad == BK && p.pe.n_freqs >= 0 && 3 + 6 * p.pe.n_freqs <= BK && p.k_splits <= 1),
+                  "gemm_split_bf16: the PE prologue produces one %d-wide K block (n_freqs=%d)", BK, p.pe.n_freqs);
+  NEFII_CHECK_ARG(!pe_mode || p.pe.side.hi == nullptr || p.pe.side.lo != nullptr, "gemm_split_bf16: PE side planes need hi and lo");
   NEFII_CHECK_ARG(p.n_pad > 0 && p.n_pad % BN == 0, "gemm_split_bf16: n_pad=%d must be a multiple of %d", p.n_pad, BN);
-  NEFII_CHECK_ARG(p.a_ld % 8 == 0 && p.b_ld % 8 == 0, "gemm_split_bf16: leading dimensions must be multiples of 8");
+  NEFII_CHECK_ARG((pe_mode || p.a_ld % 8 == 0) && p.b_ld % 8 == 0, "gemm_split_bf16: leading dimensions must be multiples of 8");
   NEFII_CHECK_ARG(p.epi.n_valid > 0 && p.epi.n_valid <= p.n_pad, "gemm_split_bf16: n_valid out of range");
   NEFII_CHECK_ARG(p.epi.n_last <= kMaxLast, "gemm_split_bf16: fused output layer supports at most %d outputs", kMaxLast);
   NEFII_CHECK_ARG(p.k_flush >= 0 && p.k_flush <= 64, "gemm_split_bf16: k_flush out of range");
@@ -310,10 +314,14 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   const int cl = (g_cluster_pref == 2 && m_tiles >= 2) ? 2 : 1;   // CTA pairs need two row tiles to work on
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   const int bk = cl == 2 ? Ring<2>::kBK : Ring<1>::kBK;
-  if ((rc = make_map(&ma_hi, p.a_hi, p.rows_cap, p.a_ld, p.k_pad, BM, bk))) return rc;
-  if ((rc = make_map(&ma_lo, p.a_lo, p.rows_cap, p.a_ld, p.k_pad, BM, bk))) return rc;
   if ((rc = make_map(&mb_hi, p.b_hi, p.n_pad, p.b_ld, p.k_pad, BN / cl, bk))) return rc;
   if ((rc = make_map(&mb_lo, p.b_lo, p.n_pad, p.b_ld, p.k_pad, BN / cl, bk))) return rc;
+  if (pe_mode) {   // the kernel never touches the A maps
+    ma_hi = mb_hi; ma_lo = mb_lo;
+  } else {
+    if ((rc = make_map(&ma_hi, p.a_hi, p.rows_cap, p.a_ld, p.k_pad, BM, bk))) return rc;
+    if ((rc = make_map(&ma_lo, p.a_lo, p.rows_cap, p.a_ld, p.k_pad, BM, bk))) return rc;
+  }
   const int n_chunks = ceil_div(p.epi.dst_zero_to > p.epi.n_valid ? p.epi.dst_zero_to : p.epi.n_valid, BN);
   // plain hidden layers (the kernel's fast_layer): the output planes as tensors for the epilogue's bulk stores
   CUtensorMap md_hi = ma_hi, md_lo = ma_lo;
@@ -338,8 +346,10 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   const bool fuse = p.epi.mode == 0 && p.epi.w_last != nullptr;
   NEFII_CHECK_ARG(!fuse || (p.epi.dst_last != nullptr && p.epi.n_last >= 1), "gemm_split_bf16: fused output layer needs dst_last");
   NEFII_CHECK_ARG(p.epi.seed.hi == nullptr || fuse, "gemm_split_bf16: seed planes need the fused output layer");
-  const int key = ((cl == 2) ? 12 : 0) + (fuse ? 8 : 0) + p.epi.mode * 4 + p.epi.act;
-  fn = cl == 2 ? reinterpret_cast<GemmKernelFn>(gemm_pair_kernel(key % 12)) : select_gemm_kernel<1>(key % 12);
+  NEFII_CHECK_ARG(!pe_mode || (p.epi.mode == 0 && !fuse && (p.epi.act == ACT_SOFTPLUS100 || p.epi.act == ACT_NONE)),
+                  "gemm_split_bf16: the PE prologue is instantiated for plain forward layers (softplus / no activation)");
+  const int key = pe_mode ? (p.epi.act == ACT_SOFTPLUS100 ? 12 : 13) : (fuse ? 8 : 0) + p.epi.mode * 4 + p.epi.act;
+  fn = cl == 2 ? reinterpret_cast<GemmKernelFn>(gemm_pair_kernel(key)) : select_gemm_kernel<1>(key);
   if (fn == nullptr) return set_error(NEFII_ERR_ARG, "gemm_split_bf16: bad mode/act (%d/%d)", p.epi.mode, p.epi.act);
   const int k_blocks = p.k_pad / BK;
   int splits = p.k_splits > 1 ? p.k_splits : 1;
@@ -396,7 +406,7 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
       scale_last = (splits == 1) ? 1.0f + rho.v[len_last < 64 ? len_last : 64] : scale_full;
     }
     NEFII_CUDA(cudaLaunchKernelEx(&cfg, fn, ma_hi, ma_lo, mb_hi, mb_lo, md_hi, md_lo, store_tma, p.count, p.rows_cap, k_blocks, n_chunks, kb_per,
-                                  (long long)p.f32_split_stride, g_debug, kf_tail | (kf_head << 8), scale_full, scale_last, p.epi));
+                                  (long long)p.f32_split_stride, g_debug, kf_tail | (kf_head << 8), scale_full, scale_last, p.epi, p.pe));
   }
   if (rec) NEFII_CUDA(cudaEventRecord(rec->b, stream));
   NEFII_LAUNCH_CHECK();

@@ -28,8 +28,8 @@ struct GemmEpilogue {
   int dst_col0 = 0;
   int dst_ncols = 0;
   int dst_zero_to = 0;      // plane columns [dst_ncols, dst_zero_to) are written as zeros
-  int dst_pad_ok = 0;       // 1: plane columns [dst_ncols, round_up(dst_ncols, 128)) may be overwritten with finite garbage
-                            // (the caller fills them afterwards): a ragged last column span then stays on the fast epilogue
+  int dst_pad_ok = 0;       // 1: a ragged last 128-column span stays on the bulk-store epilogue (the store clips at dst_ncols,
+                            // nothing beyond is written: those plane columns may hold other data, e.g. a skip layer's PE half)
   // optional fp32 copy of columns [f32_begin, f32_end): dst_f32[m * f32_ld + n - f32_begin]
   float* dst_f32 = nullptr;
   int f32_ld = 0, f32_begin = 0, f32_end = 0;
@@ -48,6 +48,19 @@ struct GemmEpilogue {
   float sav_scale = 1.f;
 };
 
+// A operand generated inside the kernel ("PE prologue"): row m of A = the positional encoding of x[m] (reference embedder.py:22-36:
+// [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...], 3 + 6 n_freqs <= 64 columns, zero padded to one 64-wide K block).  Two idle warps
+// of the kernel's role warpgroup compute it straight into the swizzled shared-memory tile the tensor core reads; no plane ever
+// holds it.  Optionally the same encoding times side_scale is also written to plane columns [side_col0, side_col0 + d_pe) of
+// `side` (the PE half of a later skip layer's input).
+struct PeSource {
+  const float* x = nullptr;   // [rows, 3] fp32; nullptr: A comes from planes (a_hi / a_lo) by TMA
+  int n_freqs = 0;
+  Planes side;                // optional
+  int side_col0 = 0;
+  float side_scale = 1.f;
+};
+
 struct GemmProblem {
   // A: activations [rows_cap, k_pad] as planes; B: weights [n_pad, k_pad] as planes (K-major both)
   const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo; int a_ld; int rows_cap;
@@ -58,6 +71,7 @@ struct GemmProblem {
   long long f32_split_stride = 0;
   int* k_splits_used = nullptr;   // host out: number of partials actually produced
   int k_flush = 0;          // K blocks per TMEM partial for this launch (accuracy tier); 0: the library default
+  PeSource pe;              // pe.x != nullptr: a_hi / a_lo are ignored, k_pad must be 64
   GemmEpilogue epi;
 };
 

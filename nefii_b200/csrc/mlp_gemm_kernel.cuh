@@ -46,6 +46,7 @@ static_assert(Ring<1>::kStages <= kMaxStages && Ring<2>::kStages <= kMaxStages, 
 // mbarriers: [0..2] operand stage full, [3..5] stage empty, [6..7] TMEM partial full, [8..9] TMEM partial empty
 constexpr int kBarFull = 0, kBarEmpty = kMaxStages, kBarTFull = 2 * kMaxStages, kBarTEmpty = 2 * kMaxStages + 2;
 constexpr int kEpiWarps = 8;
+constexpr int kPeWarps = 2;               // warps 10, 11: idle unless the A operand is a positional encoding computed in the kernel
 constexpr int kThreads = 128 + kEpiWarps * 32;  // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1,2: epilogue
 constexpr int kTmemCols = 512;
 constexpr int kMaxLast = 4;
@@ -347,9 +348,10 @@ struct FastStore {
   int y0;                       // row_warp0
 };
 
-template <int ACT, bool TMA>
+// KEEP: the span's last real column (keep_from) is not on a 16-byte boundary (a separate instance: the common one stays lean)
+template <int ACT, bool TMA, bool KEEP = false>
 __device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bias4, int n_span0, float scale, const FastStore& fs, int dbg,
-                                                 int fmt) {
+                                                 int fmt, int keep_from = -1, const uint4* keep_hi = nullptr, const uint4* keep_lo = nullptr) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int c = 0; c < kColsPerWarp / 32; ++c) {
@@ -364,6 +366,22 @@ __device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bia
       o[4] = act_fwd<ACT>(v[8 * g + 4] + bb.x) * scale; o[5] = act_fwd<ACT>(v[8 * g + 5] + bb.y) * scale;
       o[6] = act_fwd<ACT>(v[8 * g + 6] + bb.z) * scale; o[7] = act_fwd<ACT>(v[8 * g + 7] + bb.w) * scale;
       split8(o, fmt, hq[g], lq[g]);
+      // The bulk store writes whole 16-byte pieces: when the layer's last real column (keep_from) falls inside this piece, the
+      // plane elements from keep_from on are not this layer's -- they keep what is there (the PE half of a skip layer's input,
+      // written by layer 0's kernel): patched in from global memory before the tile is staged.
+      if (KEEP && TMA) {
+        const int g0 = n_span0 + c * 32 + 8 * g;
+        if (g0 < keep_from && g0 + 8 > keep_from) {
+          const uint4 kh = __ldg(keep_hi + (g0 >> 3)), kl = __ldg(keep_lo + (g0 >> 3));
+          unsigned short* ph = reinterpret_cast<unsigned short*>(&hq[g]);
+          unsigned short* pl = reinterpret_cast<unsigned short*>(&lq[g]);
+          const unsigned short* qh = reinterpret_cast<const unsigned short*>(&kh);
+          const unsigned short* ql = reinterpret_cast<const unsigned short*>(&kl);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (g0 + j >= keep_from) { ph[j] = qh[j]; pl[j] = ql[j]; }
+        }
+      }
     }
     if (dbg & 16) {   // timing ablation: math only
       if (hq[0].x == 0x7fc07fc1u && lq[3].w == 0x12345678u) fs.p_hi[c] = __float2bfloat16(1.f);
@@ -575,13 +593,16 @@ struct PartSched {
   }
 };
 
-template <int MODE, int ACT, bool FUSE, int CL>
+// PE = true: the "PE prologue" instantiation (A operand computed in the kernel, see PeSource); a separate instantiation so that
+// its code -- sincosf in warps limited to 40 registers, with a stack frame -- costs the other variants nothing.
+template <int MODE, int ACT, bool FUSE, int CL, bool PE = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const __grid_constant__ CUtensorMap map_d_hi, const __grid_constant__ CUtensorMap map_d_lo, int store_tma,
                        const int* __restrict__ count_ptr, int rows_cap, int k_blocks_total, int n_chunks, int kb_per_split,
-                       long long f32_split_stride, int dbg, int k_flush, float part_scale_full, float part_scale_last, const __grid_constant__ GemmEpilogue epi_in) {
+                       long long f32_split_stride, int dbg, int k_flush, float part_scale_full, float part_scale_last, const __grid_constant__ GemmEpilogue epi_in,
+                       const __grid_constant__ PeSource pe) {
   // Persistent over row tiles: CTA x handles tiles x, x + gridDim.x, ... so that the final epilogue math of one tile
   // overlaps the MMAs of the next (the pipelines and barrier phases simply keep running across tiles).
   int m_tile0 = blockIdx.x;
@@ -621,7 +642,8 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(&bars[kBarFull + s]), 1);    // the (leader's) producer arrives once, TMA completes the bytes
+      // the (leader's) producer arrives once, TMA completes the bytes; PE prologue: plus the two encoding warps of every CTA
+      mbar_init(smem_u32(&bars[kBarFull + s]), PE ? 1 + kPeWarps * CL : 1);
       mbar_init(smem_u32(&bars[kBarEmpty + s]), 1);   // one commit (multicast to both CTAs of a pair)
     }
     for (int b = 0; b < 2; ++b) {
@@ -694,17 +716,23 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           if (dbg & 2) { if (cta_rank == 0) mbar_arrive(full); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
           unsigned char* st = tiles + (size_t)stage * kStageBytes;
           const int kx = kb_begin * BK + ks * kBK;
+          const bool load_a = !PE;                                      // PE prologue: warps 10, 11 write the A tiles
+          const int tx = load_a ? kStageBytes : 2 * kBTileBytes;
           if (CL == 1) {
-            mbar_expect_tx(full, kStageBytes);
-            tma_load_2d(smem_u32(st), &map_a_hi, full, kx, m_tile * BM);
-            tma_load_2d(smem_u32(st + kATileBytes), &map_a_lo, full, kx, m_tile * BM);
+            mbar_expect_tx(full, tx);
+            if (load_a) {
+              tma_load_2d(smem_u32(st), &map_a_hi, full, kx, m_tile * BM);
+              tma_load_2d(smem_u32(st + kATileBytes), &map_a_lo, full, kx, m_tile * BM);
+            }
             tma_load_2d(smem_u32(st + 2 * kATileBytes), &map_b_hi, full, kx, nc * BN);
             tma_load_2d(smem_u32(st + 2 * kATileBytes + kBTileBytes), &map_b_lo, full, kx, nc * BN);
           } else {
-            if (cta_rank == 0) mbar_expect_tx(full, 2 * kStageBytes);   // both CTAs' bytes land on the leader's barrier
+            if (cta_rank == 0) mbar_expect_tx(full, 2 * tx);            // both CTAs' bytes land on the leader's barrier
             const int brow = nc * BN + cta_rank * R::kBRows;            // this CTA's half of the weight tile
-            tma_load_2d_pair(smem_u32(st), &map_a_hi, full, kx, m_tile * BM);
-            tma_load_2d_pair(smem_u32(st + kATileBytes), &map_a_lo, full, kx, m_tile * BM);
+            if (load_a) {
+              tma_load_2d_pair(smem_u32(st), &map_a_hi, full, kx, m_tile * BM);
+              tma_load_2d_pair(smem_u32(st + kATileBytes), &map_a_lo, full, kx, m_tile * BM);
+            }
             tma_load_2d_pair(smem_u32(st + 2 * kATileBytes), &map_b_hi, full, kx, brow);
             tma_load_2d_pair(smem_u32(st + 2 * kATileBytes + kBTileBytes), &map_b_lo, full, kx, brow);
           }
@@ -768,6 +796,72 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           else tc_commit_pair(smem_u32(&bars[kBarTFull + buf]), 3);       // ... in both CTAs' TMEM
         }
       }
+    }
+  } else if (PE) {
+    // ---------------------------------------------------------------- PE prologue (warps 10, 11)
+    // Row r of the tile = encoding of x[m_tile * 128 + r], written as hi / lo planes into the stage's A tiles in the layout TMA
+    // would have produced (K-major rows of 128 bytes, SWIZZLE_128B: 16-byte piece j of row r sits at piece j ^ (r & 7)), then
+    // made visible to the tensor core (async proxy) and signalled on the (leader's) full barrier like a completed load.
+    static_assert(kBK == 64, "the PE prologue writes whole 64-column K blocks");
+    const int pw = role - 2;                      // 0, 1
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int m_tile = m_tile0; NEFII_TILE_LIVE(m_tile); m_tile += tile_stride)
+    for (int nc = nc_begin; nc < nc_end; ++nc) {
+      mbar_wait(smem_u32(&bars[kBarEmpty + stage]), phase ^ 1);
+      unsigned char* st = tiles + (size_t)stage * kStageBytes;
+#pragma unroll 1
+      for (int half_rows = 0; half_rows < 2; ++half_rows) {
+        const int r = pw * 64 + half_rows * 32 + lane;
+        const long long row = (long long)m_tile * BM + r;
+        const bool ok = row < m_limit;
+        float p[3] = {0.f, 0.f, 0.f};
+        if (ok) { p[0] = pe.x[row * 3 + 0]; p[1] = pe.x[row * 3 + 1]; p[2] = pe.x[row * 3 + 2]; }
+        unsigned short* a_hi = reinterpret_cast<unsigned short*>(st + (size_t)r * 128);
+        unsigned short* a_lo = reinterpret_cast<unsigned short*>(st + kATileBytes + (size_t)r * 128);
+        const int sw = r & 7;
+        const bool side = ok && nc == 0 && pe.side.hi != nullptr;
+        unsigned short* s_hi = reinterpret_cast<unsigned short*>(pe.side.hi) + row * pe.side.ld + pe.side_col0;
+        unsigned short* s_lo = reinterpret_cast<unsigned short*>(pe.side.lo) + row * pe.side.ld + pe.side_col0;
+        auto put = [&](int col, float v) {
+          uint32_t wh, wl;
+          split_pair(v, 0.f, epi.fmt, wh, wl);
+          const int pos = (((col >> 3) ^ sw) << 3) | (col & 7);
+          a_hi[pos] = (unsigned short)wh;
+          a_lo[pos] = (unsigned short)wl;
+          if (side) {
+            split_pair(v * pe.side_scale, 0.f, epi.fmt, wh, wl);
+            s_hi[col] = (unsigned short)wh;
+            s_lo[col] = (unsigned short)wl;
+          }
+        };
+#pragma unroll
+        for (int c = 0; c < 3; ++c) put(c, p[c]);
+        for (int k = 0; k < pe.n_freqs; ++k) {
+          const float f = exp2f((float)k);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float sn, cs;
+            sincosf(p[c] * f, &sn, &cs);
+            put(3 + 6 * k + c, sn);
+            put(6 + 6 * k + c, cs);
+          }
+        }
+        // zero padding up to the 64-wide K block (finite values: the weight planes' padding is zero, but 0 * NaN is not)
+        const int d_pe = 3 + 6 * pe.n_freqs;
+        for (int col = d_pe; col < BK; ++col) {
+          const int pos = (((col >> 3) ^ sw) << 3) | (col & 7);
+          a_hi[pos] = 0;
+          a_lo[pos] = 0;
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (CL == 1) mbar_arrive(smem_u32(&bars[kBarFull + stage]));
+        else mbar_arrive_cluster(smem_u32(&bars[kBarFull + stage]), 0);
+      }
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   }
   } else {
@@ -866,12 +960,21 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       }
       const int n_span0 = nc * BN + half * kColsPerWarp;
       if (dbg & 1) continue;
-      // dst_pad_ok: the plane columns up to the next multiple of 128 belong to this layer too (zero weights, zero bias; the
-      // bulk store clips at the tensor map's extent dst_ncols, the predicated path may overwrite them: the caller refills them)
-      if (fast_layer && n_span0 + kColsPerWarp <= n_fast) {
+      // dst_pad_ok: the plane columns up to the next multiple of 128 are never written -- the bulk store clips at the tensor
+      // map's extent (dst_ncols); a ragged span that cannot take the bulk store falls through to the predicated path below
+      // (the PE half of a skip layer's input may already sit in those columns)
+      const bool whole_rows = store_tma && row - lane + 32 <= m_limit;
+      if (fast_layer && n_span0 + kColsPerWarp <= n_fast && (whole_rows || n_span0 + kColsPerWarp <= n_real)) {
         // whole 32-row tiles leave by bulk tensor store; the ragged last tile keeps per-row predicates
-        if (store_tma && row - lane + 32 <= m_limit)
-          finish_span_fast<ACT, true>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg, epi.fmt);
+        if (whole_rows) {
+          // a ragged span (dst_pad_ok) whose last real column is not on a 16-byte boundary: see finish_span_fast
+          if (n_span0 + kColsPerWarp > n_real && (n_real & 7) != 0)
+            finish_span_fast<ACT, true, true>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg, epi.fmt, n_real,
+                                              reinterpret_cast<const uint4*>(epi.dst.hi + row * epi.dst.ld + epi.dst_col0),
+                                              reinterpret_cast<const uint4*>(epi.dst.lo + row * epi.dst.ld + epi.dst_col0));
+          else
+            finish_span_fast<ACT, true>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg, epi.fmt);
+        }
         else
           finish_span_fast<ACT, false>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg, epi.fmt);
         continue;
@@ -926,9 +1029,11 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
 }
 
 using GemmKernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, int, const int*, int, int, int,
-                              int, long long, int, int, float, float, GemmEpilogue);
+                              int, long long, int, int, float, float, GemmEpilogue, PeSource);
 
-// kernel of one (mode, act, fused-output-layer) combination for cluster size CL; key = fuse * 8 + mode * 4 + act
+// kernel of one (mode, act, fused-output-layer) combination for cluster size CL; key = fuse * 8 + mode * 4 + act, 12 / 13 = the
+// PE prologue instantiations
+constexpr int kGemmKernelKeys = 14;
 template <int CL>
 GemmKernelFn select_gemm_kernel(int key) {
   switch (key) {
@@ -944,6 +1049,8 @@ GemmKernelFn select_gemm_kernel(int key) {
     case 9: return gemm_split_bf16_kernel<0, ACT_SOFTPLUS100, true, CL>;
     case 10: return gemm_split_bf16_kernel<0, ACT_RELU, true, CL>;
     case 11: return gemm_split_bf16_kernel<0, ACT_ELU, true, CL>;
+    case 12: return gemm_split_bf16_kernel<0, ACT_SOFTPLUS100, false, CL, true>;   // PE prologue (layer 0 of the SDF network)
+    case 13: return gemm_split_bf16_kernel<0, ACT_NONE, false, CL, true>;          // ... without activation (tests)
     default: return nullptr;
   }
 }

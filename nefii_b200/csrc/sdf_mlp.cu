@@ -1,5 +1,6 @@
 // SDF / feature MLP (reference ImplicitNetwork, code/model/implicit_differentiable_renderer.py:18-123)
-// sequenced over the tcgen05 layer GEMM: positional encoding -> n_hidden x (Linear + Softplus(100)),
+// sequenced over the tcgen05 layer GEMM: positional encoding (one kernel, or inside layer 0's GEMM: mlp_gemm_kernel.cuh "PE
+// prologue") -> n_hidden x (Linear + Softplus(100)),
 // skip concat at `skip_layer`, fused 1-wide output layer, and the closed-form input gradient
 // (d sdf / d x, what ImplicitNetwork.gradient obtains through autograd) as a reverse chain of GEMMs.
 #include <cstdlib>
@@ -34,25 +35,25 @@ __device__ __forceinline__ void split_pair(float a, float b, int fmt, uint32_t& 
   }
 }
 
-// Writes PE(x) * scale into plane columns [col0, col0 + d_pe) and zeros up to col0 + zero_to.
+// ONE pass over the points writes both copies of the positional encoding an evaluation needs: PE(x) as the 64-column input
+// planes of layer 0 (zero padded), and PE(x) / sqrt(2) into plane columns [side_col0, side_col0 + d_pe) of the skip layer's
+// input (next to the h columns that layer skip - 1 writes later; its bulk store leaves these columns alone).
 // One lane per point: 3 x n_freqs sincosf calls give the whole encoding of a row (layout of embedder.py:22-36:
 // [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...], 3 components each); the warp's 32 rows are staged in shared memory and
-// written back with consecutive lanes on consecutive columns (16-byte stores when the destination allows it).
+// written back with consecutive lanes on consecutive columns (16-byte stores where the destination allows it).
 constexpr int kEncWarps = 4;
 constexpr int kEncMaxWidth = 64;
 constexpr int kEncStride = kEncMaxWidth + 1;   // odd stride: conflict-free row-major writes by lane = row
 
 __global__ void __launch_bounds__(kEncWarps * 32)
-encode_kernel(const float* __restrict__ x, const int* __restrict__ count, int rows_cap, int n_freqs, float scale, Planes dst,
-              int col0, int zero_to, int fmt) {
+encode_kernel(const float* __restrict__ x, const int* __restrict__ count, int rows_cap, int n_freqs, Planes dst, Planes side,
+              int side_col0, float side_scale, int fmt) {
   __shared__ float s_v[kEncWarps][32 * kEncStride];
   int limit = rows_cap;
   if (count) limit = min(limit, *count);
   const int d_pe = 3 + 6 * n_freqs;
-  const int width = max(d_pe, zero_to);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* sv = s_v[warp];
-  const bool vec = ((col0 | dst.ld | width) & 7) == 0;
   const int n_groups = (limit + 31) / 32;
   for (int grp = blockIdx.x * kEncWarps + warp; grp < n_groups; grp += gridDim.x * kEncWarps) {
     const int row0 = grp * 32;
@@ -61,41 +62,41 @@ encode_kernel(const float* __restrict__ x, const int* __restrict__ count, int ro
       const float p[3] = {x[(size_t)row * 3 + 0], x[(size_t)row * 3 + 1], x[(size_t)row * 3 + 2]};
       float* o = sv + lane * kEncStride;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) o[c] = p[c] * scale;
+      for (int c = 0; c < 3; ++c) o[c] = p[c];
       for (int k = 0; k < n_freqs; ++k) {
         const float f = exp2f((float)k);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           float sn, cs;
           sincosf(p[c] * f, &sn, &cs);
-          o[3 + 6 * k + c] = sn * scale;
-          o[6 + 6 * k + c] = cs * scale;
+          o[3 + 6 * k + c] = sn;
+          o[6 + 6 * k + c] = cs;
         }
       }
-      for (int j = d_pe; j < width; ++j) o[j] = 0.f;
+      for (int j = d_pe; j < kEncMaxWidth; ++j) o[j] = 0.f;
     }
     __syncwarp();
     const int n_rows = min(32, limit - row0);
-    if (vec) {
-      const int per_row = width / 8;
-      for (int e = lane; e < n_rows * per_row; e += 32) {
-        const int r = e / per_row, c0 = (e % per_row) * 8;
-        const float* v = sv + r * kEncStride + c0;
-        uint32_t wh[4], wl[4];
+    // layer 0's input planes: whole 64-column rows, 16 bytes per store
+    for (int e = lane; e < n_rows * (kEncMaxWidth / 8); e += 32) {
+      const int r = e / (kEncMaxWidth / 8), c0 = (e % (kEncMaxWidth / 8)) * 8;
+      const float* v = sv + r * kEncStride + c0;
+      uint32_t wh[4], wl[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) split_pair(v[2 * q], v[2 * q + 1], fmt, wh[q], wl[q]);
-        const size_t off = (size_t)(row0 + r) * dst.ld + col0 + c0;
-        *reinterpret_cast<uint4*>(dst.hi + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-        *reinterpret_cast<uint4*>(dst.lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-      }
-    } else {
-      for (int e = lane; e < n_rows * width; e += 32) {
-        const int r = e / width, j = e % width;
+      for (int q = 0; q < 4; ++q) split_pair(v[2 * q], v[2 * q + 1], fmt, wh[q], wl[q]);
+      const size_t off = (size_t)(row0 + r) * dst.ld + c0;
+      *reinterpret_cast<uint4*>(dst.hi + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      *reinterpret_cast<uint4*>(dst.lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    }
+    // the skip layer's PE columns (d_pe of them, at an odd column offset): consecutive lanes on consecutive columns
+    if (side.hi != nullptr) {
+      for (int e = lane; e < n_rows * d_pe; e += 32) {
+        const int r = e / d_pe, j = e % d_pe;
         uint32_t wh, wl;
-        split_pair(sv[r * kEncStride + j], 0.f, fmt, wh, wl);
-        const size_t off = (size_t)(row0 + r) * dst.ld + col0 + j;
-        reinterpret_cast<unsigned short*>(dst.hi)[off] = (unsigned short)(wh & 0xFFFFu);
-        reinterpret_cast<unsigned short*>(dst.lo)[off] = (unsigned short)(wl & 0xFFFFu);
+        split_pair(sv[r * kEncStride + j] * side_scale, 0.f, fmt, wh, wl);
+        const size_t off = (size_t)(row0 + r) * side.ld + side_col0 + j;
+        reinterpret_cast<unsigned short*>(side.hi)[off] = (unsigned short)(wh & 0xFFFFu);
+        reinterpret_cast<unsigned short*>(side.lo)[off] = (unsigned short)(wl & 0xFFFFu);
       }
     }
     __syncwarp();
@@ -134,12 +135,24 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // fp16 split by default: the depth / shading parity with the reference rests on SDF values that agree with an fp32 evaluation
 // to a few 1e-7; NEFII_SDF_FORMAT=bf16 selects the wide-range format at load.
+// Where the positional encoding is computed: 0 = one encode_kernel launch per evaluation (default), 1 = inside layer 0's GEMM
+// ("PE prologue", mlp_gemm_kernel.cuh).  The prologue removes the launch and the in0 round trip but is SLOWER on B200: the 2 304
+// sincosf of a 128-row tile fall to the kernel's two idle warps, which are latency-bound on them (measured: 2^20 points 10.99 ms
+// against 9.39 ms, a latency-bound 4096-point evaluation 0.161 against 0.151 ms).  NEFII_SDF_PE_PROLOGUE=1.
+int env_pe_prologue() {
+  const char* e = getenv("NEFII_SDF_PE_PROLOGUE");
+  return (e && e[0] == '1') ? 1 : 0;
+}
+int g_pe_prologue = env_pe_prologue();
+
 int default_format() {
   const char* e = getenv("NEFII_SDF_FORMAT");
   return (e && (!strcmp(e, "bf16") || !strcmp(e, "0"))) ? PLANES_BF16 : PLANES_FP16;
 }
 
 }  // namespace
+
+int sdf_set_pe_prologue(int on) { g_pe_prologue = on ? 1 : 0; return NEFII_OK; }
 
 struct SdfNet::Impl {
   SdfConfig cfg;
@@ -264,15 +277,16 @@ int SdfNet::set_weights(cudaStream_t stream, const float* const* weights, const 
   return NEFII_OK;
 }
 
-// Workspace layout (all plane buffers hold hi then lo, [rows_cap, ld] bf16 each):
-//   in0 (ld 64) | act buffers (ld width): 2 when ping-ponging, n_hidden-1 + 2 when the gradient is needed
-//   | fp32 g0 [rows, 64] | fp32 g_skip [rows, 64]
+// Workspace layout (all plane buffers hold hi then lo, [rows_cap, width] 16-bit each):
+//   in0 (ld 64: the encoding, layer 0's input) | inference: two ping-pong activation buffers + the skip layer's input buffer (its
+//   PE half is written together with in0, its h half by layer skip - 1); with the gradient: one buffer per hidden layer + seed +
+//   spare | fp32 g0 [rows, 64] | g_skip [rows, 64]
 size_t SdfNet::workspace_bytes(int rows_cap, bool with_grad) const {
   const Impl& s = *impl_;
   const size_t rows = (size_t)round_up(rows_cap > 0 ? rows_cap : 1, 128);
   const size_t plane_w = rows * s.cfg.width * 2 * 2;
   const size_t plane_0 = rows * 64 * 2 * 2;
-  const int n_act = with_grad ? (s.cfg.n_hidden - 1) + 2 : 2;
+  const int n_act = with_grad ? (s.cfg.n_hidden - 1) + 2 : 3;
   size_t b = plane_0 + (size_t)n_act * plane_w;
   if (with_grad) b += 2 * rows * 64 * 4;
   return b + 1024;
@@ -298,7 +312,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
     return pl;
   };
   Planes in0 = planes(64);
-  const int n_act = with_grad ? (H - 1) + 2 : 2;
+  const int n_act = with_grad ? (H - 1) + 2 : 3;
   std::vector<Planes> act(n_act);
   for (int i = 0; i < n_act; ++i) act[i] = planes(W);
   float* g0 = nullptr;
@@ -307,13 +321,16 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
     g0 = (float*)p; p += rows * 64 * 4;
     g_skip = (float*)p; p += rows * 64 * 4;
   }
-  // input planes of hidden layer l (l >= 1)
-  auto in_of = [&](int l) -> Planes& { return with_grad ? act[l - 1] : act[(l - 1) & 1]; };
-
-  const int enc_blocks = kNumSMs * 6;
+  // input planes of hidden layer l (l >= 1); the skip layer's input has its own buffer in the ping-pong scheme
+  auto in_of = [&](int l) -> Planes& { return with_grad ? act[l - 1] : (l == skip ? act[2] : act[(l - 1) & 1]); };
   int rc;
-  encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, 1.f, in0, 0, 64, s.fmt);
-  NEFII_LAUNCH_CHECK();
+  const bool pe_prologue = g_pe_prologue != 0;
+  if (!pe_prologue) {
+    Planes side;
+    if (skip > 0) side = in_of(skip);
+    encode_kernel<<<kNumSMs * 6, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, in0, side, W - s.d_pe, kInvSqrt2, s.fmt);
+    NEFII_LAUNCH_CHECK();
+  }
 
   // ---------------------------------------------------------------- forward
   Planes seed;  // gradient seed G_{H-1}
@@ -325,8 +342,16 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
     GemmProblem g{};
     g.k_flush = k_flush;
     g.epi.fmt = s.fmt;
-    const Planes& a = (l == 0) ? in0 : in_of(l);
-    g.a_hi = a.hi; g.a_lo = a.lo; g.a_ld = a.ld; g.rows_cap = rows_cap;
+    g.rows_cap = rows_cap;
+    if (l == 0 && pe_prologue) {
+      // PE prologue: the encoding is computed inside the kernel; its 1/sqrt(2)-scaled copy goes next to the h columns of the
+      // skip layer's input (layer skip - 1 writes those later and leaves the PE columns alone)
+      g.pe.x = x; g.pe.n_freqs = s.cfg.n_freqs;
+      if (skip > 0) { g.pe.side = in_of(skip); g.pe.side_col0 = W - s.d_pe; g.pe.side_scale = kInvSqrt2; }
+    } else {
+      const Planes& a = (l == 0) ? in0 : in_of(l);
+      g.a_hi = a.hi; g.a_lo = a.lo; g.a_ld = a.ld;
+    }
     g.b_hi = s.w_fwd[l].hi; g.b_lo = s.w_fwd[l].lo; g.b_ld = s.w_fwd[l].ld; g.n_pad = s.n_pad[l];
     g.k_pad = s.k_pad[l];
     g.count = count;
@@ -338,7 +363,7 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
       g.epi.dst = in_of(l + 1);
       g.epi.dst_ncols = s.out_dim[l];
       g.epi.out_scale = (l + 1 == skip) ? kInvSqrt2 : 1.f;
-      g.epi.dst_pad_ok = (l + 1 == skip) ? 1 : 0;   // the PE columns next to h are written right after this layer
+      g.epi.dst_pad_ok = (l + 1 == skip) ? 1 : 0;   // the PE columns next to h are already there
     } else {
       g.epi.w_last = s.w_last; g.epi.b_last = s.b_last; g.epi.n_last = s.cfg.d_out; g.epi.w_last_ld = W;
       g.epi.dst_last = sdf;
@@ -358,11 +383,6 @@ int SdfNet::eval(cudaStream_t stream, int rows_cap, const int* count, const floa
       f.epi.mode = 0; f.epi.act = ACT_NONE; f.epi.n_valid = s.cfg.d_feat; f.epi.bias = s.b_feat;
       f.epi.dst_f32 = feat; f.epi.f32_ld = s.cfg.d_feat; f.epi.f32_begin = 0; f.epi.f32_end = s.cfg.d_feat;
       if ((rc = gemm_split_bf16(stream, f))) return rc;
-    }
-    if (l + 1 == skip) {
-      // the skip layer's input = [h / sqrt2 | PE / sqrt2]: the encoding goes next to the h columns the GEMM just wrote
-      encode_kernel<<<enc_blocks, kEncWarps * 32, 0, stream>>>(x, count, rows_cap, s.cfg.n_freqs, kInvSqrt2, in_of(skip), W - s.d_pe, 0, s.fmt);
-      NEFII_LAUNCH_CHECK();
     }
   }
   if (!with_grad) return NEFII_OK;

@@ -16,6 +16,9 @@ struct SdfConfig {
   int d_feat = 0;
 };
 
+// 1: the positional encoding is computed inside layer 0's GEMM (PE prologue); 0 (default): by one encode kernel per evaluation
+int sdf_set_pe_prologue(int on);
+
 class SdfNet {
  public:
   SdfNet();

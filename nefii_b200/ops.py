@@ -29,6 +29,8 @@ class GemmDesc(ctypes.Structure):
         ("sav_hi", c_void_p), ("sav_lo", c_void_p), ("sav_ld", c_int), ("sav_ncols", c_int), ("sav_scale", c_float),
         ("k_splits", c_int), ("f32_split_stride", ctypes.c_int64), ("k_splits_used", c_int),
         ("k_flush", c_int), ("dst_pad_ok", c_int), ("fmt", c_int),
+        ("pe_x", c_void_p), ("pe_n_freqs", c_int), ("pe_side_hi", c_void_p), ("pe_side_lo", c_void_p), ("pe_side_ld", c_int),
+        ("pe_side_col0", c_int), ("pe_side_scale", c_float),
     ]
 
 
@@ -62,12 +64,22 @@ def split_to_planes(src, rows_pad=None, cols_pad=None, transpose=False, scale=1.
 def gemm_split_bf16(a, b, k_pad, n_valid, *, mode=0, act=ACT_NONE, bias=None, out_scale=1.0, count=None,
                     dst=None, dst_col0=0, dst_ncols=0, dst_zero_to=0, dst_f32=None, f32_begin=0, f32_end=0, f32_ld=None,
                     w_last=None, b_last=None, dst_last=None, seed=None, sav=None, sav_ncols=0, sav_scale=1.0,
-                    k_splits=1, f32_split_stride=0, rows_cap=None, k_flush=0, fmt=None):
+                    k_splits=1, f32_split_stride=0, rows_cap=None, k_flush=0, fmt=None, dst_pad_ok=0,
+                    pe_x=None, pe_n_freqs=0, pe_side=None, pe_side_col0=0, pe_side_scale=1.0):
     """a=(hi,lo) activations planes [rows_cap, a_ld], b=(hi,lo) weight planes [n_pad, b_ld].  fmt: plane format of every
     plane of the launch (default: from the dtype of a)."""
     d = GemmDesc()
-    d.fmt = (PLANES_FP16 if a[0].dtype == torch.float16 else PLANES_BF16) if fmt is None else fmt
-    d.a_hi, d.a_lo, d.a_ld, d.rows_cap = _p(a[0]), _p(a[1]), a[0].stride(0), (a[0].shape[0] if rows_cap is None else rows_cap)
+    if pe_x is not None:
+        # PE prologue: a is None, the rows of A are the positional encoding of pe_x [rows, 3], computed inside the kernel
+        d.fmt = (PLANES_FP16 if b[0].dtype == torch.float16 else PLANES_BF16) if fmt is None else fmt
+        d.pe_x, d.pe_n_freqs = _p(pe_x), pe_n_freqs
+        d.rows_cap = pe_x.shape[0] if rows_cap is None else rows_cap
+        if pe_side is not None:
+            d.pe_side_hi, d.pe_side_lo, d.pe_side_ld = _p(pe_side[0]), _p(pe_side[1]), pe_side[0].stride(0)
+            d.pe_side_col0, d.pe_side_scale = pe_side_col0, pe_side_scale
+    else:
+        d.fmt = (PLANES_FP16 if a[0].dtype == torch.float16 else PLANES_BF16) if fmt is None else fmt
+        d.a_hi, d.a_lo, d.a_ld, d.rows_cap = _p(a[0]), _p(a[1]), a[0].stride(0), (a[0].shape[0] if rows_cap is None else rows_cap)
     d.b_hi, d.b_lo, d.b_ld, d.n_pad = _p(b[0]), _p(b[1]), b[0].stride(0), b[0].shape[0]
     d.k_pad = k_pad
     d.count = _p(count)
@@ -90,7 +102,8 @@ def gemm_split_bf16(a, b, k_pad, n_valid, *, mode=0, act=ACT_NONE, bias=None, ou
         d.sav_ncols, d.sav_scale = sav_ncols, sav_scale
     d.k_splits, d.f32_split_stride = k_splits, f32_split_stride
     d.k_flush = k_flush
-    _lib.check(_lib.raw().nefii_gemm_split_bf16(_lib.stream_ptr(a[0].device), ctypes.byref(d)))
+    d.dst_pad_ok = dst_pad_ok
+    _lib.check(_lib.raw().nefii_gemm_split_bf16(_lib.stream_ptr(b[0].device), ctypes.byref(d)))
     return d.k_splits_used
 
 

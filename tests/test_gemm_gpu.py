@@ -133,3 +133,29 @@ def test_both_kernel_instantiations_and_partial_lengths(cuda_device, cluster, k_
         _lib.check(lib.nefii_gemm_set_k_flush(4))
     err = (_planes_to_f32(dst).double() - ref).abs().max().item()
     assert err < 4e-5 * max(ref.abs().max().item(), 1.0), err
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("rows", [1, 127, 300, 5000])
+def test_pe_prologue_equals_encoded_planes(cuda_device, rows, fmt):
+    """The "PE prologue" (positional encoding computed inside the kernel, straight into the swizzled operand tile) gives the
+    same bits as the product on planes that hold the encoding; its side copy lands in the requested plane columns only."""
+    from nefii_b200 import mlp, ops
+    dev = cuda_device
+    torch.manual_seed(rows)
+    x = torch.rand(rows, 3, device=dev) * 2 - 1
+    w = torch.randn(512, 39, device=dev) / 6
+    enc = mlp.encode_segments([(x, 6)])
+    a = ops.split_to_planes(enc, cols_pad=64, fmt=fmt)
+    b = ops.split_to_planes(w, rows_pad=512, cols_pad=64, fmt=fmt)
+    o1 = torch.zeros(rows, 512, device=dev)
+    o2 = torch.zeros(rows, 512, device=dev)
+    ops.gemm_split_bf16(a, b, 64, 512, dst_f32=o1, f32_begin=0, f32_end=512)
+    pdt = torch.float16 if fmt else torch.bfloat16
+    side = (torch.zeros(rows, 512, device=dev, dtype=pdt), torch.zeros(rows, 512, device=dev, dtype=pdt))
+    ops.gemm_split_bf16(None, b, 64, 512, dst_f32=o2, f32_begin=0, f32_end=512, pe_x=x, pe_n_freqs=6, pe_side=side, pe_side_col0=473,
+                        pe_side_scale=0.5)
+    assert torch.equal(o1, o2)
+    got = (side[0].float() + side[1].float())
+    assert (got[:, 473:] - enc * 0.5).abs().max().item() < (1e-7 if fmt else 4e-6)
+    assert got[:, :473].abs().max().item() == 0

@@ -97,3 +97,25 @@ def test_neus_layout_width_256_features_from_last_linear(cuda_device):
     assert (out[:, 1:].double() - ref[:, 1:]).abs().max().item() < 1e-4
     rel = (g.double() - g_ref).norm(dim=-1) / g_ref.norm(dim=-1)
     assert rel.kthvalue(int(0.99 * rel.numel()))[0].item() < 5e-4
+
+
+@pytest.mark.parametrize("n", [127, 4096, 20001])
+def test_pe_prologue_mode_is_bit_identical(cuda_device, n):
+    """nefii_sdf_set_pe_prologue(1): the encoding computed inside layer 0's GEMM instead of by the encode kernel -- same SDF,
+    features and gradient bits (the option is kept for its measurements; the default is the faster encode kernel)."""
+    from nefii_b200 import _lib
+    dev = cuda_device
+    params = mlp.sdf_init(seed=1, bumps=0.3)
+    net = _net(dev, params)
+    x = (torch.rand(n, 3, generator=torch.Generator().manual_seed(n)) * 1.8 - 0.9).to(dev)
+    a = net.eval(x, want_feat=True, want_grad=True)
+    a0 = net.eval(x)[0]
+    _lib.check(_lib.raw().nefii_sdf_set_pe_prologue(1))
+    try:
+        b = net.eval(x, want_feat=True, want_grad=True)
+        b0 = net.eval(x)[0]
+    finally:
+        _lib.check(_lib.raw().nefii_sdf_set_pe_prologue(0))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    assert torch.equal(a0, b0)
