@@ -218,7 +218,11 @@ int nefii_trace_set_tiers(int march_flush, int bulk_flush);
 /* 0: fixed launch schedule (every loop unrolled to its worst case, empty rounds exit at once); 1: CUDA graph with
  * conditional WHILE nodes (default; NEFII_TRACE_GRAPH=0 selects the fixed schedule at load) */
 int nefii_trace_set_graph_mode(int mode);
-/* bisection rounds apply D iterations of the reference's loop at once while few rays are refined: the whole binary tree of
+/* Speculative rounds while few rays are in flight (a round is then latency-bound: 8 dependent layer GEMMs on a handful of row
+ * tiles).  Sphere tracing: a ray that starts an iteration also asks for the SDF at the positions its line search would step back
+ * to (1 + line_step_iters points per marching end), so the next round runs the whole iteration; used while
+ * (1 + line_step_iters) * (ends in flight) <= rows.  Bisection:
+ * bisection rounds apply D iterations of the reference's loop at once while few rays are refined: the whole binary tree of
  * mid-points that D iterations can visit is evaluated in one round ((2^D - 1) n rows instead of n, bit-identical results,
  * 1 / D of the latency-bound rounds); D = the largest depth <= max depth with (2^D - 1) * n_root <= rows, decided on the
  * device.  rows = 0 switches it off (default 12288; NEFII_TRACE_QUAD_ROWS at load); max depth 1..4 (default 4;

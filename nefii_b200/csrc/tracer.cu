@@ -48,6 +48,8 @@ struct Ctrl {
   int bis_depth;     // bisection iterations applied per round (1..kMaxBisDepth; > 1 while few rays are refined)
   int bis_rewalk;    // -1, or the number of iterations of the LAST round that the reference executes (< bis_depth)
   int spec_work[4];  // OR of the surviving work bits after each of a round's iterations
+  int march_spec;    // the requests in flight carry the line-search points of their step too (few rays: latency-bound rounds)
+  int ends_acc, march_ends;   // marching ends that asked for a value: being counted / in the round in flight
   long long evals;   // SDF point evaluations (stats)
 };
 
@@ -126,11 +128,22 @@ __device__ __forceinline__ void emit_point(const RayState& S, int slot, const fl
 // One round of the march.  first = 1: ray set-up (bounding-sphere intersection, both ends ask for their first SDF value);
 // first = 0: consume the values of the previous request, run the ray's state machine, emit the next request.
 // The last CTA publishes the request count (Ctrl::cnt_eval) and drives the WHILE node of the graph.
+// Speculative line search (few requests in flight: a round is latency-bound -- 8 dependent layer GEMMs on a handful of row
+// tiles): a ray that starts a new iteration asks for the SDF at its new position AND at the ls_iters positions the line search
+// would step back to (ray_tracing.py:170-188: back by (1 - line_search_step) / 2^j of the step, one after the other), computed
+// with the very operations march_advance applies.  The next round then runs the whole iteration -- step, up to ls_iters
+// back-offs, head of the next iteration -- from values that are already there: same results, one round per iteration instead of
+// one per evaluation.  Decided on the device per round from the previous round's request count (requests never increase).
+constexpr int kMaxLineSearch = 3;
+
 __global__ void __launch_bounds__(kBlock)
-march_round_kernel(RayState S, int first, float radius, float thr, float back0, int ls_iters, int max_iters,
+march_round_kernel(RayState S, int first, float radius, float thr, float back0, int ls_iters, int max_iters, int spec_rows,
                    unsigned long long cond) {
   Ctrl* C = S.ctrl;
   if (!first && C->cnt_eval == 0) return;   // nothing was asked for: every ray has left the march (uniform over the grid)
+  const int spec_in = first ? 0 : C->march_spec;                                  // mode of the requests being consumed
+  const int n_spec = 1 + ls_iters;                                                // values per speculative request
+  const int spec_out = (!first && ls_iters >= 1 && ls_iters <= kMaxLineSearch && (long long)C->march_ends * n_spec <= spec_rows) ? 1 : 0;
   const int r = blockIdx.x * kBlock + threadIdx.x;
   const bool live = r < S.n_rays;
   float o[3] = {0, 0, 0}, d[3] = {0, 0, 0};
@@ -154,19 +167,44 @@ march_round_kernel(RayState S, int first, float radius, float thr, float back0, 
         m.acc_s = S.acc_s[r]; m.acc_e = S.acc_e[r]; m.cur_s = S.cur_s[r]; m.cur_e = S.cur_e[r];
         m.nxt_s = S.nxt_s[r]; m.nxt_e = S.nxt_e[r];
         m.iter = S.iter[r]; m.ls = S.ls[r];
-        if (m.flags & F_PEND_S) m.nxt_s = S.req_sdf[S.slot_s[r]];
-        if (m.flags & F_PEND_E) m.nxt_e = S.req_sdf[S.slot_e[r]];
+        const int base_s = S.slot_s[r], base_e = S.slot_e[r];
+        // a request made at the start of an iteration (ls == 0, iter > 0) in speculative mode carries the back-off points
+        const bool have_ls = spec_in && m.ls == 0 && m.iter > 0;
+        if (m.flags & F_PEND_S) m.nxt_s = S.req_sdf[base_s];
+        if (m.flags & F_PEND_E) m.nxt_e = S.req_sdf[base_e];
         m.flags &= ~(F_PEND_S | F_PEND_E);
         req = march_advance(m, thr, back0, ls_iters, max_iters);
+        while (have_ls && req != 0 && m.ls > 0) {      // a line-search step whose value is already here: level m.ls
+          if (req & REQ_S) m.nxt_s = S.req_sdf[base_s + m.ls];
+          if (req & REQ_E) m.nxt_e = S.req_sdf[base_e + m.ls];
+          req = march_advance(m, thr, back0, ls_iters, max_iters);
+        }
         touched = true;
       }
     }
   }
-  const int n_req = ((req & REQ_S) ? 1 : 0) + ((req & REQ_E) ? 1 : 0);
+  // points per requesting end: the position itself, plus (speculative mode, start of an iteration) its back-off positions
+  const int per_end = (spec_out && req != 0 && m.ls == 0 && m.iter > 0) ? n_spec : 1;
+  const int n_ends = ((req & REQ_S) ? 1 : 0) + ((req & REQ_E) ? 1 : 0);
+  const int n_req = n_ends * per_end;
   int slot = reserve_slots(n_req, &C->cnt_acc);
+  {
+    const int block_ends = __syncthreads_count(n_ends >= 1) + __syncthreads_count(n_ends >= 2);
+    if (threadIdx.x == 0 && block_ends) atomicAdd(&C->ends_acc, block_ends);
+  }
   if (touched) {
-    if (req & REQ_S) { emit_point(S, slot, o, m.acc_s, d); S.slot_s[r] = slot; m.flags |= F_PEND_S; ++slot; }
-    if (req & REQ_E) { emit_point(S, slot, o, m.acc_e, d); S.slot_e[r] = slot; m.flags |= F_PEND_E; }
+    if (req & REQ_S) {
+      float t = m.acc_s;
+      emit_point(S, slot, o, t, d);
+      for (int j = 1; j < per_end; ++j) { t = t - ldexpf(back0, -(j - 1)) * m.cur_s; emit_point(S, slot + j, o, t, d); }
+      S.slot_s[r] = slot; m.flags |= F_PEND_S; slot += per_end;
+    }
+    if (req & REQ_E) {
+      float t = m.acc_e;
+      emit_point(S, slot, o, t, d);
+      for (int j = 1; j < per_end; ++j) { t = t + ldexpf(back0, -(j - 1)) * m.cur_e; emit_point(S, slot + j, o, t, d); }
+      S.slot_e[r] = slot; m.flags |= F_PEND_E;
+    }
     S.flags[r] = m.flags; S.iter[r] = m.iter; S.ls[r] = m.ls;
     S.acc_s[r] = m.acc_s; S.acc_e[r] = m.acc_e; S.cur_s[r] = m.cur_s; S.cur_e[r] = m.cur_e;
     S.nxt_s[r] = m.nxt_s; S.nxt_e[r] = m.nxt_e;
@@ -176,6 +214,9 @@ march_round_kernel(RayState S, int first, float radius, float thr, float back0, 
     C->cnt_acc = 0;
     C->cnt_eval = n;
     C->evals += n;
+    C->march_spec = spec_out;
+    C->march_ends = *(volatile int*)&C->ends_acc;
+    C->ends_acc = 0;
     if (n > 0) C->rounds += 1;
     set_cond(cond, n > 0);
   }
@@ -674,14 +715,16 @@ int ray_trace_enqueue(cudaStream_t stream, const TraceConfig& cfg, const SdfSour
 
   // ---- sphere tracing --------------------------------------------------------------------------------------------
   unsigned long long h_march = next_cond();
+  // row budget of the speculative rounds (line search here, bisection below); 0 = off
+  const int spec_rows = std::min(g_bisect_quad_rows, L.cap_pts);
   march_round_kernel<<<grid, kBlock, 0, stream>>>(S, 1, cfg.radius, cfg.sdf_threshold, back0, cfg.line_step_iters,
-                                                  cfg.sphere_tracing_iters, h_march);
+                                                  cfg.sphere_tracing_iters, spec_rows, h_march);
   NEFII_LAUNCH_CHECK();
   if ((rc = loop(trace_max_rounds(cfg), [&](cudaStream_t st, unsigned long long h) -> int {
         int rc2;
-        if ((rc2 = eval(st, std::min(2 * R, L.cap_pts), tiers.march_flush))) return rc2;
+        if ((rc2 = eval(st, std::min(std::max(2 * R, spec_rows), L.cap_pts), tiers.march_flush))) return rc2;
         march_round_kernel<<<grid, kBlock, 0, st>>>(S, 0, cfg.radius, cfg.sdf_threshold, back0, cfg.line_step_iters,
-                                                    cfg.sphere_tracing_iters, h);
+                                                    cfg.sphere_tracing_iters, spec_rows, h);
         NEFII_LAUNCH_CHECK();
         return NEFII_OK;
       })))
@@ -710,7 +753,6 @@ int ray_trace_enqueue(cudaStream_t stream, const TraceConfig& cfg, const SdfSour
   unsigned long long h_bis = next_cond();
   // up to g_bisect_max_depth iterations per round while the candidate tree still fits a latency-bound evaluation (decided on
   // the device from n_root)
-  const int spec_rows = std::min(g_bisect_quad_rows, L.cap_pts);
   const int max_depth = spec_rows > 0 ? g_bisect_max_depth : 1;
   bisect_kernel<<<grid, kBlock, 0, stream>>>(S, BIS_INIT, cfg.n_rootfind_steps, spec_rows, max_depth, h_bis);
   NEFII_LAUNCH_CHECK();
