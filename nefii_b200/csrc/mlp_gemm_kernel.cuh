@@ -349,9 +349,12 @@ struct FastStore {
 };
 
 // KEEP: the span's last real column (keep_from) is not on a 16-byte boundary (a separate instance: the common one stays lean)
-template <int ACT, bool TMA, bool KEEP = false>
+// FMT: the plane format as a compile-time constant -- the caller branches once per span, so that each instance is straight-line
+// code (a run-time format test inside the unrolled conversion groups doubles the instruction footprint of the hot loop).
+template <int ACT, bool TMA, int FMT, bool KEEP = false>
 __device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bias4, int n_span0, float scale, const FastStore& fs, int dbg,
-                                                 int fmt, int keep_from = -1, const uint4* keep_hi = nullptr, const uint4* keep_lo = nullptr) {
+                                                 int keep_from = -1, const uint4* keep_hi = nullptr, const uint4* keep_lo = nullptr) {
+  constexpr int fmt = FMT;
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int c = 0; c < kColsPerWarp / 32; ++c) {
@@ -430,9 +433,10 @@ __device__ __forceinline__ void finish_span_fast(float* acc, const float4* s_bia
 // Fast path of the data-gradient layers (MODE 1) on whole 32-row tiles whose column span is entirely real: the products are
 // scaled by the activation derivative recovered from the saved forward output (read as this lane's row, 16 bytes at a time) and
 // leave as bf16 planes through the same staged bulk tensor stores as the forward path; no per-element predicates.
-template <int ACT>
+template <int ACT, int FMT>
 __device__ __forceinline__ void finish_span_bwd_fast(float* acc, const __nv_bfloat16* sav_hi_row, const __nv_bfloat16* sav_lo_row,
-                                                     float sav_scale, int n_span0, float scale, const FastStore& fs, int fmt) {
+                                                     float sav_scale, int n_span0, float scale, const FastStore& fs) {
+  constexpr int fmt = FMT;
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int c = 0; c < kColsPerWarp / 32; ++c) {
@@ -966,23 +970,34 @@ gemm_split_bf16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       const bool whole_rows = store_tma && row - lane + 32 <= m_limit;
       if (fast_layer && n_span0 + kColsPerWarp <= n_fast && (whole_rows || n_span0 + kColsPerWarp <= n_real)) {
         // whole 32-row tiles leave by bulk tensor store; the ragged last tile keeps per-row predicates
+        const float4* sb4 = reinterpret_cast<const float4*>(s_bias);
         if (whole_rows) {
           // a ragged span (dst_pad_ok) whose last real column is not on a 16-byte boundary: see finish_span_fast
-          if (n_span0 + kColsPerWarp > n_real && (n_real & 7) != 0)
-            finish_span_fast<ACT, true, true>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg, epi.fmt, n_real,
-                                              reinterpret_cast<const uint4*>(epi.dst.hi + row * epi.dst.ld + epi.dst_col0),
-                                              reinterpret_cast<const uint4*>(epi.dst.lo + row * epi.dst.ld + epi.dst_col0));
-          else
-            finish_span_fast<ACT, true>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg, epi.fmt);
+          if (n_span0 + kColsPerWarp > n_real && (n_real & 7) != 0) {
+            const uint4* kh = reinterpret_cast<const uint4*>(epi.dst.hi + row * epi.dst.ld + epi.dst_col0);
+            const uint4* kl = reinterpret_cast<const uint4*>(epi.dst.lo + row * epi.dst.ld + epi.dst_col0);
+            if (epi.fmt == PLANES_FP16) finish_span_fast<ACT, true, PLANES_FP16, true>(acc, sb4, n_span0, epi.out_scale, fs, dbg, n_real, kh, kl);
+            else finish_span_fast<ACT, true, PLANES_BF16, true>(acc, sb4, n_span0, epi.out_scale, fs, dbg, n_real, kh, kl);
+          } else if (epi.fmt == PLANES_FP16) {
+            finish_span_fast<ACT, true, PLANES_FP16>(acc, sb4, n_span0, epi.out_scale, fs, dbg);
+          } else {
+            finish_span_fast<ACT, true, PLANES_BF16>(acc, sb4, n_span0, epi.out_scale, fs, dbg);
+          }
+        } else if (epi.fmt == PLANES_FP16) {
+          finish_span_fast<ACT, false, PLANES_FP16>(acc, sb4, n_span0, epi.out_scale, fs, dbg);
+        } else {
+          finish_span_fast<ACT, false, PLANES_BF16>(acc, sb4, n_span0, epi.out_scale, fs, dbg);
         }
-        else
-          finish_span_fast<ACT, false>(acc, reinterpret_cast<const float4*>(s_bias), n_span0, epi.out_scale, fs, dbg, epi.fmt);
         continue;
       }
       if (fast_bwd && row - lane + 32 <= m_limit && n_span0 + kColsPerWarp <= epi.n_valid && n_span0 + kColsPerWarp <= epi.dst_ncols &&
           n_span0 + kColsPerWarp <= epi.sav_ncols) {
-        finish_span_bwd_fast<ACT>(acc, epi.sav_hi + row * epi.sav_ld, epi.sav_lo + row * epi.sav_ld, epi.sav_scale, n_span0,
-                                  epi.out_scale, fs, epi.fmt);
+        if (epi.fmt == PLANES_FP16)
+          finish_span_bwd_fast<ACT, PLANES_FP16>(acc, epi.sav_hi + row * epi.sav_ld, epi.sav_lo + row * epi.sav_ld, epi.sav_scale, n_span0,
+                                                 epi.out_scale, fs);
+        else
+          finish_span_bwd_fast<ACT, PLANES_BF16>(acc, epi.sav_hi + row * epi.sav_ld, epi.sav_lo + row * epi.sav_ld, epi.sav_scale, n_span0,
+                                                 epi.out_scale, fs);
         continue;
       }
       if (fast_fused && n_span0 + kColsPerWarp <= epi.n_valid) {

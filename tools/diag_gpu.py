@@ -197,12 +197,14 @@ def diag_gemmprof():
     from nefii_b200 import ops
     dev = torch.device("cuda:0")
     rows, k, n = 131072, 512, 512
+    fmt = int(os.environ.get("DIAG_FMT", "1"))       # the SDF network's default plane format (fp16 split)
     x = torch.randn(rows, k, device=dev) * 0.3
     w = torch.randn(n, k, device=dev) / k ** 0.5
     bias = torch.zeros(n, device=dev)
-    a = ops.split_to_planes(x)
-    b = ops.split_to_planes(w)
-    dst = (torch.empty(rows, n, device=dev, dtype=torch.bfloat16), torch.empty(rows, n, device=dev, dtype=torch.bfloat16))
+    a = ops.split_to_planes(x, fmt=fmt)
+    b = ops.split_to_planes(w, fmt=fmt)
+    pdt = torch.float16 if fmt else torch.bfloat16
+    dst = (torch.empty(rows, n, device=dev, dtype=pdt), torch.empty(rows, n, device=dev, dtype=pdt))
     from nefii_b200 import _lib
     _lib.check(_lib.raw().nefii_gemm_set_debug(int(os.environ.get("GEMM_DEBUG", "0"))))     # ablation mask for A/B captures
     for _ in range(8):
