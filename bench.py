@@ -354,7 +354,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 (MLPs: bf16x3 split on tcgen05, fp32 accumulate)", "data": "synthetic",
+            "dtype": "f32 (MLPs: 3 MMAs per fp32 product on 16-bit hi/lo planes, fp32 accumulate: fp16 split for the SDF network, bf16 split for the trainable stacks)", "data": "synthetic",
             "config": {"workload": "step-2 training iteration (BASELINE configs[2]): ONE global batch of num_pixels=2048 x num_rays=64 = "
                                    "131072 primary rays + 3 secondary rays per hit, its 512 2x2 patches dealt to the ranks (patch p -> "
                                    "rank p %% N), 128 SGs, 8x512 SDF MLP frozen, fwd+loss+bwd+Adam",
@@ -707,7 +707,7 @@ def fitted_scene(dev, step, dev_batches):
 # --------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle port) on the host cores
 # --------------------------------------------------------------------------------------------------------------
-NCU_DRAM_BYTES_PER_ROW = 3813.0      # profiles/r2_gemm_ncu.md
+NCU_DRAM_BYTES_PER_ROW = 3831.0      # profiles/r2_gemm_ncu.md (502.1 MB per 131 072-row launch)
 
 
 def idr_loss_cpu(out, rgb_gt):
