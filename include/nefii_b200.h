@@ -218,6 +218,7 @@ int nefii_trace_set_tiers(int march_flush, int bulk_flush);
 /* 0: fixed launch schedule (every loop unrolled to its worst case, empty rounds exit at once); 1: CUDA graph with
  * conditional WHILE nodes (default; NEFII_TRACE_GRAPH=0 selects the fixed schedule at load) */
 int nefii_trace_set_graph_mode(int mode);
+int nefii_trace_graph_mode(void);   /* the mode in force */
 /* Speculative rounds while few rays are in flight (a round is then latency-bound: 8 dependent layer GEMMs on a handful of row
  * tiles).  Sphere tracing: a ray that starts an iteration also asks for the SDF at the positions its line search would step back
  * to (1 + line_step_iters points per marching end), so the next round runs the whole iteration; used while

@@ -48,6 +48,7 @@ SIGNATURES = {
                         c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p],
     "nefii_trace_set_tiers": [c_int, c_int],
     "nefii_trace_set_graph_mode": [c_int],
+    "nefii_trace_graph_mode": [],
     "nefii_trace_set_quad_rows": [c_int],
     "nefii_trace_set_bisect_depth": [c_int],
     "nefii_trace_graph_clear": [],

@@ -147,6 +147,26 @@ class RayTracing(nn.Module):
         self._shape_bufs[key] = b                                      # most recently used last
         return b
 
+    def _fill_missing_rays(self, bufs, batch_size, n_rays, dev):
+        """rays [batch_size:] of a bucket start far outside the bounding sphere and point away from it"""
+        far = 4.0 * float(self.object_bounding_sphere) + 1.0
+        bufs.cam[batch_size:] = torch.tensor([0.0, 0.0, far], device=dev)
+        bufs.dirs[batch_size:] = torch.tensor([0.0, 1.0, 0.0], device=dev)
+        bufs.obj[n_rays:].zero_()
+
+    def _launch(self, bufs, kind, ptr, n_prims, cap_batch, num_pixels, have_mask, flags, have_uniforms, dev, stats):
+        key = (self.n_steps, dev)
+        if key not in self._linspace:
+            self._linspace[key] = torch.linspace(0, 1, steps=self.n_steps).to(dev)   # CPU linspace, as the reference
+        lin = self._linspace[key]
+        cfg = self._config()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.raw().nefii_ray_trace(
+                _lib.stream_ptr(dev), ctypes.byref(cfg), kind, c_void_p(ptr), n_prims, cap_batch, num_pixels,
+                bufs.cam.data_ptr(), bufs.dirs.data_ptr(), bufs.obj.data_ptr() if have_mask else None, flags,
+                lin.data_ptr(), bufs.uniforms.data_ptr() if have_uniforms else None,
+                self._ws.data_ptr(), self._ws.numel(), bufs.points.data_ptr(), bufs.hit.data_ptr(), bufs.dists.data_ptr(), stats))
+
     def forward(self, sdf, cam_loc, object_mask, ray_directions, uniforms=None, skip_min_sdf=None):
         kind, ptr, n_prims, keep = resolve_sdf_source(sdf)
         dev = ray_directions.device
@@ -158,16 +178,15 @@ class RayTracing(nn.Module):
             return (torch.empty(0, 3, device=dev), torch.empty(0, dtype=torch.bool, device=dev), torch.empty(0, device=dev))
         # secondary-style rays: pad the batch to a bucket with rays that miss the bounding sphere
         cap_batch = batch_size
-        if num_pixels == 1 and batch_size > 1:
+        bucketed = num_pixels == 1 and batch_size > 1
+        if bucketed:
             cap_batch = (batch_size + self.RAY_BUCKET - 1) // self.RAY_BUCKET * self.RAY_BUCKET
+        new_shape = (dev, cap_batch, num_pixels) not in self._shape_bufs
         bufs = self._shape_buffers(dev, cap_batch, num_pixels)
         bufs.cam[:batch_size].copy_(cam_loc.detach().reshape(batch_size, 3))
         bufs.dirs[:batch_size].copy_(ray_directions.detach())
         if cap_batch > batch_size:
-            far = 4.0 * float(self.object_bounding_sphere) + 1.0
-            bufs.cam[batch_size:] = torch.tensor([0.0, 0.0, far], device=dev)
-            bufs.dirs[batch_size:] = torch.tensor([0.0, 1.0, 0.0], device=dev)
-            bufs.obj[n_rays:].zero_()
+            self._fill_missing_rays(bufs, batch_size, n_rays, dev)
         have_mask = object_mask is not None
         if have_mask:
             bufs.obj[:n_rays].copy_(object_mask.reshape(-1))
@@ -184,24 +203,29 @@ class RayTracing(nn.Module):
         if uniforms is not None:
             bufs.uniforms.copy_(uniforms.detach().reshape(-1), non_blocking=True)
             have_uniforms = True
-        key = (self.n_steps, dev)
-        if key not in self._linspace:
-            self._linspace[key] = torch.linspace(0, 1, steps=self.n_steps).to(dev)   # CPU linspace, as the reference
-        lin = self._linspace[key]
-        cfg = self._config()
-        lib = _lib.raw()
+        # the workspace is shared by every shape and its pointer is part of the graph key: size it for the next bucket too, so that a
+        # slowly growing ray count does not invalidate the graphs that exist
         n_cap = cap_batch * num_pixels
-        need = int(lib.nefii_trace_workspace_bytes(kind, c_void_p(ptr), n_cap, self.n_steps))
+        grow = (cap_batch + self.RAY_BUCKET) * num_pixels if bucketed else n_cap
+        lib = _lib.raw()
+        need = int(lib.nefii_trace_workspace_bytes(kind, c_void_p(ptr), grow, self.n_steps))
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         stats = (ctypes.c_int64 * 8)() if self.collect_stats else None
-        with torch.cuda.device(dev):
-            _lib.check(lib.nefii_ray_trace(
-                _lib.stream_ptr(dev), ctypes.byref(cfg), kind, c_void_p(ptr), n_prims, cap_batch, num_pixels,
-                bufs.cam.data_ptr(), bufs.dirs.data_ptr(), bufs.obj.data_ptr() if have_mask else None, flags,
-                lin.data_ptr(), bufs.uniforms.data_ptr() if have_uniforms else None,
-                self._ws.data_ptr(), self._ws.numel(), bufs.points.data_ptr(), bufs.hit.data_ptr(), bufs.dists.data_ptr(), stats))
+        self._launch(bufs, kind, ptr, n_prims, cap_batch, num_pixels, have_mask, flags, have_uniforms, dev, stats)
+        if bucketed and new_shape and _lib.raw().nefii_trace_graph_mode() == 1:
+            # A ray count that hovers around a bucket boundary alternates between two shapes: capture the neighbours' graphs now (one
+            # trace of rays that all miss the sphere: no SDF evaluation runs), not in the middle of somebody's timed loop.
+            for nb in (cap_batch + self.RAY_BUCKET, cap_batch - self.RAY_BUCKET):
+                if nb <= 0 or (dev, nb, num_pixels) in self._shape_bufs:
+                    continue
+                wb = self._shape_buffers(dev, nb, num_pixels)
+                self._fill_missing_rays(wb, 0, 0, dev)
+                if have_uniforms:
+                    wb.uniforms.copy_(bufs.uniforms)
+                self._launch(wb, kind, ptr, n_prims, nb, num_pixels, have_mask, flags, have_uniforms, dev, None)
+            self._shape_bufs[(dev, cap_batch, num_pixels)] = self._shape_bufs.pop((dev, cap_batch, num_pixels))    # most recent again
         if stats is not None:
             self.last_stats = dict(n_sampler=stats[0], n_rootfind=stats[1], n_min_sdf=stats[2], n_evals=stats[3],
                                    n_rounds=stats[4])
