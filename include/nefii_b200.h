@@ -47,13 +47,13 @@ int nefii_sg_render_fwd(void* stream, int n_rays, int n_sg, int n_mat,
  * g_diffuse: upstream gradients [N,3] (any may be NULL).  ACCUMULATED outputs (zero them first): g_lgt_acc [M,7] in the unit
  * parametrisation (convert with nefii_sg_param_grad, eps 1e-6), g_roughness [K], g_specular_refl [K,3]; written: g_albedo [N,3]
  * and, when not NULL, g_normal [N,3] (gradient w.r.t. the `normal` input as given, i.e. after the caller's normalisation).
- * Hand-derived adjoint of the closed-form SG integrals (csrc/sg_adjoint_math.cuh).  View directions carry no gradient;
- * blending weights (K > 1 with per-point weights) are not differentiated. */
+ * blending: the forward's per-point weights [N,K] or NULL; g_blending [N,K] (written) or NULL.
+ * Hand-derived adjoint of the closed-form SG integrals (csrc/sg_adjoint_math.cuh).  View directions carry no gradient. */
 int nefii_sg_render_bwd(void* stream, int n_rays, int n_sg, int n_mat, const float* lgt_sgs, const float* specular,
                         const float* roughness, const float* albedo, const float* normal, const float* view,
                         const float* out_specular, const float* out_diffuse, const float* g_rgb, const float* g_specular,
                         const float* g_diffuse, float* g_lgt_acc, float* g_roughness, float* g_specular_refl, float* g_albedo,
-                        float* g_normal);
+                        float* g_normal, const float* blending, float* g_blending);
 
 /* Environment radiance along miss rays -- replaces IDRNetwork.get_background_rgb (light_type 'sg'),
  * code/model/implicit_differentiable_renderer.py:646-663 + sg_fn path_tracing_render.py:404-413. */

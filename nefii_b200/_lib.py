@@ -18,7 +18,7 @@ SIGNATURES = {
     "nefii_abi_version": [],
     "nefii_launch_count": [],
     "nefii_sg_render_fwd": [c_void_p, c_int, c_int, c_int] + [c_void_p] * 10,
-    "nefii_sg_render_bwd": [c_void_p, c_int, c_int, c_int] + [c_void_p] * 16,
+    "nefii_sg_render_bwd": [c_void_p, c_int, c_int, c_int] + [c_void_p] * 18,
     "nefii_background_sg_fwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "nefii_gemm_split_bf16": [c_void_p, c_void_p],
     "nefii_probe_fp32": [c_void_p, c_int, c_int, c_void_p],

@@ -33,7 +33,8 @@ int sg_render_fwd(cudaStream_t, int, int, int, const float*, const float*, const
                   const float*, const float*, float*, float*, float*);
 int background_sg_fwd(cudaStream_t, int, int, const float*, const float*, float*);
 int sg_render_bwd(cudaStream_t, int, int, int, const float*, const float*, const float*, const float*, const float*, const float*,
-                  const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*, float*);
+                  const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
+                  float*, float*);
 int mis_sample(cudaStream_t, int, int, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*);
 int mis_shade_fwd(cudaStream_t, int, int, const float*, const float*, int, const float*, const float*, const float*, const float*,
                   const float*, const float*, const float*, const unsigned char*, const float*, float*, float*, float*, float*);
@@ -271,10 +272,10 @@ int nefii_sg_render_bwd(void* stream, int n_rays, int n_sg, int n_mat, const flo
                         const float* roughness, const float* albedo, const float* normal, const float* view,
                         const float* out_specular, const float* out_diffuse, const float* g_rgb, const float* g_specular,
                         const float* g_diffuse, float* g_lgt_acc, float* g_roughness, float* g_specular_refl, float* g_albedo,
-                        float* g_normal) {
+                        float* g_normal, const float* blending, float* g_blending) {
   return nefii::sg_render_bwd((cudaStream_t)stream, n_rays, n_sg, n_mat, lgt_sgs, specular, roughness, albedo, normal, view,
-                              out_specular, out_diffuse, g_rgb, g_specular, g_diffuse, g_lgt_acc, g_roughness, g_specular_refl,
-                              g_albedo, g_normal);
+                              blending, out_specular, out_diffuse, g_rgb, g_specular, g_diffuse, g_lgt_acc, g_roughness,
+                              g_specular_refl, g_albedo, g_normal, g_blending);
 }
 
 int nefii_idr_loss_fwd(void* stream, int n, int patch, const float* idr_rgb, const float* sg_rgb, const float* rgb_gt,

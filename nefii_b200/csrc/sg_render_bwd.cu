@@ -32,10 +32,11 @@ __device__ __forceinline__ float warp_sum(float x) {
 __global__ void __launch_bounds__(kSgBwdThreads, 4)
 sg_render_bwd_kernel(int n_rays, int n_sg, int n_mat, const float* __restrict__ lgt, const float* __restrict__ spec,
                      const float* __restrict__ rough, const float* __restrict__ albedo, const float* __restrict__ normal,
-                     const float* __restrict__ view, const float* __restrict__ out_spec, const float* __restrict__ out_diff,
-                     const float* __restrict__ g_rgb, const float* __restrict__ g_spec, const float* __restrict__ g_diff,
-                     float* __restrict__ g_lgt_acc, float* __restrict__ g_rough, float* __restrict__ g_specrefl,
-                     float* __restrict__ g_albedo, float* __restrict__ g_normal) {
+                     const float* __restrict__ view, const float* __restrict__ blend, const float* __restrict__ out_spec,
+                     const float* __restrict__ out_diff, const float* __restrict__ g_rgb, const float* __restrict__ g_spec,
+                     const float* __restrict__ g_diff, float* __restrict__ g_lgt_acc, float* __restrict__ g_rough,
+                     float* __restrict__ g_specrefl, float* __restrict__ g_albedo, float* __restrict__ g_normal,
+                     float* __restrict__ g_blend) {
   extern __shared__ unsigned char smem_raw[];
   constexpr int kWarps = kSgBwdThreads / 32;
   float* sL = reinterpret_cast<float*>(smem_raw);                    // [n_sg][8]: unit axis, sharpness, amplitude
@@ -77,18 +78,23 @@ sg_render_bwd_kernel(int n_rays, int n_sg, int n_mat, const float* __restrict__ 
       const float sp[3] = {spec[k * 3 + 0], spec[k * 3 + 1], spec[k * 3 + 2]};
       sgm::make_brdf_lobe(n, v, rough[k], sp, B);
       float b_bar[3] = {0.f, 0.f, 0.f}, beta_bar = 0.f, nu_bar[3] = {0.f, 0.f, 0.f};
+      // per-point blending weight of this base material (sg_render.py:254-256): the specular sum of material k enters scaled by it
+      const float wk = (blend != nullptr && live) ? blend[ray * n_mat + k] : 1.0f;
+      const float gsw[3] = {gs[0] * wk, gs[1] * wk, gs[2] * wk};
+      float sk[3] = {0.f, 0.f, 0.f};      // this material's un-weighted specular sum (for d / d blending weight)
       for (int m = 0; m < n_sg; ++m) {
         const float4 l0 = *reinterpret_cast<const float4*>(sL + m * 8), l1 = *reinterpret_cast<const float4*>(sL + m * 8 + 4);
         const float a[3] = {l0.x, l0.y, l0.z}, mu[3] = {l1.x, l1.y, l1.z};
         const float lambda = l0.w;
         float t[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // a_bar[3], lambda_bar, mu_bar[3] of this light from this ray
         {
-          const float w = (gs[0] * mu[0]) * B.amp[0] + (gs[1] * mu[1]) * B.amp[1] + (gs[2] * mu[2]) * B.amp[2];
+          const float w = (gsw[0] * mu[0]) * B.amp[0] + (gsw[1] * mu[1]) * B.amp[1] + (gsw[2] * mu[2]) * B.amp[2];
           const float phi = sga::specular_phi_vjp(n, a, lambda, B.axis, B.sharp, w, t, t[3], b_bar, beta_bar, n_bar);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            t[4 + c] += (gs[c] * B.amp[c]) * phi;
-            nu_bar[c] += (gs[c] * mu[c]) * phi;
+            t[4 + c] += (gsw[c] * B.amp[c]) * phi;
+            nu_bar[c] += (gsw[c] * mu[c]) * phi;
+            sk[c] += (mu[c] * B.amp[c]) * phi;
           }
         }
         if (k == 0) {   // the diffuse term of the same light
@@ -111,6 +117,7 @@ sg_render_bwd_kernel(int n_rays, int n_sg, int n_mat, const float* __restrict__ 
       sga::brdf_lobe_vjp(n, v, rough[k], sp, b_bar, beta_bar, nu_bar, n_bar, g_r, g_s);
       g_r = warp_sum(g_r); g_s[0] = warp_sum(g_s[0]); g_s[1] = warp_sum(g_s[1]); g_s[2] = warp_sum(g_s[2]);
       if (lane == 0) { wMat[k * 4 + 0] += g_r; wMat[k * 4 + 1] += g_s[0]; wMat[k * 4 + 2] += g_s[1]; wMat[k * 4 + 3] += g_s[2]; }
+      if (g_blend != nullptr && live) g_blend[ray * n_mat + k] = (gs[0] * sk[0] + gs[1] * sk[1]) + gs[2] * sk[2];
     }
     if (live) {
 #pragma unroll
@@ -137,9 +144,9 @@ sg_render_bwd_kernel(int n_rays, int n_sg, int n_mat, const float* __restrict__ 
 }
 
 int sg_render_bwd(cudaStream_t stream, int n_rays, int n_sg, int n_mat, const float* lgt, const float* spec, const float* rough,
-                  const float* albedo, const float* normal, const float* view, const float* out_spec, const float* out_diff,
-                  const float* g_rgb, const float* g_spec, const float* g_diff, float* g_lgt_acc, float* g_rough,
-                  float* g_specrefl, float* g_albedo, float* g_normal) {
+                  const float* albedo, const float* normal, const float* view, const float* blend, const float* out_spec,
+                  const float* out_diff, const float* g_rgb, const float* g_spec, const float* g_diff, float* g_lgt_acc,
+                  float* g_rough, float* g_specrefl, float* g_albedo, float* g_normal, float* g_blend) {
   NEFII_CHECK_ARG(n_rays >= 0 && n_sg > 0 && n_mat > 0 && n_mat <= kMaxMaterials, "sg_render_bwd: bad sizes");
   if (n_rays == 0) return NEFII_OK;
   NEFII_CHECK_ARG(lgt && spec && rough && albedo && normal && view && out_spec && out_diff && g_lgt_acc && g_rough && g_specrefl &&
@@ -150,9 +157,9 @@ int sg_render_bwd(cudaStream_t stream, int n_rays, int n_sg, int n_mat, const fl
   NEFII_CHECK_ARG(smem <= 48 * 1024, "sg_render_bwd: too many light SGs (%d)", n_sg);
   int blocks = ceil_div(n_rays, kSgBwdThreads);
   if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-  sg_render_bwd_kernel<<<blocks, kSgBwdThreads, smem, stream>>>(n_rays, n_sg, n_mat, lgt, spec, rough, albedo, normal, view, out_spec,
-                                                                out_diff, g_rgb, g_spec, g_diff, g_lgt_acc, g_rough, g_specrefl,
-                                                                g_albedo, g_normal);
+  sg_render_bwd_kernel<<<blocks, kSgBwdThreads, smem, stream>>>(n_rays, n_sg, n_mat, lgt, spec, rough, albedo, normal, view, blend,
+                                                                out_spec, out_diff, g_rgb, g_spec, g_diff, g_lgt_acc, g_rough,
+                                                                g_specrefl, g_albedo, g_normal, g_blend);
   NEFII_LAUNCH_CHECK();
   return NEFII_OK;
 }

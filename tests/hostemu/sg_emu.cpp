@@ -67,13 +67,15 @@ void emu_sg_render_fwd_f64(int n_rays, int n_sg, int n_mat, const double* lgt, c
 extern "C" void emu_sg_render_bwd_f64(int n_rays, int n_sg, int n_mat, const double* lgt, const double* spec, const double* rough,
                                       const double* albedo, const double* normal, const double* view,
                                       const double* g_spec, const double* g_diff, double* acc /*[M,7]*/, double* g_rough /*[K]*/,
-                                      double* g_specrefl /*[K,3]*/, double* g_albedo /*[N,3]*/, double* g_normal /*[N,3]*/) {
+                                      double* g_specrefl /*[K,3]*/, double* g_albedo /*[N,3]*/, double* g_normal /*[N,3]*/,
+                                      const double* blend /*[N,K] or null*/, double* g_blend /*[N,K] or null*/) {
   namespace sga = nefii::sga;
   const double inv_pi = 1.0 / K<double>::pi();
   for (int r = 0; r < n_rays; ++r) {
     // the reference clamps the summed specular / diffuse radiance at 0: recompute the sums for the masks
     double out_rgb[3], out_s[3], out_d[3];
-    sg_render_fwd_t<double>(1, n_sg, n_mat, lgt, spec, rough, albedo + 3 * r, normal + 3 * r, view + 3 * r, nullptr, out_rgb, out_s, out_d);
+    sg_render_fwd_t<double>(1, n_sg, n_mat, lgt, spec, rough, albedo + 3 * r, normal + 3 * r, view + 3 * r,
+                            blend ? blend + (size_t)r * n_mat : nullptr, out_rgb, out_s, out_d);
     double gs[3], gd[3];
     for (int c = 0; c < 3; ++c) {
       gs[c] = out_s[c] > 0 ? g_spec[3 * r + c] : 0.0;
@@ -85,21 +87,25 @@ extern "C" void emu_sg_render_bwd_f64(int n_rays, int n_sg, int n_mat, const dou
     for (int k = 0; k < n_mat; ++k) {
       BrdfLobe<double> B;
       make_brdf_lobe(n, v, rough[k], spec + 3 * k, B);
-      double b_bar[3] = {0, 0, 0}, beta_bar = 0, nu_bar[3] = {0, 0, 0};
+      double b_bar[3] = {0, 0, 0}, beta_bar = 0, nu_bar[3] = {0, 0, 0}, sk[3] = {0, 0, 0};
+      const double wk = blend ? blend[(size_t)r * n_mat + k] : 1.0;
+      const double gsw[3] = {gs[0] * wk, gs[1] * wk, gs[2] * wk};
       for (int m = 0; m < n_sg; ++m) {
         LightSG<double> L;
         load_light(lgt + 7 * m, L);
         double w = 0;
-        for (int c = 0; c < 3; ++c) w += gs[c] * L.amp[c] * B.amp[c];
+        for (int c = 0; c < 3; ++c) w += gsw[c] * L.amp[c] * B.amp[c];
         double a_bar[3] = {0, 0, 0}, l_bar = 0;
         const double phi = sga::specular_phi_vjp(n, L.axis, L.sharp, B.axis, B.sharp, w, a_bar, l_bar, b_bar, beta_bar, n_bar);
         for (int i = 0; i < 3; ++i) acc[7 * m + i] += a_bar[i];
         acc[7 * m + 3] += l_bar;
         for (int c = 0; c < 3; ++c) {
-          acc[7 * m + 4 + c] += gs[c] * B.amp[c] * phi;
-          nu_bar[c] += gs[c] * L.amp[c] * phi;
+          acc[7 * m + 4 + c] += gsw[c] * B.amp[c] * phi;
+          nu_bar[c] += gsw[c] * L.amp[c] * phi;
+          sk[c] += L.amp[c] * B.amp[c] * phi;
         }
       }
+      if (g_blend) g_blend[(size_t)r * n_mat + k] = gs[0] * sk[0] + gs[1] * sk[1] + gs[2] * sk[2];
       sga::brdf_lobe_vjp(n, v, rough[k], spec + 3 * k, b_bar, beta_bar, nu_bar, n_bar, g_rough[k], g_specrefl + 3 * k);
     }
     for (int m = 0; m < n_sg; ++m) {

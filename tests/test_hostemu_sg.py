@@ -81,7 +81,7 @@ def test_backward_f64_matches_autograd_of_oracle(emu):
     g_nrm = torch.zeros(n, 3, dtype=dt)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     emu.emu_sg_render_bwd_f64(n, M, K, p(lgt), p(spec), p(rough), p(albedo.contiguous()), p(normal.contiguous()), p(view.contiguous()),
-                              p(g_spec), p(g_diff), p(acc), p(g_rough), p(g_sr), p(g_alb), p(g_nrm))
+                              p(g_spec), p(g_diff), p(acc), p(g_rough), p(g_sr), p(g_alb), p(g_nrm), None, None)
     ln = lgt[:, :3].norm(dim=-1, keepdim=True)
     d = ln + 1e-6
     g_axis = acc[:, :3] / d - lgt[:, :3] * (lgt[:, :3] * acc[:, :3]).sum(-1, keepdim=True) / (ln * d * d)
@@ -91,3 +91,34 @@ def test_backward_f64_matches_autograd_of_oracle(emu):
     assert torch.allclose(g_rough, leaves[2].grad[:, 0], rtol=1e-6, atol=1e-9)
     assert torch.allclose(g_alb, leaves[3].grad, rtol=1e-6, atol=1e-9)
     assert torch.allclose(g_nrm, leaves[4].grad, rtol=1e-6, atol=1e-8), (g_nrm - leaves[4].grad).abs().max()
+
+
+def test_backward_f64_with_blending_weights(emu):
+    """K = 3 base materials with per-point blending weights (sg_render.py:254-256): gradients incl. d / d blending weight."""
+    dt = torch.float64
+    n, M, K = 90, 16, 3
+    normal, view, albedo = [x.to(dt) for x in inputs.shading_inputs(n, seed=18)]
+    lgt = inputs.synthetic_light_sgs(M, seed=19).to(dt)
+    spec = torch.tensor([[0.04, 0.05, 0.06], [0.1, 0.2, 0.3], [0.5, 0.4, 0.3]], dtype=dt)
+    rough = torch.tensor([[0.35], [0.7], [0.2]], dtype=dt)
+    g = torch.Generator().manual_seed(5)
+    blend = torch.softmax(torch.randn(n, K, generator=g, dtype=dt), -1)
+    g_spec = torch.rand(n, 3, generator=g, dtype=dt)
+    g_diff = torch.rand(n, 3, generator=g, dtype=dt)
+    leaves = [t.clone().requires_grad_(True) for t in (lgt, spec, rough, albedo, normal, blend)]
+    ref = sg.render_with_sg(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], view, blending_weights=leaves[5])
+    ((ref["sg_specular_rgb"] * g_spec).sum() + (ref["sg_diffuse_rgb"] * g_diff).sum()).backward()
+    acc = torch.zeros(M, 7, dtype=dt)
+    g_rough = torch.zeros(K, dtype=dt)
+    g_sr = torch.zeros(K, 3, dtype=dt)
+    g_alb = torch.zeros(n, 3, dtype=dt)
+    g_nrm = torch.zeros(n, 3, dtype=dt)
+    g_bl = torch.zeros(n, K, dtype=dt)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    emu.emu_sg_render_bwd_f64(n, M, K, p(lgt), p(spec), p(rough), p(albedo.contiguous()), p(normal.contiguous()), p(view.contiguous()),
+                              p(g_spec), p(g_diff), p(acc), p(g_rough), p(g_sr), p(g_alb), p(g_nrm), p(blend.contiguous()), p(g_bl))
+    assert torch.allclose(g_sr, leaves[1].grad, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(g_rough, leaves[2].grad[:, 0], rtol=1e-6, atol=1e-9)
+    assert torch.allclose(g_alb, leaves[3].grad, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(g_nrm, leaves[4].grad, rtol=1e-6, atol=1e-8)
+    assert torch.allclose(g_bl, leaves[5].grad, rtol=1e-6, atol=1e-9)

@@ -146,3 +146,31 @@ def test_backward_two_materials(cuda_device):
     for a, b, name in zip(got, want, ("lgtSGs", "specular", "roughness", "albedo", "normal")):
         rel = (a - b).norm().item() / (b.norm().item() + 1e-20)
         assert rel < 1e-3, (name, rel)
+
+
+def test_backward_with_blending_weights(cuda_device):
+    """K = 3 base materials with per-point blending weights: every gradient, the one w.r.t. the weights included."""
+    from nefii_b200.model.sg_render import render_with_sg
+    dev = cuda_device
+    n, K = 900, 3
+    normal, view, albedo = [x.to(dev) for x in inputs.shading_inputs(n, seed=15)]
+    lgt = inputs.synthetic_light_sgs(48, seed=16).to(dev)
+    spec = torch.tensor([[0.04, 0.05, 0.06], [0.3, 0.2, 0.1], [0.5, 0.5, 0.5]], device=dev)
+    r = torch.tensor([[0.25], [0.6], [0.9]], device=dev)
+    g = torch.Generator().manual_seed(4)
+    blend = torch.softmax(torch.randn(n, K, generator=g), -1).to(dev)
+    gy = torch.rand(n, 3, generator=g).to(dev)
+
+    def run(fn, dt=torch.float32):
+        leaves = [t.clone().to(dt).requires_grad_(True) for t in (lgt, spec, r, albedo, normal, blend)]
+        out = fn(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], view.to(dt), blending_weights=leaves[5])
+        (out["sg_rgb"] * gy.to(dt)).sum().backward()
+        return [t.grad for t in leaves]
+
+    got, want, want64 = run(render_with_sg), run(sg.render_with_sg), run(sg.render_with_sg, torch.float64)
+    for a, b, b64, name in zip(got, want, want64, ("lgtSGs", "specular", "roughness", "albedo", "normal", "blending")):
+        rel = (a - b).norm().item() / (b.norm().item() + 1e-20)
+        rel64 = (a.double() - b64).norm().item() / (b64.norm().item() + 1e-20)
+        ref_err = (b.double() - b64).norm().item() / (b64.norm().item() + 1e-20)
+        print("sg bwd blending %-9s rel vs fp32 autograd %.2e, vs f64 %.2e (fp32 autograd vs f64: %.2e)" % (name, rel, rel64, ref_err))
+        assert rel < 1e-3 or rel64 <= max(1e-3, 1.2 * ref_err), (name, rel, rel64, ref_err)
