@@ -152,3 +152,35 @@ def test_mlp_scene_statistics(cuda_device):
     err = (dist - o_dist)[both].abs()
     assert err.median().item() < 1e-5
     assert (err < 1e-4).float().mean().item() > 0.98
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_fixed_schedule_equals_graph_mode(cuda_device, training):
+    """nefii_trace_set_graph_mode(0): every loop unrolled to its worst case (empty rounds exit at once) instead of a CUDA graph
+    with conditional WHILE nodes -- the same kernels, the same results, with the speculative rounds on and off."""
+    from nefii_b200 import _lib
+    from nefii_b200.model.ray_tracing import AnalyticSDF
+    dev = cuda_device
+    lib = _lib.raw()
+    dirs, loc = _camera(dev, 96, seed=4, f=160.0)
+    n = 96 * 96
+    obj = torch.ones(n, dtype=torch.bool, device=dev)
+    obj[::5] = False
+    sdf_dev = AnalyticSDF(otr.robot_scene(), dev)
+    rt, cfg = _module(training)
+    u = torch.rand(100, generator=torch.Generator().manual_seed(9))
+    ref = None
+    try:
+        for mode in (1, 0):
+            for rows in (12288, 0):
+                _lib.check(lib.nefii_trace_set_graph_mode(mode))
+                _lib.check(lib.nefii_trace_set_quad_rows(rows))
+                out = rt(sdf_dev, loc, obj, dirs, uniforms=u if training else None)
+                if ref is None:
+                    ref = out
+                else:
+                    for a, b in zip(out, ref):
+                        assert torch.equal(a, b), (mode, rows)
+    finally:
+        _lib.check(lib.nefii_trace_set_graph_mode(1))
+        _lib.check(lib.nefii_trace_set_quad_rows(12288))
