@@ -645,22 +645,24 @@ def gpu_eager_baseline(dev):
                       "oracle/pipeline.py restating the reference" % (px, rays)}
 
 
-def fitted_scene(dev, step, dev_batches):
-    """The same step on an SDF network L1-fitted to the analytic "robot-scale" primitive union (SURVEY 8d cfg 2(iii)) with the
-    step-1 trainer path (geometry_train.py:354-378: Adam, L1(sdf(points), gt), batch 16384) on the trainable tcgen05 stack."""
+ROBOT_PRIMS = [[1, 0.00, 0.05, 0.00, 0.22, 0.28, 0.14, 0], [0, 0.00, 0.48, 0.00, 0.16, 0, 0, 0],
+               [1, -0.34, 0.10, 0.00, 0.07, 0.24, 0.07, 0], [1, 0.34, 0.10, 0.00, 0.07, 0.24, 0.07, 0],
+               [1, -0.12, -0.48, 0.00, 0.08, 0.24, 0.08, 0], [1, 0.12, -0.48, 0.00, 0.08, 0.24, 0.08, 0],
+               [0, -0.34, -0.20, 0.00, 0.09, 0, 0, 0], [0, 0.34, -0.20, 0.00, 0.09, 0, 0, 0],
+               [0, 0.00, 0.05, 0.17, 0.08, 0, 0, 0]]
+
+
+def fit_geometry(dev, n_fit=None):
+    """conf.conf's model with its SDF network L1-fitted to the analytic "robot-scale" primitive union (SURVEY 8d cfg 2(iii)) with the
+    step-1 trainer path (geometry_train.py:354-378: Adam, L1(sdf(points), gt), batch 16384) on the trainable tcgen05 stack.
+    -> (model with an un-frozen geometry, seconds, last L1)"""
     from nefii_b200.model.ray_tracing import AnalyticSDF
-    pose, K = [t.to(dev) for t in make_camera()]
     fit = build_model(dev, bumps=0.0)
     fit.unfreeze_geometry()
-    prims = torch.tensor([[1, 0.00, 0.05, 0.00, 0.22, 0.28, 0.14, 0], [0, 0.00, 0.48, 0.00, 0.16, 0, 0, 0],
-                          [1, -0.34, 0.10, 0.00, 0.07, 0.24, 0.07, 0], [1, 0.34, 0.10, 0.00, 0.07, 0.24, 0.07, 0],
-                          [1, -0.12, -0.48, 0.00, 0.08, 0.24, 0.08, 0], [1, 0.12, -0.48, 0.00, 0.08, 0.24, 0.08, 0],
-                          [0, -0.34, -0.20, 0.00, 0.09, 0, 0, 0], [0, 0.34, -0.20, 0.00, 0.09, 0, 0, 0],
-                          [0, 0.00, 0.05, 0.17, 0.08, 0, 0, 0]], dtype=torch.float32)
-    target = AnalyticSDF(prims, dev)
+    target = AnalyticSDF(torch.tensor(ROBOT_PRIMS, dtype=torch.float32), dev)
     opt = torch.optim.Adam(fit.implicit_network.parameters(), lr=5e-4)
     g = torch.Generator(device=dev).manual_seed(3)
-    n_fit = env_int("NEFII_BENCH_FIT_STEPS", 400)
+    n_fit = env_int("NEFII_BENCH_FIT_STEPS", 400) if n_fit is None else n_fit
     t0 = time.perf_counter()
     last = None
     for i in range(n_fit):
@@ -673,7 +675,14 @@ def fitted_scene(dev, step, dev_batches):
         last.backward()
         opt.step()
     torch.cuda.synchronize()
-    fit_s = time.perf_counter() - t0
+    return fit, time.perf_counter() - t0, float(last.item())
+
+
+def fitted_scene(dev, step, dev_batches):
+    """The same step on the fitted geometry of fit_geometry()."""
+    pose, K = [t.to(dev) for t in make_camera()]
+    n_fit = env_int("NEFII_BENCH_FIT_STEPS", 400)
+    fit, fit_s, last_l1 = fit_geometry(dev, n_fit)
     fit.freeze_geometry()
     fit.train()
     # the step function's optimizers and flat gradient buffer belong to the headline model: time forward + loss + backward here
@@ -700,7 +709,7 @@ def fitted_scene(dev, step, dev_batches):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / len(batches[1:])
-    return {"fit_steps": n_fit, "fit_seconds": fit_s, "fit_l1": float(last.item()), "pixel_hit_fraction": hit_frac,
+    return {"fit_steps": n_fit, "fit_seconds": fit_s, "fit_l1": last_l1, "pixel_hit_fraction": hit_frac,
             "ms_per_step_fwd_loss_bwd": ms, "value": rays / (a.elapsed_time(b) * 1e-3), "unit": "rays/s",
             "note": "SDF MLP fitted to the analytic robot scene with the step-1 path (batch 16384, Adam 5e-4), then frozen; "
                     "same batches as the headline, forward + loss + backward (no optimizer step)"}

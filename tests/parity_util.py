@@ -23,7 +23,7 @@ def _quant(x, qs=(0.5, 0.95, 0.99, 1.0)):
     return tuple(srt[min(srt.numel() - 1, int(q * (srt.numel() - 1) + 0.5))].item() for q in qs)
 
 
-def fullsize_compare(dev, bumps, n_px, n_rays, training, tiers=None, grads=True, seed=0, verbose=True, ref64=False):
+def fullsize_compare(dev, bumps, n_px, n_rays, training, tiers=None, grads=True, seed=0, verbose=True, ref64=False, model=None):
     """BASELINE configs[2]-sized parity run: IDRNetwork.forward_with_uv against oracle/pipeline.py on the same device, same
     weights, same uniforms.  Returns a dict of statistics (used by tests/test_parity_fullsize_gpu.py and printed here)."""
     import bench
@@ -33,10 +33,14 @@ def fullsize_compare(dev, bumps, n_px, n_rays, training, tiers=None, grads=True,
     from nefii_b200.utils.conf import default_model_conf
     if tiers is not None:
         _lib.check(_lib.raw().nefii_trace_set_tiers(int(tiers[0]), int(tiers[1])))
-    om = rh.small_model(seed=seed, bumps=bumps)
-    torch.manual_seed(0)
-    net = IDRNetwork(default_model_conf()).to(dev)
-    rh.load_oracle_weights(net, om)
+    if model is None:
+        om = rh.small_model(seed=seed, bumps=bumps)
+        torch.manual_seed(0)
+        net = IDRNetwork(default_model_conf()).to(dev)
+        rh.load_oracle_weights(net, om)
+    else:          # a prepared IDRNetwork (e.g. a fitted geometry): the oracle gets exactly its weights
+        net = model
+        om = bench.oracle_from_net(net)
     om = om.to(dev)
     om.sdf_fn = _chunked(om.sdf_fn)
     net.train(training)
