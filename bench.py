@@ -19,7 +19,8 @@ contract's keys the line carries `roofline` (the tcgen05 layer GEMM, timed live 
 port in eager PyTorch on this GPU, fp32 matmuls -- what BASELINE.md calls the comparison baseline), `configs` (stand-alone
 timings of BASELINE configs[0] and [1] with their roofline fractions), `weak_scaling` (N > 1: every rank its own 2048-pixel
 batch), `fitted_scene` (the step on an SDF network L1-fitted to the analytic robot scene with the step-1 trainer path),
-`ms_per_frame_800x800`, `cfg4_1080p_256spp` (N = 8), `ms_per_secondary_training_pass` and `gpu_launches`.
+`ms_per_frame_800x800`, `cfg4_1080p_256spp` (N = 8), `ms_per_secondary_training_pass`, `gpu_launches` and
+`trace_graph_captures_in_timed_region` (trace graphs are captured per secondary-ray bucket; a new bucket costs ~5 ms once).
 """
 import argparse
 import ctypes
@@ -31,7 +32,12 @@ import sys
 import threading
 import time
 
-import torch
+# The hit count -- and with it the size of every tensor after the primary trace -- changes from one pixel batch to the next (72 k .. 107 k
+# secondary rays in the bench scene).  torch's default caching allocator answers new sizes with cudaMalloc / cudaFree of whole segments
+# (a device synchronisation each: measured 250 ms instead of 180 ms on the steps that hit one); expandable segments grow in place.
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -111,6 +117,12 @@ class ClockSampler:
 
     def __init__(self, gpu_index, enabled=True):
         self.samples, self.proc, self.gpu, self.enabled = [], None, gpu_index, enabled
+        self.first = 0
+
+    def mark(self):
+        """samples from here on count (the poller is started EARLY: nvidia-smi's own start-up takes driver locks for a few
+        hundred milliseconds and stalls kernel launches -- measured +18 ms per step when it fell inside a 10-step timed loop)"""
+        self.first = len(self.samples)
 
     def __enter__(self):
         if not self.enabled:        # one poller per job (rank 0's GPU): eight NVML pollers contend with the ranks' launch threads
@@ -140,7 +152,7 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in self.samples[self.first:]:
             try:
                 sm.append(float(s[0]))
                 mx.append(float(s[1]))
@@ -285,13 +297,16 @@ def run_ours(args):
         return max_over_ranks(a.elapsed_time(b)), reduce_ranks(ray_count.item())
 
     # ---- device-resident timing ------------------------------------------------------------------------------
-    for i in range(args.warmup):
-        step(*dev_batches[i], count_rays=False)
-    barrier()
-    launches0 = int(lib.nefii_launch_count())
-    with ClockSampler(local, enabled=(rank == 0)) as clocks:
+    with ClockSampler(local, enabled=(rank == 0)) as clocks:      # started before the warm-up, read from the timed region on
+        for i in range(args.warmup):
+            step(*dev_batches[i], count_rays=False)
+        barrier()
+        launches0 = int(lib.nefii_launch_count())
+        captures0 = int(lib.nefii_trace_graph_captures())
+        clocks.mark()
         ms, rays = timed_steps(dev_batches[args.warmup:])
     launches = int(lib.nefii_launch_count()) - launches0
+    captures = int(lib.nefii_trace_graph_captures()) - captures0
     value = rays / (ms * 1e-3)
 
     # ---- end to end through the public API: pinned host inputs -> device, loss read back, every step -------------
@@ -365,6 +380,7 @@ def run_ours(args):
             "e2e": {"value": rays_e2e / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
+            "trace_graph_captures_in_timed_region": captures,
             "gpu_launches_note": "kernels of libnefii_b200.so; a replay of a captured trace graph counts one trip per device-driven loop",
             "clocks": clocks.summary(),
             "roofline": roofline,

@@ -219,6 +219,9 @@ int nefii_trace_set_tiers(int march_flush, int bulk_flush);
  * conditional WHILE nodes (default; NEFII_TRACE_GRAPH=0 selects the fixed schedule at load) */
 int nefii_trace_set_graph_mode(int mode);
 int nefii_trace_graph_mode(void);   /* the mode in force */
+/* trace graphs captured so far in this process (a capture + instantiate costs tens of milliseconds: callers that time a loop
+ * check that the count did not move inside it) */
+int64_t nefii_trace_graph_captures(void);
 /* Speculative rounds while few rays are in flight (a round is then latency-bound: 8 dependent layer GEMMs on a handful of row
  * tiles).  Sphere tracing: a ray that starts an iteration also asks for the SDF at the positions its line search would step back
  * to (1 + line_step_iters points per marching end), so the next round runs the whole iteration; used while

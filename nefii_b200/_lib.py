@@ -49,6 +49,7 @@ SIGNATURES = {
     "nefii_trace_set_tiers": [c_int, c_int],
     "nefii_trace_set_graph_mode": [c_int],
     "nefii_trace_graph_mode": [],
+    "nefii_trace_graph_captures": [],
     "nefii_trace_set_quad_rows": [c_int],
     "nefii_trace_set_bisect_depth": [c_int],
     "nefii_trace_graph_clear": [],
@@ -87,6 +88,7 @@ def _load():
         fn.restype = c_int
     lib.nefii_sdf_workspace_bytes.restype = c_longlong
     lib.nefii_launch_count.restype = c_longlong
+    lib.nefii_trace_graph_captures.restype = c_longlong
     lib.nefii_trace_workspace_bytes.restype = c_longlong
     return lib
 

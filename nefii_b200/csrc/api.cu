@@ -182,6 +182,7 @@ int nefii_ray_trace(void* stream, const nefii_trace_config* cfg, int sdf_kind, c
 int nefii_trace_set_tiers(int march_flush, int bulk_flush) { return nefii::trace_set_tiers(march_flush, bulk_flush); }
 int nefii_trace_set_graph_mode(int mode) { return nefii::trace_set_graph_mode(mode); }
 int nefii_trace_graph_mode(void) { return nefii::trace_graph_mode(); }
+int64_t nefii_trace_graph_captures(void) { return (int64_t)nefii::trace_graph_captures(); }
 int nefii_trace_set_quad_rows(int rows) { return nefii::trace_set_quad_rows(rows); }
 int nefii_trace_set_bisect_depth(int depth) { return nefii::trace_set_bisect_depth(depth); }
 int nefii_trace_graph_clear(void) { return nefii::trace_graph_clear(); }

@@ -80,6 +80,7 @@ int trace_read_stats(cudaStream_t stream, const SdfSource& src, int n_rays, int 
 // 0: fixed launch schedule, 1: CUDA graph with conditional WHILE nodes (default; NEFII_TRACE_GRAPH overrides at load)
 int trace_set_graph_mode(int mode);
 int trace_graph_mode();
+long long trace_graph_captures();
 // drops every cached graph (call when a workspace or a network the graphs point into is freed)
 int trace_graph_clear();
 

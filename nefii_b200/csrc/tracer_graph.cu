@@ -43,6 +43,7 @@ struct Entry {
 
 std::mutex g_mu;
 std::list<Entry> g_cache;        // most recently used first
+long long g_captures = 0;        // graphs captured so far (a capture + instantiate costs tens of milliseconds)
 constexpr size_t kMaxGraphs = 24;
 
 struct DevStreams { cudaStream_t cap = nullptr, body = nullptr; };
@@ -131,6 +132,11 @@ int trace_graph_clear() {
   return NEFII_OK;
 }
 
+long long trace_graph_captures() {
+  std::lock_guard<std::mutex> lock(g_mu);
+  return g_captures;
+}
+
 int ray_trace(cudaStream_t stream, const TraceConfig& cfg, const SdfSource& src, int n_batch, int n_pix,
               const float* cam_loc, const float* ray_dirs, const unsigned char* object_mask, int flags,
               const float* linspace, const float* uniforms, void* workspace, size_t ws_bytes, float* points,
@@ -203,6 +209,7 @@ int ray_trace(cudaStream_t stream, const TraceConfig& cfg, const SdfSource& src,
       return set_error(NEFII_ERR_CUDA, "trace graph: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
     }
     add_launches(-e.launches);      // the capture itself launched nothing; every replay is counted below
+    ++g_captures;
     g_cache.push_front(e);
     while (g_cache.size() > kMaxGraphs) {
       destroy(g_cache.back());

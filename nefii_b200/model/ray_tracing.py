@@ -104,7 +104,10 @@ class RayTracing(nn.Module):
     # rays with their own origin (the integrator's secondary rays: n_pix == 1) are padded to a multiple of this many rays
     # with rays that miss the bounding sphere, so that a slowly varying ray count replays the same CUDA graph
     RAY_BUCKET = 8192
-    MAX_SHAPES = 8
+    MAX_SHAPES = 16
+    # a new secondary-ray bucket also captures the graphs of the buckets within this distance (hit counts of consecutive pixel batches
+    # of a scene differ by +-20 %: 72 k .. 107 k secondary rays in the bench scene)
+    PRECAPTURE_RADIUS = 3
 
     def __init__(
             self,
@@ -206,7 +209,7 @@ class RayTracing(nn.Module):
         # the workspace is shared by every shape and its pointer is part of the graph key: size it for the next bucket too, so that a
         # slowly growing ray count does not invalidate the graphs that exist
         n_cap = cap_batch * num_pixels
-        grow = (cap_batch + self.RAY_BUCKET) * num_pixels if bucketed else n_cap
+        grow = (cap_batch + (self.PRECAPTURE_RADIUS + 1) * self.RAY_BUCKET) * num_pixels if bucketed else n_cap
         lib = _lib.raw()
         need = int(lib.nefii_trace_workspace_bytes(kind, c_void_p(ptr), grow, self.n_steps))
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
@@ -217,8 +220,9 @@ class RayTracing(nn.Module):
         if bucketed and new_shape and _lib.raw().nefii_trace_graph_mode() == 1:
             # A ray count that hovers around a bucket boundary alternates between two shapes: capture the neighbours' graphs now (one
             # trace of rays that all miss the sphere: no SDF evaluation runs), not in the middle of somebody's timed loop.
-            for nb in (cap_batch + self.RAY_BUCKET, cap_batch - self.RAY_BUCKET):
-                if nb <= 0 or (dev, nb, num_pixels) in self._shape_bufs:
+            near = [cap_batch + d * self.RAY_BUCKET for k in range(1, self.PRECAPTURE_RADIUS + 1) for d in (k, -k)]
+            for nb in near:
+                if nb <= 0 or (dev, nb, num_pixels) in self._shape_bufs or len(self._shape_bufs) >= self.MAX_SHAPES - 1:
                     continue
                 wb = self._shape_buffers(dev, nb, num_pixels)
                 self._fill_missing_rays(wb, 0, 0, dev)
