@@ -68,7 +68,7 @@ def test_forward_matches_oracle_pipeline(cuda_device, training, rays):
         p95 = err.flatten().kthvalue(max(1, int(0.95 * err.numel())))[0].item()
         # idr_rgb = (raw MLP output)^2 of a random-init net: tiny values, the relative error of the square is amplified
         print('pipeline train=%d %-28s p95 rel err %.2e' % (training, k, p95))
-        assert p95 < (6e-3 if k == 'idr_rgb_values' else 3e-4), (k, p95)
+        assert p95 < (1.5e-3 if k == 'idr_rgb_values' else 1e-4), (k, p95)        # measured 3.5e-4 / <= 1.3e-5 (fp16-split planes)
     # secondary rays: same directions (bit-exact sampler) wherever the primary hit point agrees
     if mine['secondary_dir'] is not None and mine['secondary_dir'].shape == ref['secondary_dir'].shape:
         d = (mine['secondary_dir'] - ref['secondary_dir']).abs().amax(-1)
@@ -110,11 +110,11 @@ def test_gradients_match_oracle_pipeline(cuda_device):
 
     # north_star: gradients rel 1e-3 -- met at BASELINE size (tests/test_parity_fullsize_gpu.py); this 1024-pixel x 2-ray batch
     # has so few samples per weight that single ReLU / ELU sign flips of near-zero pre-activations show (measured: lgtSGs 1e-6,
-    # material <= 8e-5, radiance 1e-4 .. 4.6e-3): 1e-2 here
+    # material <= 1.4e-5, radiance 1e-5 .. 1.9e-3): 1e-2 for the radiance network here, rel 1e-3 for the others
     print('grad rel: lgtSGs %.2e material %s' % (rel(g_lgt, om.lgtSGs.grad), ' '.join('%.1e' % rel(a, w.grad) for a, w in zip(g_mat, om.material.W))))
-    assert rel(g_lgt, om.lgtSGs.grad) < 5e-3, rel(g_lgt, om.lgtSGs.grad)
+    assert rel(g_lgt, om.lgtSGs.grad) < 1e-3, rel(g_lgt, om.lgtSGs.grad)       # measured 7e-7
     for a, b in zip(g_mat, [w.grad for w in om.material.W]):
-        assert rel(a, b) < 5e-3, rel(a, b)
+        assert rel(a, b) < 1e-3, rel(a, b)                                     # measured <= 1.4e-5
     # radiance net: the oracle holds effective weights W = g v/|v| with |v| = g at init, so dL/dW == dL/dv + radial part;
     # compare the tangential gradient (what weight_v receives) after projecting the oracle's gradient the same way
     for a, w in zip(g_rad_v, om.radiance.W):
