@@ -317,6 +317,37 @@ int nefii_reduce_splits(void* stream, const float* partial, int n_splits, int64_
                         float* out);
 
 
+/* The whole trainable dense stack in ONE host call each way (RenderingNetwork.forward :196-241; EnvmapMaterialNetwork's
+ * diffuse_albedo / roughness layers, sg_envmap_material.py:357-366, :403-425): input assembly, weight packing, the hidden-layer
+ * GEMMs and the fused 1..4-wide output layer; backward = output layer, then per hidden layer the two transposes, the split-K
+ * weight-gradient GEMM + reduction and the data-gradient GEMM.  Same kernels and arithmetic as the helpers above, sequenced
+ * natively (at small batches the per-call host cost of sequencing them one by one was the limiter).
+ * Host arrays: seg_* [n_seg <= 4]; weights / biases / dim_in / dim_out / grad_w / grad_b [n_hidden + 1] (hidden layers, then
+ * the output layer; effective fp32 weights [out, in] row-major, device).  workspace: device, >= nefii_dense_stack_workspace_bytes;
+ * with need_grad the forward leaves the activation planes in it and the backward must get the same workspace, untouched.
+ * y [rows, n_out]; gy [rows, n_out]; grad_w / grad_b are overwritten. */
+typedef struct nefii_dense_stack_desc {
+  int32_t rows, n_hidden, act, n_seg;
+  const float* seg_src[4];
+  int32_t seg_width[4];
+  int32_t seg_freqs[4];            /* >= 0: positional encoding of a 3-vector with that many octaves, -1: raw copy */
+  const float* const* weights;     /* host array [n_hidden + 1] of device pointers */
+  const float* const* biases;
+  const int32_t* dim_in;           /* host [n_hidden + 1] */
+  const int32_t* dim_out;
+  int32_t need_grad;
+  void* workspace;
+  int64_t workspace_bytes;
+  float* y;                        /* forward out */
+  const float* gy;                 /* backward in */
+  float* const* grad_w;            /* backward out, host array [n_hidden + 1] of device pointers */
+  float* const* grad_b;
+} nefii_dense_stack_desc;
+int64_t nefii_dense_stack_workspace_bytes(const nefii_dense_stack_desc* desc /* host */);   /* < 0: error */
+int nefii_dense_stack_fwd(void* stream, const nefii_dense_stack_desc* desc);
+int nefii_dense_stack_bwd(void* stream, const nefii_dense_stack_desc* desc);
+
+
 /* ---- IDRLoss, the step right after the rendering path (reference code/model/loss.py:122-320) -----------------
  * One launch for the five terms live in the step-2 recipe, means formed on the device (an empty mask yields 0 like the
  * reference's `mask.sum() == 0` early-outs, without their host round trips):

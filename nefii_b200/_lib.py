@@ -65,6 +65,9 @@ SIGNATURES = {
     "nefii_sdf_get_format": [c_void_p],
     "nefii_sdf_set_pe_prologue": [c_int],
     "nefii_gemm_set_trunc_comp_fmt": [c_int, c_int, c_float],
+    "nefii_dense_stack_workspace_bytes": [c_void_p],
+    "nefii_dense_stack_fwd": [c_void_p, c_void_p],
+    "nefii_dense_stack_bwd": [c_void_p, c_void_p],
     "nefii_idr_loss_fwd": [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_int, c_int, c_float, c_void_p],
     "nefii_idr_loss_bwd": [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_int, c_int, c_float] + [c_void_p] * 6,
 }
@@ -87,6 +90,7 @@ def _load():
         fn.argtypes = argtypes
         fn.restype = c_int
     lib.nefii_sdf_workspace_bytes.restype = c_longlong
+    lib.nefii_dense_stack_workspace_bytes.restype = c_longlong
     lib.nefii_launch_count.restype = c_longlong
     lib.nefii_trace_graph_captures.restype = c_longlong
     lib.nefii_trace_workspace_bytes.restype = c_longlong

@@ -8,6 +8,7 @@
 #include "sdf_mlp.cuh"
 #include "tracer.cuh"
 #include "loss.cuh"
+#include "dense_stack.cuh"
 
 namespace nefii {
 
@@ -291,6 +292,39 @@ int nefii_idr_loss_bwd(void* stream, int n, int patch, const float* idr_rgb, con
                        float* g_idr_rgb, float* g_sg_rgb, float* g_normal, float* g_sdf_output) {
   return nefii::idr_loss_bwd((cudaStream_t)stream, n, patch, idr_rgb, sg_rgb, rgb_gt, normal, sdf_output, net_mask, obj_mask,
                              loss_type, env_loss_type, alpha, terms, g_terms, g_idr_rgb, g_sg_rgb, g_normal, g_sdf_output);
+}
+
+namespace {
+int fill_stack(const nefii_dense_stack_desc* c, bool with_ptrs, nefii::DenseStack& d) {
+  if (!c || !c->dim_in || !c->dim_out) return nefii::set_error(NEFII_ERR_ARG, "nefii_dense_stack: null descriptor");
+  if (c->n_hidden < 1 || c->n_hidden >= nefii::kDenseMaxLayers || c->n_seg < 1 || c->n_seg > 4)
+    return nefii::set_error(NEFII_ERR_ARG, "nefii_dense_stack: n_hidden %d / n_seg %d out of range", c->n_hidden, c->n_seg);
+  if (with_ptrs && (!c->weights || !c->biases)) return nefii::set_error(NEFII_ERR_ARG, "nefii_dense_stack: null weights / biases");
+  d.rows = c->rows; d.n_hidden = c->n_hidden; d.act = c->act; d.n_seg = c->n_seg;
+  for (int s = 0; s < c->n_seg; ++s) { d.seg_src[s] = c->seg_src[s]; d.seg_width[s] = c->seg_width[s]; d.seg_freqs[s] = c->seg_freqs[s]; }
+  for (int l = 0; l <= c->n_hidden; ++l) {
+    d.dim_in[l] = c->dim_in[l]; d.dim_out[l] = c->dim_out[l];
+    if (with_ptrs) { d.weights[l] = c->weights[l]; d.biases[l] = c->biases[l]; }
+    if (with_ptrs && c->grad_w && c->grad_b) { d.grad_w[l] = c->grad_w[l]; d.grad_b[l] = c->grad_b[l]; }
+  }
+  d.need_grad = c->need_grad; d.workspace = c->workspace; d.workspace_bytes = c->workspace_bytes; d.y = c->y; d.gy = c->gy;
+  return NEFII_OK;
+}
+}  // namespace
+int64_t nefii_dense_stack_workspace_bytes(const nefii_dense_stack_desc* desc) {
+  nefii::DenseStack d;
+  if (fill_stack(desc, false, d)) return -1;
+  return nefii::dense_stack_workspace_bytes(d);
+}
+int nefii_dense_stack_fwd(void* stream, const nefii_dense_stack_desc* desc) {
+  nefii::DenseStack d;
+  if (int rc = fill_stack(desc, true, d)) return rc;
+  return nefii::dense_stack_fwd((cudaStream_t)stream, d);
+}
+int nefii_dense_stack_bwd(void* stream, const nefii_dense_stack_desc* desc) {
+  nefii::DenseStack d;
+  if (int rc = fill_stack(desc, true, d)) return rc;
+  return nefii::dense_stack_bwd((cudaStream_t)stream, d);
 }
 
 }  // extern "C"

@@ -231,6 +231,8 @@ int device_sms() {
 }
 }  // namespace
 
+int gemm_device_sms() { return device_sms(); }
+
 int gemm_set_cluster(int cl) {
   NEFII_CHECK_ARG(cl == 1 || cl == 2, "gemm_set_cluster: 1 (single CTA) or 2 (cta_group::2 pair)");
   g_cluster_pref = cl;

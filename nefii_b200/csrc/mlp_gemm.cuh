@@ -96,6 +96,8 @@ int gemm_profile_fetch(double* out3);
 bool gemm_profile_active();
 // per-device one-time set-up (dynamic shared memory opt-in of every kernel variant, SM count); cheap when already done
 int gemm_prepare_device();
+// SM count of the current device (after gemm_prepare_device)
+int gemm_device_sms();
 // bumped by every setter above: anything that caches launches (trace graphs) keys on it
 long long gemm_config_epoch();
 

@@ -13,6 +13,7 @@ Backward: output layer backward (elementwise + reductions), then per hidden laye
           column sums, and the data-gradient GEMM with the activation derivative fused into its epilogue.
 """
 import ctypes
+import os
 
 import torch
 
@@ -22,6 +23,69 @@ c_void_p = ctypes.c_void_p
 # accuracy tier of the forward layer GEMMs of the trainable stacks (K blocks per TMEM partial; 1 = shortest partial sums,
 # 0 = library default).  With the truncation compensation of the layer GEMM (csrc/mlp_gemm.cu) the default is as accurate as 1.
 FWD_FLUSH = 0
+
+
+# one native call per direction for the plain stacks (csrc/dense_stack.cu) instead of one ctypes call per kernel; 0 = the
+# per-kernel sequence below (kept: it is the only one that knows skip connections and want_hidden)
+NATIVE_STACK = int(os.environ.get("NEFII_DENSE_NATIVE", "1"))
+
+
+class DenseStackDesc(ctypes.Structure):
+    """Mirror of ``nefii_dense_stack_desc``."""
+    _fields_ = [("rows", ctypes.c_int32), ("n_hidden", ctypes.c_int32), ("act", ctypes.c_int32), ("n_seg", ctypes.c_int32),
+                ("seg_src", c_void_p * 4), ("seg_width", ctypes.c_int32 * 4), ("seg_freqs", ctypes.c_int32 * 4),
+                ("weights", c_void_p), ("biases", c_void_p), ("dim_in", c_void_p), ("dim_out", c_void_p),
+                ("need_grad", ctypes.c_int32), ("workspace", c_void_p), ("workspace_bytes", ctypes.c_int64),
+                ("y", c_void_p), ("gy", c_void_p), ("grad_w", c_void_p), ("grad_b", c_void_p)]
+
+
+class _NativeStack:
+    """Descriptor + the host arrays it points to + the tensors the device pointers belong to (kept alive together)."""
+
+    def __init__(self, act, srcs, seg_freqs, Ws, bs, need_grad):
+        n_lin = len(Ws)
+        self.n_lin = n_lin
+        self.keep = (srcs, Ws, bs)
+        self.w_ptrs = (c_void_p * n_lin)(*[w.data_ptr() for w in Ws])
+        self.b_ptrs = (c_void_p * n_lin)(*[b.data_ptr() for b in bs])
+        self.dim_in = (ctypes.c_int32 * n_lin)(*[w.shape[1] for w in Ws])
+        self.dim_out = (ctypes.c_int32 * n_lin)(*[w.shape[0] for w in Ws])
+        d = DenseStackDesc()
+        d.rows, d.n_hidden, d.act, d.n_seg = srcs[0].shape[0], n_lin - 1, act, len(srcs)
+        for i, (t, f) in enumerate(zip(srcs, seg_freqs)):
+            d.seg_src[i], d.seg_width[i], d.seg_freqs[i] = t.data_ptr(), t.shape[1], f
+        d.weights, d.biases = ctypes.addressof(self.w_ptrs), ctypes.addressof(self.b_ptrs)
+        d.dim_in, d.dim_out = ctypes.addressof(self.dim_in), ctypes.addressof(self.dim_out)
+        d.need_grad = 1 if need_grad else 0
+        self.desc = d
+        need = int(_lib.raw().nefii_dense_stack_workspace_bytes(ctypes.byref(d)))
+        if need < 0:
+            _lib.check(1)
+        self.ws = torch.empty(need, dtype=torch.uint8, device=srcs[0].device)
+        d.workspace, d.workspace_bytes = self.ws.data_ptr(), need
+
+    def forward(self, y):
+        self.desc.y = y.data_ptr()
+        _lib.check(_lib.raw().nefii_dense_stack_fwd(_lib.stream_ptr(y.device), ctypes.byref(self.desc)))
+
+    def backward(self, gy):
+        """-> [gW_0, gb_0, gW_1, ...] as views of one flat buffer."""
+        Ws, bs = self.keep[1], self.keep[2]
+        sizes = []
+        for w, b in zip(Ws, bs):
+            sizes += [w.numel(), b.numel()]
+        flat = torch.empty(sum(sizes), device=gy.device, dtype=torch.float32)
+        parts = list(torch.split(flat, sizes))
+        base = flat.data_ptr()
+        offs = [0]
+        for sz in sizes:
+            offs.append(offs[-1] + 4 * sz)
+        gw = (c_void_p * self.n_lin)(*[base + offs[2 * l] for l in range(self.n_lin)])
+        gb = (c_void_p * self.n_lin)(*[base + offs[2 * l + 1] for l in range(self.n_lin)])
+        self.desc.gy = gy.data_ptr()
+        self.desc.grad_w, self.desc.grad_b = ctypes.addressof(gw), ctypes.addressof(gb)
+        _lib.check(_lib.raw().nefii_dense_stack_bwd(_lib.stream_ptr(gy.device), ctypes.byref(self.desc)))
+        return [p.view(t.shape) for p, t in zip(parts, [x for wb in zip(Ws, bs) for x in wb])]
 
 
 def _num_sms(device):
@@ -101,6 +165,17 @@ class _DenseMlp(torch.autograd.Function):
             ctx.empty = True
             ctx.shapes = [p.shape for p in params]
             return y, hidden
+        if NATIVE_STACK and not skip and not want_hidden:
+            srcs = [_lib.f32c(t).reshape(n, -1) for t in seg_src]
+            st = _NativeStack(act, srcs, seg_freqs, [_lib.f32c(w) for w in Ws], [_lib.f32c(b) for b in bs], need_grad)
+            st.forward(y)
+            ctx.empty = False
+            ctx.native = st if need_grad else None
+            ctx.acts = True
+            if need_grad:
+                ctx.needs = [ctx.needs_input_grad[7 + n_seg + i] for i in range(len(params))]
+            return y, hidden
+        ctx.native = None
         k0 = ops.round_up(d_in, 64)
         in0, _keep = assemble_input(segments, k0)
         w_last = _lib.f32c(Ws[-1])
@@ -161,6 +236,10 @@ class _DenseMlp(torch.autograd.Function):
         if ctx.acts is None:
             raise _lib.NefiiError("dense_mlp: backward called a second time; the activation planes are released after the first "
                                   "pass (retain_graph is not supported on this path)")
+        if ctx.native is not None:
+            grads = ctx.native.backward(_lib.f32c(gy))
+            ctx.native = ctx.acts = None
+            return (None,) * (n_lead + ctx.n_seg) + tuple(g if need else None for g, need in zip(grads, ctx.needs))
         act, L, n = ctx.act, ctx.n_hidden, ctx.n
         dev = gy.device
         gy = _lib.f32c(gy)
