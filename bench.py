@@ -45,6 +45,9 @@ sys.path.insert(0, ROOT)
 METRIC = "shaded rays/sec (primary+indirect, fwd+bwd)"
 NUM_PIXELS, NUM_RAYS, NUM_SGS, IMG = int(os.environ.get("NEFII_BENCH_PIXELS", 2048)), 64, 128, 800      # env: diagnostics only
 SDF_FLOPS_PER_POINT = 3.671e6      # 1,835,520 MAC forward
+# the primary trace of batch i + 1 enqueued on a side stream next to the step of batch i (IDRNetwork.prefetch_trace); 0 = the steps
+# run strictly one after the other (round 2's numbers up to trip T)
+PREFETCH = int(os.environ.get("NEFII_BENCH_PREFETCH", "1"))
 SCENE_BUMPS = 0.08                 # perturbation of the geometric-init sphere (the parity tests' rough scene)
 SG_FLOPS_PER_RAY, SG_BYTES_PER_RAY = 35.0e3, 72.0      # render_with_sg at M = 128, K = 1 (algorithmic)
 
@@ -284,14 +287,25 @@ def run_ours(args):
         import torch.distributed as dist
         return reduce_ranks(x, dist.ReduceOp.MAX) if world > 1 else x
 
+    def prefetch(bt):
+        """Software pipelining across steps (geometry frozen: the trace of a batch does not depend on the parameter update before
+        it): the primary trace of the NEXT batch is enqueued on a side stream before this batch's step.  Every trace still runs
+        inside the timed region -- the loop below starts one per step (the last step's wraps around to the first batch) and joins
+        the side stream before the closing event; the first step consumes the one the warm-up started."""
+        if PREFETCH:
+            model.prefetch_trace({'uv': bt[0], 'object_mask': bt[1], 'pose': pose, 'intrinsics': K})
+
     def timed_steps(batches, count=True):
         """W warm-up steps were done by the caller; EXACTLY len(batches) steps between barrier + synchronize, device-timed"""
         ray_count.zero_()
+        prefetch(batches[0])
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for bt in batches:
+        for i, bt in enumerate(batches):
+            prefetch(batches[(i + 1) % len(batches)])
             step(*bt, count_rays=count)
+        model.prefetch_join()
         b.record()
         barrier()
         return max_over_ranks(a.elapsed_time(b)), reduce_ranks(ray_count.item())
@@ -299,6 +313,8 @@ def run_ours(args):
     # ---- device-resident timing ------------------------------------------------------------------------------
     with ClockSampler(local, enabled=(rank == 0)) as clocks:      # started before the warm-up, read from the timed region on
         for i in range(args.warmup):
+            if i > 0:
+                prefetch(dev_batches[i + 1] if i + 1 < args.warmup else dev_batches[0])
             step(*dev_batches[i], count_rays=False)
         barrier()
         launches0 = int(lib.nefii_launch_count())
@@ -313,11 +329,17 @@ def run_ours(args):
     ray_count.zero_()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nxt = [t.to(dev, non_blocking=True) for t in pinned[args.warmup]]
+    prefetch(nxt)
+    barrier()
     e0.record()
     for i in range(args.warmup, n_steps):
-        uv, obj, rgb = [t.to(dev, non_blocking=True) for t in pinned[i]]
+        uv, obj, rgb = nxt
+        nxt = [t.to(dev, non_blocking=True) for t in pinned[i + 1 if i + 1 < n_steps else args.warmup]]     # H2D of the next batch
+        prefetch(nxt)
         loss = step(uv, obj, rgb)
         _ = loss.item()
+    model.prefetch_join()
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -374,6 +396,9 @@ def run_ours(args):
                                    "131072 primary rays + 3 secondary rays per hit, its 512 2x2 patches dealt to the ranks (patch p -> "
                                    "rank p %% N), 128 SGs, 8x512 SDF MLP frozen, fwd+loss+bwd+Adam",
                        "rays_per_step": rays / args.steps, "primary_rays_per_step": NUM_PIXELS * NUM_RAYS,
+                       "pipelining": ("the primary trace of batch i+1 runs on a side stream next to the step of batch i (frozen geometry: "
+                                      "identical results); every trace is inside the timed region, the side stream is joined before the "
+                                      "closing event") if PREFETCH else "none (steps strictly one after the other)",
                        "scene": "geometric-init sphere perturbed into a bumpy blob (bumps %.2f), camera at distance 3, ~50 %% hits" % SCENE_BUMPS,
                        "l2": "per-step working set (MLP activations, several GB) >> 126 MB L2; a different pixel batch every step",
                        "parallelism": "dp%d (patches dealt to the ranks, one flat NCCL all-reduce of 3.2M grads)" % world},

@@ -115,6 +115,11 @@ int nefii_gemm_set_debug(int mask);
 /* programmatic dependent launch of the layer GEMMs (a launch's prologue overlaps the tail of the previous kernel in the stream;
  * default on, NEFII_GEMM_PDL=0 switches it off at load) */
 int nefii_gemm_set_pdl(int on);
+/* upper bound on the persistent grid (SMs) of the layer-GEMM launches that follow, 0 = every SM (default).  For a caller that runs
+ * a bulk evaluation on one stream next to a latency-bound chain on another (IDRNetwork.prefetch_trace: the primary trace of the next
+ * batch beside the shading of this one; the reference runs them back to back, implicit_differentiable_renderer.py:343-349): persistent
+ * CTAs keep their SM for the whole kernel, the bound leaves the other stream SMs to start on.  Part of the trace-graph cache key. */
+int nefii_gemm_set_grid_cap(int sms);
 /* accuracy / overlap knob of the layer GEMM: 64-wide K blocks accumulated inside TMEM before the partial sum moves to the fp32
  * register accumulators (1 = most accurate; default 4, NEFII_GEMM_KFLUSH sets the default at load) */
 int nefii_gemm_set_k_flush(int k_blocks);

@@ -29,6 +29,7 @@ SIGNATURES = {
     "nefii_gemm_set_cluster": [c_int],
     "nefii_gemm_set_debug": [c_int],
     "nefii_gemm_set_pdl": [c_int],
+    "nefii_gemm_set_grid_cap": [c_int],
     "nefii_gemm_set_k_flush": [c_int],
     "nefii_gemm_set_k_flush_head": [c_int],
     "nefii_gemm_set_trunc_comp": [c_int, c_float],

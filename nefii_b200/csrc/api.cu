@@ -264,6 +264,7 @@ int nefii_gemm_profile_enable(int on) { return nefii::gemm_profile_enable(on); }
 int nefii_gemm_set_cluster(int cl) { return nefii::gemm_set_cluster(cl); }
 int nefii_gemm_set_debug(int mask) { return nefii::gemm_set_debug(mask); }
 int nefii_gemm_set_pdl(int on) { return nefii::gemm_set_pdl(on); }
+int nefii_gemm_set_grid_cap(int sms) { return nefii::gemm_set_grid_cap(sms); }
 int nefii_gemm_set_k_flush(int k) { return nefii::gemm_set_k_flush(k); }
 int nefii_gemm_set_k_flush_head(int k) { return nefii::gemm_set_k_flush_head(k); }
 int nefii_gemm_set_trunc_comp(int k_blocks, float rho) { return nefii::gemm_set_trunc_comp(k_blocks, rho); }

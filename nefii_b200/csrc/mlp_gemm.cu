@@ -233,6 +233,18 @@ int device_sms() {
 
 int gemm_device_sms() { return device_sms(); }
 
+// Upper bound on the persistent grid of the launches that follow (0 = every SM).  A caller that runs a bulk evaluation next to a
+// latency-bound chain on another stream (IDRNetwork.prefetch_trace) leaves a few SMs to that chain: persistent CTAs hold their SM
+// for the whole kernel, so without the bound a 15 us kernel of the other stream waits for a ~1 ms bulk kernel to END.  Not part of
+// the configuration epoch (it is toggled around single calls); the trace-graph cache keys on it separately.
+int g_grid_cap = 0;
+int gemm_set_grid_cap(int sms) {
+  NEFII_CHECK_ARG(sms >= 0 && sms <= 4096, "gemm_set_grid_cap: SM count out of range");
+  g_grid_cap = sms;
+  return NEFII_OK;
+}
+int gemm_grid_cap() { return g_grid_cap; }
+
 int gemm_set_cluster(int cl) {
   NEFII_CHECK_ARG(cl == 1 || cl == 2, "gemm_set_cluster: 1 (single CTA) or 2 (cta_group::2 pair)");
   g_cluster_pref = cl;
@@ -343,7 +355,8 @@ int gemm_split_bf16(cudaStream_t stream, const GemmProblem& p) {
   int grid = ceil_div(m_tiles, cl) * cl;
   // few row tiles: room for the kernel's device-side split of the column chunks over clusters (see the kernel)
   if (n_chunks > 1 && !(p.epi.mode == 0 && p.epi.w_last != nullptr) && p.k_splits <= 1) grid *= n_chunks;
-  if (grid > n_sms) grid = n_sms / cl * cl;   // persistent CTAs: one per SM, looping over row tiles
+  const int grid_max = (g_grid_cap > 0 && g_grid_cap < n_sms) ? (g_grid_cap < cl ? cl : g_grid_cap) : n_sms;
+  if (grid > grid_max) grid = grid_max / cl * cl;   // persistent CTAs: one per SM, looping over row tiles
   GemmKernelFn fn = nullptr;
   const bool fuse = p.epi.mode == 0 && p.epi.w_last != nullptr;
   NEFII_CHECK_ARG(!fuse || (p.epi.dst_last != nullptr && p.epi.n_last >= 1), "gemm_split_bf16: fused output layer needs dst_last");

@@ -98,6 +98,9 @@ bool gemm_profile_active();
 int gemm_prepare_device();
 // SM count of the current device (after gemm_prepare_device)
 int gemm_device_sms();
+// upper bound on the persistent grid of the following launches (0 = every SM); NOT part of the epoch below
+int gemm_set_grid_cap(int sms);
+int gemm_grid_cap();
 // bumped by every setter above: anything that caches launches (trace graphs) keys on it
 long long gemm_config_epoch();
 

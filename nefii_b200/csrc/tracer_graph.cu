@@ -31,7 +31,7 @@ struct Key {
   const void *cam_loc, *ray_dirs, *object_mask, *linspace, *uniforms, *workspace, *points, *hit, *dists;
   size_t ws_bytes;
   long long gemm_epoch;
-  int march_flush, bulk_flush, quad_rows, bisect_depth;
+  int march_flush, bulk_flush, quad_rows, bisect_depth, grid_cap, pad_;
 };
 
 struct Entry {
@@ -165,6 +165,7 @@ int ray_trace(cudaStream_t stream, const TraceConfig& cfg, const SdfSource& src,
   key.gemm_epoch = gemm_config_epoch();
   const TraceTiers tiers = trace_tiers();
   key.march_flush = tiers.march_flush; key.bulk_flush = tiers.bulk_flush; key.quad_rows = trace_quad_rows(); key.bisect_depth = trace_bisect_depth();
+  key.grid_cap = gemm_grid_cap();
 
   std::lock_guard<std::mutex> lock(g_mu);
   Entry* found = nullptr;

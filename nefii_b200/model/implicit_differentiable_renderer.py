@@ -11,6 +11,8 @@ rendering, evaluation, and the same forward with a TRAINABLE geometry (`training
 :354-389: eikonal samples, d sdf/dx with a graph, SampleNetwork; a composition of twice-differentiable tcgen05 products).
 Everything device-side runs through the C ABI; there is no PyTorch fallback.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -371,6 +373,99 @@ class IDRNetwork(nn.Module):
         return self.forward_with_point(input)
 
     # ---- implicit_differentiable_renderer.py:312-501 ---------------------------------------------------
+    # ---- the primary trace of a forward (reference :335-352), factored out so that it can run ahead of time ---------------
+    def _primary_trace(self, uv, pose, intrinsics, object_mask, trace_uniforms, tracer, want_sdf):
+        """uv [B, n, 2], object_mask [B * n] -> ray_dirs [B, n, 3], cam_loc, points [B * n, 3], hit mask, dists, sdf_output | None"""
+        ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics)
+        batch_size, num_pixels, _ = ray_dirs.shape
+        sdf_output = None
+        with torch.no_grad():
+            points, network_object_mask, dists = tracer(sdf=self.implicit_network, cam_loc=cam_loc, object_mask=object_mask,
+                                                        ray_directions=ray_dirs, uniforms=trace_uniforms)
+            points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
+            if want_sdf:
+                sdf_all, _, _ = self.implicit_network.evaluate(points)
+                sdf_output = sdf_all.unsqueeze(-1)
+        return ray_dirs, cam_loc, points, network_object_mask, dists, sdf_output
+
+    # SMs the prefetched trace's bulk evaluations may occupy (the rest stay free for the latency-bound chain of the current
+    # forward / backward on the caller's stream); NEFII_PREFETCH_SMS overrides
+    PREFETCH_SMS = int(os.environ.get("NEFII_PREFETCH_SMS", "120"))
+
+    @staticmethod
+    def _prefetch_key(input):
+        return tuple((input[k].data_ptr(), input[k]._version, tuple(input[k].shape)) for k in ("uv", "pose", "intrinsics", "object_mask"))
+
+    def prefetch_trace(self, input):
+        """nefii_b200 extension: start the primary trace of a LATER ``forward(input)`` now, on a side stream, next to whatever the
+        caller's stream is doing (the shading, backward and optimizer step of the current batch).  With a frozen geometry (step 2,
+        rendering) the trace of batch i + 1 does not depend on the parameter update of batch i, so the result is the one that
+        forward would compute itself -- same kernels, same inputs -- and ``forward`` picks it up when it is called with the same
+        input tensors.  Returns False (and does nothing) when the geometry is trainable.  The reference runs the two back to back
+        (implicit_differentiable_renderer.py:343-349); at small per-GPU batches the trace is a chain of latency-bound rounds that
+        leaves most of the GPU idle."""
+        if self.training and not self.state_freeze_geo and torch.is_grad_enabled():
+            return False
+        uv, pose, intrinsics = input["uv"], input["pose"], input["intrinsics"]
+        if pose.requires_grad or intrinsics.requires_grad or not uv.is_cuda:
+            return False
+        object_mask = input["object_mask"].reshape(-1)
+        if len(uv.shape) == 4:
+            B, S, R, D = uv.shape
+            uv = uv.reshape(B, S * R, D)
+            object_mask = object_mask.reshape(B, S, 1).expand(B, S, R).reshape(-1)
+        dev = uv.device
+        st = self.__dict__.setdefault("_prefetch_state", {})
+        if st.get("device") != dev:
+            rt = self.ray_tracer
+            tracer = RayTracing(rt.object_bounding_sphere, rt.sdf_threshold, rt.line_search_step, rt.line_step_iters,
+                                rt.sphere_tracing_iters, rt.n_steps, rt.n_rootfind_steps)     # own buffers, workspace and graphs
+            st.clear()
+            st.update(device=dev, stream=torch.cuda.Stream(device=dev), tracer=tracer)
+        tracer, side = st["tracer"], st["stream"]
+        tracer.train(self.ray_tracer.training)
+        tracer.skip_min_sdf = self.ray_tracer.skip_min_sdf
+        main = torch.cuda.current_stream(dev)
+        side.wait_stream(main)                 # the inputs (and the weights) are ready where the caller's stream stands now
+        lib = _lib.raw()
+        _lib.check(lib.nefii_gemm_set_grid_cap(self.PREFETCH_SMS))
+        try:
+            with torch.cuda.stream(side), torch.no_grad():
+                res = self._primary_trace(uv, pose, intrinsics, object_mask, None, tracer, True)
+                done = torch.cuda.Event()
+                done.record(side)
+        finally:
+            _lib.check(lib.nefii_gemm_set_grid_cap(0))
+        # two slots: a pipelined loop starts the trace of batch i + 1 BEFORE it calls forward on batch i
+        pending = st.setdefault("pending", {})
+        pending[self._prefetch_key(input)] = (done, res, tracer.training, (uv, pose, intrinsics, object_mask))
+        while len(pending) > 2:
+            pending.pop(next(iter(pending)))
+        return True
+
+    def prefetch_join(self):
+        """Make the current stream wait for a prefetched trace that nobody picked up (end of a timed loop)."""
+        st = self.__dict__.get("_prefetch_state")
+        for done, _res, _mode, _keep in (st or {}).get("pending", {}).values():
+            torch.cuda.current_stream(st["device"]).wait_event(done)
+
+    def _take_prefetched(self, input):
+        st = self.__dict__.get("_prefetch_state")
+        if not st or not st.get("pending"):
+            return None
+        got = st["pending"].pop(self._prefetch_key(input), None)
+        if got is None:
+            return None
+        done, res, mode, _keep = got
+        if mode != self.ray_tracer.training:
+            return None
+        main = torch.cuda.current_stream(st["device"])
+        main.wait_event(done)
+        for t in res:
+            if t is not None:
+                t.record_stream(main)          # allocated on the side stream, consumed (and freed) on this one
+        return res
+
     def forward_with_uv(self, input, uniforms=None, trace_uniforms=None, eikonal_points=None):
         """uniforms / trace_uniforms / eikonal_points: optional injected random numbers (parity tests); by default they are
         drawn like the reference draws them."""
@@ -384,20 +479,16 @@ class IDRNetwork(nn.Module):
             B, S, R, D = uv.shape
             uv = uv.reshape(B, S * R, D)
             object_mask = object_mask.reshape(B, S, 1).expand(B, S, R).reshape(-1)
-        ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics)
-        batch_size, num_pixels, _ = ray_dirs.shape
-
         if pose.requires_grad or intrinsics.requires_grad:
             raise _lib.NefiiError("nefii_b200: camera parameters that require grad (--train_cameras) are outside the "
                                   "accelerated path: surface points are computed without a graph")
-        with torch.no_grad():
-            points, network_object_mask, dists = self.ray_tracer(sdf=self.implicit_network, cam_loc=cam_loc,
-                                                                 object_mask=object_mask, ray_directions=ray_dirs,
-                                                                 uniforms=trace_uniforms)
-            points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
-            if not unfrozen:
-                sdf_all, _, _ = self.implicit_network.evaluate(points)
-                sdf_output = sdf_all.unsqueeze(-1)
+        pre = self._take_prefetched(input) if (trace_uniforms is None and not unfrozen) else None
+        if pre is not None:
+            ray_dirs, cam_loc, points, network_object_mask, dists, sdf_output = pre
+        else:
+            ray_dirs, cam_loc, points, network_object_mask, dists, sdf_output = self._primary_trace(
+                uv, pose, intrinsics, object_mask, trace_uniforms, self.ray_tracer, not unfrozen)
+        batch_size, num_pixels, _ = ray_dirs.shape
         if unfrozen:      # the mask loss reaches the geometry through sdf_output (:354): fused trainable stack
             sdf_output = self.implicit_network._forward_trainable(points)[:, 0:1]
         ray_dirs = ray_dirs.reshape(-1, 3)

@@ -163,10 +163,15 @@ class SdfMlp:
 
     def workspace(self, rows_cap, with_grad):
         need = int(_lib.raw().nefii_sdf_workspace_bytes(self._h, int(rows_cap), 1 if with_grad else 0))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._ws
+        # one workspace per stream: evaluations enqueued on different streams (IDRNetwork.prefetch_trace) may overlap
+        sid = torch.cuda.current_stream(self.device).cuda_stream
+        if self._ws is None:
+            self._ws = {}
+        ws = self._ws.get(sid)
+        if ws is None or ws.numel() < need:
+            self._ws.pop(sid, None)
+            ws = self._ws[sid] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return ws
 
     def eval(self, x, want_feat=False, want_grad=False, count=None, k_flush=0):
         """x [N,3] -> (sdf [N], feat [N,width] | None, grad [N,3] | None).  k_flush: accuracy tier (1 = most accurate,

@@ -304,3 +304,35 @@ def test_runner_toggles_roughness_warmup_and_load_light(cuda_device, tmp_path):
     dirs, _ = rend_util.get_camera_params(inp['uv'], inp['pose'], inp['intrinsics'])
     bg = sg.background_sg(torch.from_numpy(sunrise).to(dev), dirs.reshape(-1, 3)[~hit])
     assert torch.allclose(lit['sg_rgb_values'][~hit], bg, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("training,rays", [(False, 0), (True, 4)])
+def test_prefetched_trace_is_bit_identical(cuda_device, training, rays):
+    """IDRNetwork.prefetch_trace: the primary trace of a later forward, run ahead on a side stream (bounded grid) while the
+    caller's stream does other work, is the one forward computes itself -- every output bit-identical; a forward on other
+    inputs in between does not pick it up."""
+    dev = cuda_device
+    net, _ = _build(dev)
+    net.train(training)
+    inp, U, _ = _inputs(dev, 32, rays, seed=3)
+    inp2, U2, _ = _inputs(dev, 24, rays, seed=4)
+    with torch.no_grad():
+        torch.manual_seed(11)
+        ref = net.forward_with_uv(inp, uniforms=U)
+        torch.manual_seed(11)
+        assert net.prefetch_trace(inp)
+        other = net.forward_with_uv(inp2, uniforms=U2)          # the caller's stream is busy with another batch meanwhile
+        assert len(net._prefetch_state["pending"]) == 1
+        got = net.forward_with_uv(inp, uniforms=U)
+        assert len(net._prefetch_state["pending"]) == 0
+    assert other['points'].shape[0] == inp2['uv'].shape[1]
+    assert int(ref['network_object_mask'].sum()) > 100
+    for k in KEYS + ['network_object_mask', 'object_mask', 'secondary_points', 'secondary_mask', 'secondary_dir']:
+        if ref[k] is None:
+            assert got[k] is None
+            continue
+        assert torch.equal(got[k], ref[k]), k
+    # a trainable geometry: the trace would depend on the parameter update before it -- refused
+    net.train(True)
+    net.unfreeze_geometry()
+    assert net.prefetch_trace(inp) is False

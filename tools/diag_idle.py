@@ -55,6 +55,25 @@ def main():
             else:
                 cur_e = max(cur_e, t)
         union += (cur_e - cur_s) if cur_e is not None else 0
+        # where the device waits: the largest gaps between consecutive device activities, and the gap time by what follows
+        named = sorted(((ev.time_range.start, ev.time_range.end, ev.name) for ev in evs), key=lambda x: x[0])
+        gaps, end, last = [], None, ""
+        for s, t, name in named:
+            if end is not None and s > end:
+                gaps.append((s - end, last, name))
+            if end is None or t > end:
+                end, last = t, name
+        tot = sum(g[0] for g in gaps) / 3 / 1000.0
+        big = sum(g[0] for g in gaps if g[0] > 20) / 3 / 1000.0
+        print("px %d: gaps %.2f ms per step in %d gaps (%.2f ms in gaps > 20 us)" % (n_px, tot, len(gaps) // 3, big))
+        by_next = {}
+        for g, a_, b_ in gaps:
+            k = b_[:60]
+            by_next[k] = by_next.get(k, 0.0) + g
+        for k, v in sorted(by_next.items(), key=lambda kv: -kv[1])[:14]:
+            print("    wait before %-60s %.3f ms per step" % (k, v / 3 / 1000.0))
+        for g, a_, b_ in sorted(gaps, key=lambda x: -x[0])[:12]:
+            print("    gap %7.1f us  after %-44s before %s" % (g, a_[:44], b_[:44]))
         print("px %d: step %.2f ms (events) | %d device activities per step, summed %.2f ms, union of intervals %.2f ms per step" % (
             n_px, wall, len(evs) // 3, busy, union / 3 / 1000.0))
 
