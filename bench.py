@@ -45,9 +45,10 @@ sys.path.insert(0, ROOT)
 METRIC = "shaded rays/sec (primary+indirect, fwd+bwd)"
 NUM_PIXELS, NUM_RAYS, NUM_SGS, IMG = int(os.environ.get("NEFII_BENCH_PIXELS", 2048)), 64, 128, 800      # env: diagnostics only
 SDF_FLOPS_PER_POINT = 3.671e6      # 1,835,520 MAC forward
-# the primary trace of batch i + 1 enqueued on a side stream next to the step of batch i (IDRNetwork.prefetch_trace); 0 = the steps
-# run strictly one after the other (round 2's numbers up to trip T)
-PREFETCH = int(os.environ.get("NEFII_BENCH_PREFETCH", "1"))
+# 1: the primary trace of batch i + 1 is enqueued on a side stream next to the step of batch i (IDRNetwork.prefetch_trace, bit-identical
+# results).  Measured (profiles/r2_small_step.md): the trace is not as idle as its launch train suggests -- 20.1 ms alone + 11.1 ms for
+# the rest of a 16 384-ray step, 27.3 - 30.2 ms pipelined against 29.6 - 29.7 ms back to back -- so the default stays the reference's order.
+PREFETCH = int(os.environ.get("NEFII_BENCH_PREFETCH", "0"))
 SCENE_BUMPS = 0.08                 # perturbation of the geometric-init sphere (the parity tests' rough scene)
 SG_FLOPS_PER_RAY, SG_BYTES_PER_RAY = 35.0e3, 72.0      # render_with_sg at M = 128, K = 1 (algorithmic)
 
