@@ -98,6 +98,7 @@ class _TraceBuffers:
         self.points = torch.empty(n, 3, device=dev, dtype=torch.float32)
         self.hit = torch.empty(n, device=dev, dtype=torch.uint8)
         self.dists = torch.empty(n, device=dev, dtype=torch.float32)
+        self.missing_from = n_batch      # rows [missing_from:] hold the padding rays of RayTracing._fill_missing_rays (none yet)
 
 
 class RayTracing(nn.Module):
@@ -151,11 +152,19 @@ class RayTracing(nn.Module):
         return b
 
     def _fill_missing_rays(self, bufs, batch_size, n_rays, dev):
-        """rays [batch_size:] of a bucket start far outside the bounding sphere and point away from it"""
+        """rays [batch_size:] of a bucket start far outside the bounding sphere and point away from it.  Written with fills (a
+        `torch.tensor([...], device=dev)` is a synchronous host-to-device copy: it drained the stream in the middle of every forward),
+        and only where the previous call left real rays: rows [bufs.missing_from:] already hold missing rays."""
         far = 4.0 * float(self.object_bounding_sphere) + 1.0
-        bufs.cam[batch_size:] = torch.tensor([0.0, 0.0, far], device=dev)
-        bufs.dirs[batch_size:] = torch.tensor([0.0, 1.0, 0.0], device=dev)
-        bufs.obj[n_rays:].zero_()
+        end = min(bufs.missing_from, bufs.cam.shape[0])
+        if batch_size < end:
+            cam, dirs = bufs.cam[batch_size:end], bufs.dirs[batch_size:end]
+            cam.zero_()
+            cam[:, 2].fill_(far)
+            dirs.zero_()
+            dirs[:, :, 1].fill_(1.0)
+            bufs.obj[n_rays:end * bufs.dirs.shape[1]].zero_()
+        bufs.missing_from = batch_size
 
     def _launch(self, bufs, kind, ptr, n_prims, cap_batch, num_pixels, have_mask, flags, have_uniforms, dev, stats):
         key = (self.n_steps, dev)
@@ -188,8 +197,8 @@ class RayTracing(nn.Module):
         bufs = self._shape_buffers(dev, cap_batch, num_pixels)
         bufs.cam[:batch_size].copy_(cam_loc.detach().reshape(batch_size, 3))
         bufs.dirs[:batch_size].copy_(ray_directions.detach())
-        if cap_batch > batch_size:
-            self._fill_missing_rays(bufs, batch_size, n_rays, dev)
+        if bucketed:
+            self._fill_missing_rays(bufs, batch_size, n_rays, dev)      # (also keeps bufs.missing_from current when nothing is padded)
         have_mask = object_mask is not None
         if have_mask:
             bufs.obj[:n_rays].copy_(object_mask.reshape(-1))
