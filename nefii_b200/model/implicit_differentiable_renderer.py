@@ -117,6 +117,14 @@ class ImplicitNetwork(nn.Module):
             self._packed_versions = versions
         return self._sdf_mlp
 
+    # copy.deepcopy / pickling of the module (EMA copies, torch.save(model)): the native handle and its packed weights belong to
+    # THIS object (a copied raw pointer would be freed twice); the copy rebuilds them on first use
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_sdf_mlp"] = None
+        state["_packed_versions"] = None
+        return state
+
     def nefii_sdf_source(self):
         dev = next(self.parameters()).device
         net = self._sync(dev)
@@ -371,6 +379,11 @@ class IDRNetwork(nn.Module):
         if not with_point:
             return self.forward_with_uv(input)
         return self.forward_with_point(input)
+
+    def __getstate__(self):       # the side stream / pending traces of prefetch_trace stay with this object
+        state = dict(self.__dict__)
+        state.pop("_prefetch_state", None)
+        return state
 
     # ---- implicit_differentiable_renderer.py:312-501 ---------------------------------------------------
     # ---- the primary trace of a forward (reference :335-352), factored out so that it can run ahead of time ---------------

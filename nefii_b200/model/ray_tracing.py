@@ -137,6 +137,11 @@ class RayTracing(nn.Module):
         self._linspace = {}
         self._shape_bufs = {}
 
+    def __getstate__(self):       # device buffers whose raw pointers key the C side's graph cache are not copied / pickled
+        state = dict(self.__dict__)
+        state.update(_ws=None, _linspace={}, _shape_bufs={}, last_stats=None)
+        return state
+
     def _config(self):
         return TraceConfig(self.object_bounding_sphere, self.sdf_threshold, self.line_search_step, self.line_step_iters,
                            self.sphere_tracing_iters, self.n_steps, self.n_rootfind_steps)

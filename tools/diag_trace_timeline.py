@@ -38,8 +38,28 @@ def main():
     trace(batches[0])
     print("stats:", model.ray_tracer.last_stats)
     model.ray_tracer.collect_stats = False
+    whole_step = os.environ.get("PHASE", "trace") == "step"
+    if whole_step:
+        flat = bench.FlatGrads(model.parameters())
+        opt_idr = torch.optim.Adam([p for p in model.rendering_network.parameters() if p.requires_grad], lr=5e-4)
+        opt_sg = torch.optim.Adam([p for p in model.envmap_material_network.parameters() if p.requires_grad], lr=5e-4)
+
+        def step(b):
+            flat.zero()
+            out = model({'uv': b[0], 'object_mask': b[1], 'pose': pose, 'intrinsics': K})
+            loss = bench.idr_loss(out, b[2])
+            loss.backward()
+            opt_idr.step()
+            opt_sg.step()
+        for b in batches:
+            step(b)
+        torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        trace(batches[0])
+        if whole_step:
+            step(batches[0])
+            step(batches[1])
+        else:
+            trace(batches[0])
         torch.cuda.synchronize()
     evs = sorted(((ev.time_range.start, ev.time_range.end, ev.name) for ev in prof.events()
                   if ev.device_type == torch.autograd.DeviceType.CUDA), key=lambda x: x[0])
@@ -48,6 +68,8 @@ def main():
     for s, t, name in evs:
         short = name.split("::")[-1].split("(")[0].split("<")[0]
         kind = "eval" if ("gemm_split" in name or "encode_kernel" in name) else short
+        if whole_step and kind != "eval":
+            kind = "nefii-other" if "nefii" in name else "torch"
         if groups and groups[-1]["kind"] == kind and not (kind == "eval" and "encode_kernel" in name):
             g = groups[-1]
             g["end"] = max(g["end"], t); g["busy"] += t - s; g["n"] += 1
