@@ -45,7 +45,8 @@ sys.path.insert(0, ROOT)
 METRIC = "shaded rays/sec (primary+indirect, fwd+bwd)"
 NUM_PIXELS, NUM_RAYS, NUM_SGS, IMG = int(os.environ.get("NEFII_BENCH_PIXELS", 2048)), 64, 128, 800      # env: diagnostics only
 SDF_FLOPS_PER_POINT = 3.671e6      # 1,835,520 MAC forward
-# 1: the primary trace of batch i + 1 is enqueued on a side stream next to the step of batch i (IDRNetwork.prefetch_trace, bit-identical
+# 1 / 2: the primary trace of batch i + 1 is enqueued on a side stream next to the whole step of batch i (1) or next to its loss /
+# backward / optimizer part (2) (IDRNetwork.prefetch_trace, bit-identical
 # results).  Measured (profiles/r2_small_step.md): the trace is not as idle as its launch train suggests -- 20.1 ms alone + 11.1 ms for
 # the rest of a 16 384-ray step, 27.3 - 30.2 ms pipelined against 29.6 - 29.7 ms back to back -- so the default stays the reference's order.
 PREFETCH = int(os.environ.get("NEFII_BENCH_PREFETCH", "0"))
@@ -257,10 +258,12 @@ def run_ours(args):
     dev_batches = [[t.to(dev) for t in b] for b in host_batches]
     ray_count = torch.zeros(1, device=dev, dtype=torch.float64)
 
-    def step(uv, obj, rgb, count_rays=True, net=None):
+    def step(uv, obj, rgb, count_rays=True, net=None, nxt=None):
         net = net or model
         flat.zero()
         out = net({'uv': uv, 'object_mask': obj, 'pose': pose, 'intrinsics': K})
+        if nxt is not None and PREFETCH == 2:      # next batch's primary trace next to this batch's loss / backward / optimizer
+            model.prefetch_trace({'uv': nxt[0], 'object_mask': nxt[1], 'pose': pose, 'intrinsics': K})
         loss = idr_loss(out, rgb)
         loss.backward()
         flat.all_reduce(world)
@@ -288,24 +291,24 @@ def run_ours(args):
         import torch.distributed as dist
         return reduce_ranks(x, dist.ReduceOp.MAX) if world > 1 else x
 
-    def prefetch(bt):
+    def prefetch(bt, first=False):
         """Software pipelining across steps (geometry frozen: the trace of a batch does not depend on the parameter update before
         it): the primary trace of the NEXT batch is enqueued on a side stream before this batch's step.  Every trace still runs
         inside the timed region -- the loop below starts one per step (the last step's wraps around to the first batch) and joins
         the side stream before the closing event; the first step consumes the one the warm-up started."""
-        if PREFETCH:
+        if PREFETCH == 1 or (PREFETCH == 2 and first):
             model.prefetch_trace({'uv': bt[0], 'object_mask': bt[1], 'pose': pose, 'intrinsics': K})
 
     def timed_steps(batches, count=True):
         """W warm-up steps were done by the caller; EXACTLY len(batches) steps between barrier + synchronize, device-timed"""
         ray_count.zero_()
-        prefetch(batches[0])
+        prefetch(batches[0], first=True)
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i, bt in enumerate(batches):
             prefetch(batches[(i + 1) % len(batches)])
-            step(*bt, count_rays=count)
+            step(*bt, count_rays=count, nxt=batches[(i + 1) % len(batches)])
         model.prefetch_join()
         b.record()
         barrier()
@@ -331,14 +334,14 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nxt = [t.to(dev, non_blocking=True) for t in pinned[args.warmup]]
-    prefetch(nxt)
+    prefetch(nxt, first=True)
     barrier()
     e0.record()
     for i in range(args.warmup, n_steps):
         uv, obj, rgb = nxt
         nxt = [t.to(dev, non_blocking=True) for t in pinned[i + 1 if i + 1 < n_steps else args.warmup]]     # H2D of the next batch
         prefetch(nxt)
-        loss = step(uv, obj, rgb)
+        loss = step(uv, obj, rgb, nxt=nxt)
         _ = loss.item()
     model.prefetch_join()
     e1.record()
