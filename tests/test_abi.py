@@ -69,3 +69,33 @@ def test_argument_errors_return_codes_not_crashes():
     assert lib.nefii_sg_render_fwd(null, 0, 128, 1, null, null, null, null, null, null, null, null, null, null) == 0
     assert lib.nefii_idr_loss_bwd(null, 0, 4, null, null, null, null, null, null, null, 0, 1, ctypes.c_float(50.0), null, null,
                                   null, null, null, null) == 0
+
+
+def test_ctypes_struct_mirrors_match_the_header_layout(tmp_path):
+    """Every descriptor struct of include/nefii_b200.h against its ctypes mirror: size and the offset of every field, as gcc lays
+    the header out (a drifted field order would silently mis-read pointers)."""
+    import subprocess
+    from nefii_b200 import mlp, ops
+    from nefii_b200.model import ray_tracing
+    mirrors = {"nefii_gemm_desc": ops.GemmDesc, "nefii_sdf_config": ops.SdfConfig, "nefii_trace_config": ray_tracing.TraceConfig,
+               "nefii_dense_stack_desc": mlp.DenseStackDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include <stdint.h>', '#include "%s"' % os.path.join(ROOT, "include", "nefii_b200.h"),
+             'int main(void) {']
+    for cname, mirror in mirrors.items():
+        lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in mirror._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for row in filter(None, out):
+        cname, field, value = row.split()
+        mirror = mirrors[cname]
+        want = ctypes.sizeof(mirror) if field == "sizeof" else getattr(mirror, field).offset
+        assert int(value) == want, (cname, field, int(value), want)
+        seen += 1
+    assert seen == sum(len(m._fields_) + 1 for m in mirrors.values())
